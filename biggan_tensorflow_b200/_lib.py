@@ -1,0 +1,107 @@
+"""ctypes binding of libbiggan_b200.so (the C ABI declared in include/biggan_b200.h).
+
+The argument types are parsed from the header itself, so the Python side can never drift from the
+ABI.  There is NO CPU fallback: if the shared library is missing this module raises at import.
+"""
+import ctypes
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_HEADER = os.path.join(os.path.dirname(_PKG), "include", "biggan_b200.h")
+_SO = os.path.join(_PKG, "libbiggan_b200.so")
+
+BG_F32, BG_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+PAD_ZERO, PAD_REFLECT = 0, 1
+
+
+class ConvDesc(ctypes.Structure):
+    """mirror of bg_conv_desc"""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("B", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "kh", "kw", "stride",
+                 "pad_t", "pad_l", "pad_b", "pad_r", "pad_mode", "transposed")]
+
+
+_CTYPES = {
+    "int": ctypes.c_int, "long": ctypes.c_long, "size_t": ctypes.c_size_t,
+    "float": ctypes.c_float, "double": ctypes.c_double,
+}
+
+
+def parse_header(path=_HEADER):
+    """-> {name: (restype, [argtypes])} for every function declared in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    src = re.sub(r"#[^\n]*", "", src)
+    src = re.sub(r"typedef\s+(enum|struct)\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"(const\s+char\s*\*|size_t|int)\s+(bg_\w+)\s*\(([^)]*)\)\s*;", src, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        if ret.startswith("const"):
+            restype = ctypes.c_char_p
+        elif ret == "size_t":
+            restype = ctypes.c_size_t
+        else:
+            restype = ctypes.c_int
+        argtypes = []
+        args = args.strip()
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    toks = [t for t in a.split() if t != "const"]
+                    argtypes.append(_CTYPES[toks[0]])
+        decls[name] = (restype, argtypes)
+    return decls
+
+
+DECLS = parse_header()
+
+if not os.path.exists(_SO):
+    raise RuntimeError(
+        "libbiggan_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C biggan_tensorflow_b200/csrc`.  There is no CPU fallback." % _SO)
+
+lib = ctypes.CDLL(_SO)
+for _name, (_res, _args) in DECLS.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+launch_count = 0   # kernels-launching C calls issued (bench.py reports it as gpu_launches)
+
+
+class BgError(RuntimeError):
+    pass
+
+
+def _conv(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    if isinstance(a, ctypes.Structure):
+        return ctypes.addressof(a)
+    return a
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point; raise with bg_last_error() on failure."""
+    global launch_count
+    fn = getattr(lib, name)
+    rc = fn(*[_conv(a) for a in args])
+    launch_count += 1
+    if rc != 0:
+        msg = lib.bg_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise ValueError("%s: %s" % (name, msg))
+        raise BgError("%s failed (%d): %s" % (name, rc, msg))
+
+
+def query(name, *args):
+    """Invoke a value-returning entry point (workspace sizes etc.)."""
+    return getattr(lib, name)(*[_conv(a) for a in args])

@@ -1,0 +1,470 @@
+// SIMT (CUDA-core, fp32 accumulate) gather-GEMM kernels: the fp32 parity-mode implementation of
+// conv / conv2d_transpose / their dgrad + wgrad (ops.py:49-139), and the fallback for shapes the
+// tcgen05 path does not take (Cin = 3, Cout = 3, ...).  Same geometry abstraction as conv_tc.cu.
+#include "bg_common.cuh"
+
+#define GF_BM 128
+#define GF_BN 64
+#define GF_BK 16
+
+__device__ __forceinline__ float bg_apply_act(float v, int act) {
+  if (act == BG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == BG_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward-type: out[b, oy, ox, n] = act( sum_t sum_k in[b, iy_t, ix_t, k] * w[t, k, n] + bias + res )
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_gemm_fwd_kernel(const __grid_constant__ BgGeom g, const T* __restrict__ in,
+                       const T* __restrict__ w, const float* __restrict__ bias,
+                       const T* residual, T* out, int act, int tiles_per_phase) {
+  __shared__ float As[GF_BK][GF_BM + 4];
+  __shared__ float Bs[GF_BK][GF_BN + 4];
+  const int tid = threadIdx.x;
+  const int phase = blockIdx.x / tiles_per_phase;
+  const int mt = blockIdx.x % tiles_per_phase;
+  const int n0 = blockIdx.y * GF_BN;
+  const BgPhase& ph = g.ph[phase];
+  const int HWp = ph.Hp * ph.Wp;
+  const int Mph = g.B * HWp;
+  if (mt * GF_BM >= Mph) return;
+
+  // A-load role: pixel pa, 8 consecutive k
+  const int pa = tid >> 1, ka = (tid & 1) * 8;
+  const int ma = mt * GF_BM + pa;
+  const bool mvalid = ma < Mph;
+  int ab = 0, ai = 0, aj = 0;
+  if (mvalid) { ab = ma / HWp; int r = ma - ab * HWp; ai = r / ph.Wp; aj = r - ai * ph.Wp; }
+  const bool vecA = (g.Ci % 4 == 0);
+  // B-load role
+  const bool n_contig = (g.wn == 1);
+  int kb, nb;
+  if (n_contig) { kb = tid >> 4; nb = (tid & 15) * 4; } else { nb = tid >> 2; kb = (tid & 3) * 4; }
+
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < ph.ntaps; ++t) {
+    const BgTap tap = ph.taps[t];
+    int iy = ai * g.istep + tap.dy, ix = aj * g.istep + tap.dx;
+    bool ok = mvalid;
+    if (g.pad_mode == BG_PAD_REFLECT) {
+      if (iy < 0) iy = -iy;
+      if (iy >= g.Hi) iy = 2 * (g.Hi - 1) - iy;
+      if (ix < 0) ix = -ix;
+      if (ix >= g.Wi) ix = 2 * (g.Wi - 1) - ix;
+    }
+    ok = ok && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+    const long abase = (((long)ab * g.Hi + iy) * g.Wi + ix) * g.Ci;
+    const T* wt = w + (long)tap.widx * g.wtap;
+    for (int k0 = 0; k0 < g.Ci; k0 += GF_BK) {
+      float ra[8], rb[4];
+      if (vecA) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int k = k0 + ka + h * 4;
+          f4 v = {0.f, 0.f, 0.f, 0.f};
+          if (ok && k < g.Ci) v = bg_ld4(in, abase + k);
+          ra[h * 4 + 0] = v.x; ra[h * 4 + 1] = v.y; ra[h * 4 + 2] = v.z; ra[h * 4 + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int k = k0 + ka + e;
+          ra[e] = (ok && k < g.Ci) ? bg_ld(in, abase + k) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int k = k0 + kb + (n_contig ? 0 : e);
+        int n = n0 + nb + (n_contig ? e : 0);
+        rb[e] = (k < g.Ci && n < g.Co) ? bg_ld(wt, (long)k * g.wk + (long)n * g.wn) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) As[ka + e][pa] = ra[e];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (n_contig) Bs[kb][nb + e] = rb[e]; else Bs[kb + e][nb] = rb[e];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < GF_BK; ++kk) {
+        float a[8], b[4];
+        float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = mt * GF_BM + ty * 8 + i;
+    if (m >= Mph) continue;
+    const int b = m / HWp; const int r = m - b * HWp; const int pi = r / ph.Wp; const int pj = r - pi * ph.Wp;
+    const int oy = ph.oy0 + pi * g.ostep, ox = ph.ox0 + pj * g.ostep;
+    const long obase = (((long)b * g.Ho + oy) * g.Wo + ox) * g.Co;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.Co) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[n];
+      if (residual) v += bg_ld(residual, obase + n);
+      bg_st(out, obase + n, bg_apply_act(v, act));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad-type: dw[t, k, n] = sum_pixels in[b, iy_t, ix_t, k] * og[b, oy, ox, n]   (one phase)
+// partial results per split z go to part + z*zstride with the final (strided) dw layout.
+// ------------------------------------------------------------------------------------------------
+#define GW_BK 64
+#define GW_BN 64
+#define GW_BP 16
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_gemm_wgrad_kernel(const __grid_constant__ BgGeom g, const T* __restrict__ in,
+                         const T* __restrict__ og, float* part, long zstride, int nsplit, int ntile_n) {
+  __shared__ float As[GW_BP][GW_BK + 4];
+  __shared__ float Bs[GW_BP][GW_BN + 4];
+  const int tid = threadIdx.x;
+  const BgPhase& ph = g.ph[0];
+  const BgTap tap = ph.taps[blockIdx.y];
+  const int k0 = (blockIdx.x / ntile_n) * GW_BK, n0 = (blockIdx.x % ntile_n) * GW_BN;
+  const int HWp = ph.Hp * ph.Wp;
+  const int Mph = g.B * HWp;
+  const int chunk = (int)(((long)Mph + nsplit - 1) / nsplit);
+  const int mbeg = blockIdx.z * chunk;
+  const int mend = min(Mph, mbeg + chunk);
+
+  const int pl = tid >> 4, c4 = (tid & 15) * 4;     // load role: pixel row, 4 channels
+  const int tx = tid & 15, ty = tid >> 4;           // compute role: 4 n x 4 k
+  const bool vecA = (g.Ci % 4 == 0), vecB = (g.Co % 4 == 0);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int m0 = mbeg; m0 < mend; m0 += GW_BP) {
+    const int m = m0 + pl;
+    float ra[4] = {0.f, 0.f, 0.f, 0.f}, rb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < mend) {
+      const int b = m / HWp; const int r = m - b * HWp; const int pi = r / ph.Wp; const int pj = r - pi * ph.Wp;
+      int iy = pi * g.istep + tap.dy, ix = pj * g.istep + tap.dx;
+      if (g.pad_mode == BG_PAD_REFLECT) {
+        if (iy < 0) iy = -iy;
+        if (iy >= g.Hi) iy = 2 * (g.Hi - 1) - iy;
+        if (ix < 0) ix = -ix;
+        if (ix >= g.Wi) ix = 2 * (g.Wi - 1) - ix;
+      }
+      if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi) {
+        const long abase = (((long)b * g.Hi + iy) * g.Wi + ix) * g.Ci;
+        const int k = k0 + c4;
+        if (vecA) { if (k < g.Ci) { f4 v = bg_ld4(in, abase + k); ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; ra[3] = v.w; } }
+        else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (k + e < g.Ci) ra[e] = bg_ld(in, abase + k + e);
+        }
+      }
+      const int oy = ph.oy0 + pi * g.ostep, ox = ph.ox0 + pj * g.ostep;
+      const long obase = (((long)b * g.Ho + oy) * g.Wo + ox) * g.Co;
+      const int n = n0 + c4;
+      if (vecB) { if (n < g.Co) { f4 v = bg_ld4(og, obase + n); rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w; } }
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (n + e < g.Co) rb[e] = bg_ld(og, obase + n + e);
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[pl][c4]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    *reinterpret_cast<float4*>(&Bs[pl][c4]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < GW_BP; ++p) {
+      float4 a = *reinterpret_cast<const float4*>(&As[p][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[p][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  float* dst = part + (long)blockIdx.z * zstride + (long)tap.widx * g.wtap;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= g.Ci) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.Co) continue;
+      dst[(long)k * g.wk + (long)n * g.wn] = acc[i][j];
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, long n, long zstride, int nsplit) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float s = 0.f;
+    for (int z = 0; z < nsplit; ++z) s += part[(long)z * zstride + i];
+    dw[i] = s;
+  }
+}
+
+// adjoint of tf.pad(mode='REFLECT') (ops.py:82): fold the padded gradient back (+ residual)
+template <typename T>
+__global__ void reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, int H, int W, int C,
+                                    int pt, int pl, int pb, int pr) {
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  const long total = (long)B * H * W * C;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    const int c = (int)(idx % C); long r = idx / C;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H); const int b = (int)(r / H);
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = y + pt;
+    if (y >= 1 && y <= pt) ys[ny++] = pt - y;
+    if (y >= H - 1 - pb && y <= H - 2) ys[ny++] = 2 * (H - 1) - y + pt;
+    xs[nx++] = x + pl;
+    if (x >= 1 && x <= pl) xs[nx++] = pl - x;
+    if (x >= W - 1 - pr && x <= W - 2) xs[nx++] = 2 * (W - 1) - x + pl;
+    float s = residual ? bg_ld(residual, idx) : 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int e = 0; e < nx; ++e) s += bg_ld(dxp, (((long)b * Hp + ys[a]) * Wp + xs[e]) * C + c);
+    bg_st(dx, idx, s);
+  }
+}
+
+template <typename T>
+__global__ void reflect_pad_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C,
+                                   int pt, int pl, int pb, int pr) {
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  const long total = (long)B * Hp * Wp * C;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    const int c = (int)(idx % C); long r = idx / C;
+    const int xp = (int)(r % Wp); r /= Wp;
+    const int yp = (int)(r % Hp); const int b = (int)(r / Hp);
+    int iy = yp - pt, ix = xp - pl;
+    if (iy < 0) iy = -iy;
+    if (iy >= H) iy = 2 * (H - 1) - iy;
+    if (ix < 0) ix = -ix;
+    if (ix >= W) ix = 2 * (W - 1) - ix;
+    y[idx] = x[(((long)b * H + iy) * W + ix) * C + c];
+  }
+}
+
+// column sums of [rows, C] -> partial[chunk][C] -> out[C]   (bias gradient)
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, float* __restrict__ part, long rows, int C, long rows_per_chunk) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;
+  const long r0 = (long)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s = 0.f;
+  if (c < C) for (long r = r0 + ty; r < r1; r += 8) s += bg_ld(x, r * C + c);
+  __shared__ float sh[8][33];
+  sh[ty][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x & 31];
+    part[(long)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int nchunk, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int i = 0; i < nchunk; ++i) s += part[(long)i * C + c];
+  out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int bg_tc_conv_fwd_type(const BgGeom& g, const bg_conv_desc* d, int op, const void* in, const void* w_k_major,
+                        const float* bias, const void* residual, void* out, int act, cudaStream_t st, int* taken);
+int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw,
+                     void* ws, size_t ws_bytes, cudaStream_t st, int* taken);
+size_t bg_tc_conv_wgrad_ws(const BgGeom& g, const bg_conv_desc* d);
+
+template <typename T>
+static int launch_fwd_type(const BgGeom& g, const T* in, const T* w, const float* bias, const T* residual, T* out,
+                           int act, cudaStream_t st) {
+  long maxM = 0;
+  for (int p = 0; p < g.nphase; ++p) maxM = max(maxM, (long)g.B * g.ph[p].Hp * g.ph[p].Wp);
+  const int tiles = (int)bg_cdiv(maxM, GF_BM);
+  dim3 grid(tiles * g.nphase, (unsigned)bg_cdiv(g.Co, GF_BN));
+  gather_gemm_fwd_kernel<T><<<grid, 256, 0, st>>>(g, in, w, bias, residual, out, act, tiles);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const void* w_t, const float* bias,
+                             const void* residual, void* y, int act, int dtype, int force_simt, void* stream) {
+  BgGeom g;
+  int rc = bg_build_geom(d, BG_OP_FWD, &g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!force_simt && dtype == BG_BF16) {
+    // K-major B operand [tap][n][k]: transposed conv has it natively, plain conv needs w_t
+    const void* wk = d->transposed ? w : w_t;
+    if (wk) {
+      int taken = 0;
+      rc = bg_tc_conv_fwd_type(g, d, BG_OP_FWD, x, wk, bias, residual, y, act, st, &taken);
+      if (rc) return rc;
+      if (taken) return BG_OK;
+    }
+  }
+  BG_DISPATCH_DTYPE(dtype, T, return launch_fwd_type<T>(g, (const T*)x, (const T*)w, bias, (const T*)residual, (T*)y, act, st));
+}
+
+static bool dgrad_padded(const bg_conv_desc* d) {
+  return !d->transposed && d->pad_mode == BG_PAD_REFLECT && (d->pad_t | d->pad_b | d->pad_l | d->pad_r);
+}
+
+extern "C" size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype) {
+  if (!dgrad_padded(d)) return 0;
+  size_t es = dtype == BG_F32 ? 4 : 2;
+  return (size_t)d->B * (d->Hi + d->pad_t + d->pad_b) * (d->Wi + d->pad_l + d->pad_r) * d->Ci * es + 256;
+}
+
+extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void* w, const void* w_t, const void* residual,
+                               void* dx, int dtype, void* ws, size_t ws_bytes, int force_simt, void* stream) {
+  BgGeom g;
+  int rc = bg_build_geom(d, BG_OP_DGRAD, &g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool padded = dgrad_padded(d);
+  if (padded) BG_REQUIRE(ws && ws_bytes >= bg_conv2d_dgrad_workspace_bytes(d, dtype), BG_ERR_WORKSPACE, "dgrad workspace too small");
+  void* gout = padded ? ws : dx;
+  const void* gres = padded ? nullptr : residual;
+  bool done = false;
+  if (!force_simt && dtype == BG_BF16) {
+    const void* wk = d->transposed ? w_t : w;     // dgrad contracts over Co: HWIO [tap][ci][co] is K-major natively
+    if (wk) {
+      int taken = 0;
+      rc = bg_tc_conv_fwd_type(g, d, BG_OP_DGRAD, dy, wk, nullptr, gres, gout, BG_ACT_NONE, st, &taken);
+      if (rc) return rc;
+      done = taken != 0;
+    }
+  }
+  if (!done) {
+    BG_DISPATCH_DTYPE(dtype, T, rc = launch_fwd_type<T>(g, (const T*)dy, (const T*)w, nullptr, (const T*)gres, (T*)gout, BG_ACT_NONE, st));
+    if (rc) return rc;
+  }
+  if (padded) {
+    const long total = (long)d->B * d->Hi * d->Wi * d->Ci;
+    const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
+    BG_DISPATCH_DTYPE(dtype, T, reflect_fold_kernel<T><<<blocks, 256, 0, st>>>((const T*)ws, (const T*)residual, (T*)dx, d->B, d->Hi,
+                                                                            d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r));
+    BG_LAUNCH_CHECK();
+  }
+  return BG_OK;
+}
+
+static int wgrad_nsplit(const BgGeom& g) {
+  const BgPhase& ph = g.ph[0];
+  const long M = (long)g.B * ph.Hp * ph.Wp;
+  const long tiles = (long)ph.ntaps * bg_cdiv(g.Ci, GW_BK) * bg_cdiv(g.Co, GW_BN);
+  long ns = bg_cdiv(4L * bg_num_sms(), tiles);
+  ns = min(ns, bg_cdiv(M, 256));
+  ns = max(1L, min(ns, 64L));
+  return (int)ns;
+}
+
+static long wgrad_numel(const bg_conv_desc* d) { return (long)d->kh * d->kw * d->Ci * d->Co; }
+
+extern "C" size_t bg_conv2d_wgrad_workspace_bytes(const bg_conv_desc* d, int dtype) {
+  BgGeom g;
+  if (bg_build_geom(d, BG_OP_WGRAD, &g)) return 0;
+  size_t simt = (size_t)wgrad_nsplit(g) * wgrad_numel(d) * sizeof(float);
+  size_t tc = dtype == BG_BF16 ? bg_tc_conv_wgrad_ws(g, d) : 0;
+  return (simt > tc ? simt : tc) + 256;
+}
+
+extern "C" int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x, const void* dy, float* dw, int dtype, void* ws,
+                               size_t ws_bytes, int force_simt, void* stream) {
+  BgGeom g;
+  int rc = bg_build_geom(d, BG_OP_WGRAD, &g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const void* in = d->transposed ? dy : x;
+  const void* og = d->transposed ? x : dy;
+  if (!force_simt && dtype == BG_BF16) {
+    int taken = 0;
+    rc = bg_tc_conv_wgrad(g, d, in, og, dw, ws, ws_bytes, st, &taken);
+    if (rc) return rc;
+    if (taken) return BG_OK;
+  }
+  const int ns = wgrad_nsplit(g);
+  const long numel = wgrad_numel(d);
+  float* part = dw;
+  if (ns > 1) {
+    BG_REQUIRE(ws && ws_bytes >= (size_t)ns * numel * sizeof(float), BG_ERR_WORKSPACE, "wgrad workspace too small");
+    part = (float*)ws;
+  }
+  const int ntn = (int)bg_cdiv(g.Co, GW_BN);
+  dim3 grid((unsigned)(bg_cdiv(g.Ci, GW_BK) * ntn), g.ph[0].ntaps, ns);
+  BG_DISPATCH_DTYPE(dtype, T, gather_gemm_wgrad_kernel<T><<<grid, 256, 0, st>>>(g, (const T*)in, (const T*)og, part, numel, ns, ntn));
+  BG_LAUNCH_CHECK();
+  if (ns > 1) {
+    const int blocks = (int)min(bg_cdiv(numel, 256), (long)bg_num_sms() * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(part, dw, numel, numel, ns);
+    BG_LAUNCH_CHECK();
+  }
+  return BG_OK;
+}
+
+extern "C" size_t bg_colsum_workspace_bytes(long rows, int C) {
+  long nchunk = min(bg_cdiv(rows, 64), 1024L);
+  return (size_t)nchunk * C * sizeof(float) + 256;
+}
+
+extern "C" int bg_colsum(const void* dy, float* db, long rows, int C, int dtype, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  long nchunk = min(bg_cdiv(rows, 64), 1024L);
+  BG_REQUIRE(ws && ws_bytes >= (size_t)nchunk * C * sizeof(float), BG_ERR_WORKSPACE, "colsum workspace too small");
+  const long rpc = bg_cdiv(rows, nchunk);
+  dim3 grid((unsigned)bg_cdiv(C, 32), (unsigned)nchunk);
+  BG_DISPATCH_DTYPE(dtype, T, colsum_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (float*)ws, rows, C, rpc));
+  BG_LAUNCH_CHECK();
+  colsum_final_kernel<<<(unsigned)bg_cdiv(C, 128), 128, 0, st>>>((const float*)ws, db, (int)nchunk, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+extern "C" int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr, int dtype,
+                              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long total = (long)B * (H + pt + pb) * (W + pl + pr) * C;
+  const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
+  BG_DISPATCH_DTYPE(dtype, T, reflect_pad_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, pt, pl, pb, pr));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

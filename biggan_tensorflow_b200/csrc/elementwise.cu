@@ -1,0 +1,308 @@
+// Elementwise / small-reduction kernels of the BigGAN step: relu (ops.py:529-530), tanh (:539-540),
+// global_sum_pooling (:503-506), max_pooling (:508-510), softmax + batched matmuls of
+// self_attention_2 (:481-485), gamma*o + x (:490), residual adds, casts, fills.
+#include "bg_common.cuh"
+
+static inline int ew_blocks(long n, int per_thread = 1) {
+  long b = bg_cdiv(n, 256L * per_thread);
+  long mx = (long)bg_num_sms() * 16;
+  if (b > mx) b = mx;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define EW_LOOP(i, n)                                                     \
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x, _s = (long)gridDim.x * blockDim.x; i < (n); i += _s)
+
+template <typename T> __global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long n) {
+  EW_LOOP(i, n) bg_st(y, i, fmaxf(bg_ld(x, i), 0.f));
+}
+template <typename T> __global__ void relu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long n) {
+  EW_LOOP(i, n) bg_st(dx, i, bg_ld(x, i) > 0.f ? bg_ld(dy, i) : 0.f);
+}
+template <typename T> __global__ void tanh_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long n) {
+  EW_LOOP(i, n) { float t = bg_ld(y, i); bg_st(dx, i, bg_ld(dy, i) * (1.f - t * t)); }
+}
+template <typename T> __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long n) {
+  EW_LOOP(i, n) bg_st(o, i, bg_ld(a, i) + bg_ld(b, i));
+}
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ alpha_dev, float alpha,
+                             float beta, T* __restrict__ o, long n) {
+  const float a = alpha_dev ? alpha_dev[0] : alpha;
+  EW_LOOP(i, n) bg_st(o, i, a * bg_ld(x, i) + (y ? beta * bg_ld(y, i) : 0.f));
+}
+template <typename T> __global__ void fill_kernel(T* __restrict__ p, float v, long n) { EW_LOOP(i, n) bg_st(p, i, v); }
+template <typename S, typename D> __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, long n) {
+  EW_LOOP(i, n) bg_st(d, i, bg_ld(s, i));
+}
+
+extern "C" int bg_relu_fwd(const void* x, void* y, long n, int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, relu_fwd_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_relu_bwd(const void* x, const void* dy, void* dx, long n, int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, relu_bwd_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, (T*)dx, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_tanh_bwd(const void* y, const void* dy, void* dx, long n, int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, tanh_bwd_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dy, (T*)dx, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_add(const void* a, const void* b, void* out, long n, int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, add_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_axpby(const void* x, const void* y, const float* alpha_dev, float alpha, float beta, void* out, long n,
+                        int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, axpby_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)y, alpha_dev, alpha,
+                                                                                          beta, (T*)out, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_fill(void* p, float value, long n, int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, fill_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((T*)p, value, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_cast(const void* src, int sdt, void* dst, int ddt, long n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sdt == BG_F32 && ddt == BG_BF16) cast_kernel<float, bf16><<<ew_blocks(n), 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+  else if (sdt == BG_BF16 && ddt == BG_F32) cast_kernel<bf16, float><<<ew_blocks(n), 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+  else if (sdt == BG_F32 && ddt == BG_F32) cast_kernel<float, float><<<ew_blocks(n), 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (sdt == BG_BF16 && ddt == BG_BF16) cast_kernel<bf16, bf16><<<ew_blocks(n), 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+  else { bg_set_error("bad cast dtypes"); return BG_ERR_UNSUPPORTED; }
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// deterministic dot product: per-block partials, then a single block sums them in order
+template <typename T>
+__global__ void __launch_bounds__(256) dot_partial_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ part, long n) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  EW_LOOP(i, n) s = fmaf(bg_ld(a, i), bg_ld(b, i), s);
+  s = bg_block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) dot_final_kernel(const float* __restrict__ part, int np, float* __restrict__ out) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s += part[i];
+  s = bg_block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s;
+}
+extern "C" size_t bg_dot_workspace_bytes(long n) { (void)n; return 1024 * sizeof(float) + 256; }
+extern "C" int bg_dot(const void* a, const void* b, float* out, long n, int dtype, void* ws, size_t ws_bytes, void* stream) {
+  BG_REQUIRE(ws && ws_bytes >= 1024 * sizeof(float), BG_ERR_WORKSPACE, "dot workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np = (int)min(bg_cdiv(n, 2048), 1024L);
+  BG_DISPATCH_DTYPE(dtype, T, dot_partial_kernel<T><<<np, 256, 0, st>>>((const T*)a, (const T*)b, (float*)ws, n));
+  BG_LAUNCH_CHECK();
+  dot_final_kernel<<<1, 256, 0, st>>>((const float*)ws, np, out);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// global sum pooling with optional fused ReLU (BigGAN.py:669-671): y[b,c] = sum_hw relu(x[b,hw,c])
+template <typename T>
+__global__ void sumpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long HW, int C, int relu_first) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  float s = 0.f;
+  for (long r = 0; r < HW; ++r) {
+    float v = bg_ld(x, ((long)b * HW + r) * C + c);
+    s += relu_first ? fmaxf(v, 0.f) : v;
+  }
+  bg_st(y, (long)b * C + c, s);
+}
+template <typename T>
+__global__ void sumpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long HW, int C, int relu_first, long n) {
+  EW_LOOP(i, n) {
+    const int c = (int)(i % C);
+    const long b = i / ((long)C * HW);
+    float g = bg_ld(dy, b * C + c);
+    if (relu_first && !(bg_ld(x, i) > 0.f)) g = 0.f;
+    bg_st(dx, i, g);
+  }
+}
+extern "C" int bg_sumpool_fwd(const void* x, void* y, int B, long HW, int C, int relu_first, int dtype, void* stream) {
+  dim3 grid((unsigned)bg_cdiv(C, 128), B);
+  BG_DISPATCH_DTYPE(dtype, T, sumpool_fwd_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, HW, C, relu_first));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_sumpool_bwd(const void* x, const void* dy, void* dx, int B, long HW, int C, int relu_first, int dtype, void* stream) {
+  const long n = (long)B * HW * C;
+  BG_DISPATCH_DTYPE(dtype, T, sumpool_bwd_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, (T*)dx, HW, C,
+                                                                                                relu_first, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// 2x2/2 max pooling, NHWC (tf.layers.max_pooling2d(2,2,'SAME') on even sizes)
+template <typename T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, long n) {
+  const int Ho = H / 2, Wo = W / 2;
+  EW_LOOP(i, n) {
+    const int c = (int)(i % C); long r = i / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho); const long b = r / Ho;
+    const long base = ((b * H + 2 * oy) * W + 2 * ox) * C + c;
+    float m = bg_ld(x, base);
+    m = fmaxf(m, bg_ld(x, base + C));
+    m = fmaxf(m, bg_ld(x, base + (long)W * C));
+    m = fmaxf(m, bg_ld(x, base + (long)W * C + C));
+    bg_st(y, i, m);
+  }
+}
+template <typename T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int C, long n) {
+  const int Ho = H / 2, Wo = W / 2;
+  EW_LOOP(i, n) {   // one thread per pooled element: writes its 4 inputs
+    const int c = (int)(i % C); long r = i / C;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho); const long b = r / Ho;
+    const long base = ((b * H + 2 * oy) * W + 2 * ox) * C + c;
+    const long off[4] = {0, (long)C, (long)W * C, (long)W * C + C};
+    float v[4];
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = bg_ld(x, base + off[k]); if (v[k] > v[best]) best = k; }
+    const float g = bg_ld(dy, i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bg_st(dx, base + off[k], k == best ? g : 0.f);
+  }
+}
+extern "C" int bg_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream) {
+  BG_REQUIRE(H % 2 == 0 && W % 2 == 0, BG_ERR_UNSUPPORTED, "maxpool2: odd size");
+  const long n = (long)B * (H / 2) * (W / 2) * C;
+  BG_DISPATCH_DTYPE(dtype, T, maxpool2_fwd_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_maxpool2_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream) {
+  BG_REQUIRE(H % 2 == 0 && W % 2 == 0, BG_ERR_UNSUPPORTED, "maxpool2: odd size");
+  const long n = (long)B * (H / 2) * (W / 2) * C;
+  BG_DISPATCH_DTYPE(dtype, T, maxpool2_bwd_kernel<T><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, (T*)dx, H, W, C, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// softmax over the last axis: one warp per row (n up to a few thousand)
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * n;
+  T* yr = y + row * n;
+  float m = -INFINITY;
+  for (int i = lane; i < n; i += 32) m = fmaxf(m, bg_ld(xr, i));
+  m = bg_warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s += expf(bg_ld(xr, i) - m);
+  s = bg_warp_sum(s);
+  const float inv = 1.f / s;
+  for (int i = lane; i < n; i += 32) bg_st(yr, i, expf(bg_ld(xr, i) - m) * inv);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* yr = y + row * n;
+  const T* dr = dy + row * n;
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s = fmaf(bg_ld(yr, i), bg_ld(dr, i), s);
+  s = bg_warp_sum(s);
+  for (int i = lane; i < n; i += 32) bg_st(dx + row * n, i, bg_ld(yr, i) * (bg_ld(dr, i) - s));
+}
+extern "C" int bg_softmax_fwd(const void* x, void* y, long rows, int n, int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, softmax_fwd_kernel<T><<<(unsigned)bg_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, rows, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_softmax_bwd(const void* y, const void* dy, void* dx, long rows, int n, int dtype, void* stream) {
+  BG_DISPATCH_DTYPE(dtype, T, softmax_bwd_kernel<T><<<(unsigned)bg_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const T*)y, (const T*)dy, (T*)dx, rows, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// generic strided batched GEMM (SIMT, fp32 accumulate): C[b][m][n] = alpha * sum_k A[b][m,k] B[b][k,n] (+C)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bgemm_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ Cm, int M, int N, int K, long a_rs, long a_cs,
+             long a_bs, long b_rs, long b_cs, long b_bs, long c_rs, long c_bs, float alpha, int accumulate) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const T* Ab = A + (long)blockIdx.z * a_bs;
+  const T* Bb = Bm + (long)blockIdx.z * b_bs;
+  T* Cb = Cm + (long)blockIdx.z * c_bs;
+  // load roles: A tile 64(m) x 16(k); B tile 16(k) x 64(n); 4 elements per thread each
+  const bool a_kcontig = (a_cs == 1), b_ncontig = (b_cs == 1);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    float ra[4], rb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int m, k;
+      if (a_kcontig) { m = tid >> 2; k = (tid & 3) * 4 + e; } else { k = tid >> 4; m = (tid & 15) * 4 + e; }
+      ra[e] = (m0 + m < M && k0 + k < K) ? bg_ld(Ab, (long)(m0 + m) * a_rs + (long)(k0 + k) * a_cs) : 0.f;
+      int kk, n;
+      if (b_ncontig) { kk = tid >> 4; n = (tid & 15) * 4 + e; } else { n = tid >> 2; kk = (tid & 3) * 4 + e; }
+      rb[e] = (k0 + kk < K && n0 + n < N) ? bg_ld(Bb, (long)(k0 + kk) * b_rs + (long)(n0 + n) * b_cs) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (a_kcontig) As[(tid & 3) * 4 + e][tid >> 2] = ra[e]; else As[tid >> 4][(tid & 15) * 4 + e] = ra[e];
+      if (b_ncontig) Bs[tid >> 4][(tid & 15) * 4 + e] = rb[e]; else Bs[(tid & 3) * 4 + e][tid >> 2] = rb[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (accumulate) v += bg_ld(Cb, (long)m * c_rs + n);
+      bg_st(Cb, (long)m * c_rs + n, v);
+    }
+  }
+}
+extern "C" int bg_bgemm(const void* A, const void* Bm, void* C, int batch, int M, int N, int K, long a_rs, long a_cs, long a_bs,
+                        long b_rs, long b_cs, long b_bs, long c_rs, long c_bs, float alpha, int accumulate, int dtype,
+                        void* stream) {
+  BG_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, BG_ERR_SHAPE, "bgemm: bad shape");
+  dim3 grid((unsigned)bg_cdiv(N, 64), (unsigned)bg_cdiv(M, 64), batch);
+  BG_DISPATCH_DTYPE(dtype, T, bgemm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)A, (const T*)Bm, (T*)C, M, N, K, a_rs, a_cs, a_bs,
+                                                                                  b_rs, b_cs, b_bs, c_rs, c_bs, alpha, accumulate));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

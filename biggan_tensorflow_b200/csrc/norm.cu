@@ -1,0 +1,260 @@
+// (Conditional) batch norm: ops.py:611-643 (condition_batch_norm), ops.py:580-585 (batch_norm).
+// HBM-bound channel reductions over NHWC with per-sample gamma/beta and fused ReLU.  Statistics
+// are produced as double-precision (sum, sumsq) so that data-parallel ranks can all-reduce them
+// (cross-replica BN) before bg_bn_finalize.
+#include "bg_common.cuh"
+
+#define BN_CPB 128   // channels per block (32 lanes x 4)
+
+static inline int bn_nchunk(long rows, int C) {
+  long want = bg_cdiv(8L * bg_num_sms(), bg_cdiv(C, BN_CPB));
+  long mx = bg_cdiv(rows, 32);
+  long n = want < mx ? want : mx;
+  if (n < 1) n = 1;
+  if (n > 4096) n = 4096;
+  return (int)n;
+}
+
+// MODE 0: q1 = x, q2 = x^2.   MODE 1: g = dy * act'(y); q1 = g, q2 = g * xhat
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
+                 const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 int gb_bstride, int act, float eps, float* __restrict__ part, long HW, int C, int nchunk) {
+  // grid: x = channel block, y = chunk (over HW of one sample), z = sample
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * BN_CPB + lane * 4;
+  const int b = blockIdx.z;
+  const long rpc = (HW + nchunk - 1) / nchunk;
+  const long r0 = (long)blockIdx.y * rpc, r1 = min(HW, r0 + rpc);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    float inv[4], shift[4], mu[4], rs[4];
+    if (MODE == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        rs[e] = rsqrtf(var[c + e] + eps);
+        mu[e] = mean[c + e];
+        inv[e] = rs[e] * gamma[(long)b * gb_bstride + c + e];
+        shift[e] = beta[(long)b * gb_bstride + c + e] - mu[e] * inv[e];
+      }
+    }
+    const long base = (long)b * HW * C + c;
+    for (long r = r0 + ty; r < r1; r += 8) {
+      f4 xv = bg_ld4(x, base + r * C);
+      float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s1[e] += xe[e]; s2[e] = fmaf(xe[e], xe[e], s2[e]); }
+      } else {
+        f4 dv = bg_ld4(dy, base + r * C);
+        float de[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float g = de[e];
+          if (act == BG_ACT_RELU && !(xe[e] * inv[e] + shift[e] > 0.f)) g = 0.f;
+          s1[e] += g;
+          s2[e] = fmaf(g, (xe[e] - mu[e]) * rs[e], s2[e]);
+        }
+      }
+    }
+  }
+  __shared__ float sh[8][2][BN_CPB + 4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sh[ty][0][lane * 4 + e] = s1[e]; sh[ty][1][lane * 4 + e] = s2[e]; }
+  __syncthreads();
+  if (threadIdx.x < BN_CPB) {
+    const int cc = blockIdx.x * BN_CPB + threadIdx.x;
+    if (cc < C) {
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a += sh[i][0][threadIdx.x]; q += sh[i][1][threadIdx.x]; }
+      float* dst = part + (((long)b * nchunk + blockIdx.y) * 2) * C;
+      dst[cc] = a;
+      dst[C + cc] = q;
+    }
+  }
+}
+
+// sums over (sample, chunk) partials -> double [2C]
+__global__ void bn_stats_final_kernel(const float* __restrict__ part, double* __restrict__ sums, int nrow, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, q = 0.0;
+  for (int i = 0; i < nrow; ++i) { a += (double)part[((long)i * 2) * C + c]; q += (double)part[((long)i * 2 + 1) * C + c]; }
+  sums[c] = a;
+  sums[C + c] = q;
+}
+
+// per-sample: dbeta[b,c], dgamma[b,c] = sum over chunks
+__global__ void bn_bwd_final_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    int nchunk, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  float a = 0.f, q = 0.f;
+  for (int i = 0; i < nchunk; ++i) {
+    a += part[(((long)b * nchunk + i) * 2) * C + c];
+    q += part[(((long)b * nchunk + i) * 2 + 1) * C + c];
+  }
+  dbeta[(long)b * C + c] = a;
+  dgamma[(long)b * C + c] = q;
+}
+
+extern "C" size_t bg_bn_workspace_bytes(int B, long HW, int C) {
+  return (size_t)B * bn_nchunk(HW, C) * 2 * C * sizeof(float) + 256;
+}
+
+extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, int dtype, void* ws, size_t ws_bytes,
+                           void* stream) {
+  BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
+  BG_REQUIRE(ws && ws_bytes >= bg_bn_workspace_bytes(B, HW, C), BG_ERR_WORKSPACE, "bn workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk = bn_nchunk(HW, C);
+  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
+  BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0,
+                                                                        0.f, (float*)ws, HW, C, nchunk));
+  BG_LAUNCH_CHECK();
+  bn_stats_final_kernel<<<(unsigned)bg_cdiv(C, 128), 128, 0, st>>>((const float*)ws, sums, B * nchunk, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, float* __restrict__ mean,
+                                   float* __restrict__ var, float* run_mean, float* run_var, float momentum,
+                                   float var_correction, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / count;
+  double v = sums[C + c] / count - m * m;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)m;
+  var[c] = (float)v;
+  if (run_mean) run_mean[c] = run_mean[c] * momentum + (float)m * (1.f - momentum);
+  if (run_var) run_var[c] = run_var[c] * momentum + (float)v * var_correction * (1.f - momentum);
+}
+
+extern "C" int bg_bn_finalize(const double* sums, double count, float* mean, float* var, float* run_mean, float* run_var,
+                              float momentum, float var_correction, int C, void* stream) {
+  bn_finalize_kernel<<<(unsigned)bg_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, mean, var, run_mean, run_var,
+                                                                                momentum, var_correction, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// y = act(x*inv + (beta - mean*inv)), inv = rsqrt(var+eps)*gamma   (tf.nn.batch_normalization form)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int gb_bstride, T* __restrict__ y, int act,
+                float eps, long HW, int C, long total4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const int C4 = C >> 2;
+  for (; i < total4; i += stride) {
+    const int c = (int)(i % C4) * 4;
+    const long b = i / ((long)C4 * HW);
+    f4 xv = bg_ld4(x, i * 4);
+    float xe[4] = {xv.x, xv.y, xv.z, xv.w}, o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float inv = rsqrtf(var[c + e] + eps) * gamma[b * gb_bstride + c + e];
+      float v = xe[e] * inv + (beta[b * gb_bstride + c + e] - mean[c + e] * inv);
+      if (act == BG_ACT_RELU) v = fmaxf(v, 0.f);
+      o[e] = v;
+    }
+    bg_st4(y, i * 4, f4{o[0], o[1], o[2], o[3]});
+  }
+}
+
+extern "C" int bg_bn_apply(const void* x, const float* mean, const float* var, const float* gamma, const float* beta,
+                           int gb_bstride, void* y, int act, float eps, int B, long HW, int C, int dtype, void* stream) {
+  BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
+  const long total4 = (long)B * HW * C / 4;
+  const int blocks = (int)min(bg_cdiv(total4, 256), (long)bg_num_sms() * 16);
+  BG_DISPATCH_DTYPE(dtype, T, bn_apply_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, mean, var, gamma, beta, gb_bstride,
+                                                                                       (T*)y, act, eps, HW, C, total4));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+extern "C" int bg_bn_bwd_reduce(const void* dy, const void* x, const float* mean, const float* var, const float* gamma,
+                                const float* beta, int gb_bstride, float* dgamma, float* dbeta, int act, float eps, int B,
+                                long HW, int C, int dtype, void* ws, size_t ws_bytes, void* stream) {
+  BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
+  BG_REQUIRE(ws && ws_bytes >= bg_bn_workspace_bytes(B, HW, C), BG_ERR_WORKSPACE, "bn workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk = bn_nchunk(HW, C);
+  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
+  BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, mean, var, gamma, beta, gb_bstride,
+                                                                        act, eps, (float*)ws, HW, C, nchunk));
+  BG_LAUNCH_CHECK();
+  dim3 g2((unsigned)bg_cdiv(C, 128), B);
+  bn_bwd_final_kernel<<<g2, 128, 0, st>>>((const float*)ws, dgamma, dbeta, nchunk, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+__global__ void bn_bwd_sums_kernel(const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                   const float* __restrict__ gamma, int gb_bstride, double* __restrict__ s, int B, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, q = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const double gm = (double)gamma[(long)b * gb_bstride + c];
+    a += gm * (double)dbeta[(long)b * C + c];
+    q += gm * (double)dgamma[(long)b * C + c];
+  }
+  s[c] = a;
+  s[C + c] = q;
+}
+
+extern "C" int bg_bn_bwd_sums(const float* dgamma, const float* dbeta, const float* gamma, int gb_bstride, double* s, int B,
+                              int C, void* stream) {
+  bn_bwd_sums_kernel<<<(unsigned)bg_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(dgamma, dbeta, gamma, gb_bstride, s, B, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// dx = rstd * (gamma*g - s1/count - xhat * s2/count)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    int gb_bstride, const double* __restrict__ s, double count, T* __restrict__ dx, int act, float eps,
+                    long HW, int C, long total4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const int C4 = C >> 2;
+  for (; i < total4; i += stride) {
+    const int c = (int)(i % C4) * 4;
+    const long b = i / ((long)C4 * HW);
+    f4 xv = bg_ld4(x, i * 4), dv = bg_ld4(dy, i * 4);
+    float xe[4] = {xv.x, xv.y, xv.z, xv.w}, de[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float rs = rsqrtf(var[c + e] + eps);
+      const float gm = gamma[b * gb_bstride + c + e];
+      const float inv = rs * gm;
+      const float xhat = (xe[e] - mean[c + e]) * rs;
+      float g = de[e];
+      if (act == BG_ACT_RELU && !(xe[e] * inv + (beta[b * gb_bstride + c + e] - mean[c + e] * inv) > 0.f)) g = 0.f;
+      const float m1 = (float)(s[c + e] / count), m2 = (float)(s[C + c + e] / count);
+      o[e] = rs * (gm * g - m1 - xhat * m2);
+    }
+    bg_st4(dx, i * 4, f4{o[0], o[1], o[2], o[3]});
+  }
+}
+
+extern "C" int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* var, const float* gamma,
+                               const float* beta, int gb_bstride, const double* s, double count, void* dx, int act, float eps,
+                               int B, long HW, int C, int dtype, void* stream) {
+  BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
+  const long total4 = (long)B * HW * C / 4;
+  const int blocks = (int)min(bg_cdiv(total4, 256), (long)bg_num_sms() * 16);
+  BG_DISPATCH_DTYPE(dtype, T, bn_bwd_apply_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, mean, var, gamma,
+                                                                                           beta, gb_bstride, s, count, (T*)dx, act,
+                                                                                           eps, HW, C, total4));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

@@ -1,0 +1,833 @@
+"""Operator surface of the reference's ops.py, re-implemented on libbiggan_b200.so.
+
+Same function names, positional order and defaults as /root/reference/ops.py (cited per function),
+operating on NHWC device tensors (`tensor.Tensor`).  Variables are created through the
+`tf_shim.variable_scope/get_variable` shim with the reference's names.  There is no TF and no CPU
+fallback: every computation is a call into the C ABI (include/biggan_b200.h).
+
+Precision modes (north_star): `set_compute_dtype(F32)` = parity mode (fp32 SIMT kernels),
+`set_compute_dtype(BF16)` = performance mode (bf16 activations, fp32 accumulate, tcgen05 kernels
+where the shape is eligible).  Fully-connected layers always run in fp32 (they are tiny).
+"""
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, call, query
+from .tensor import (BF16, F32, Tensor, accumulate_grad, bg_dtype, empty, grad_target, record,
+                     recording, stream, workspace)
+from .tf_shim import (constant_initializer, current_scope_name, get_store, get_variable,
+                      random_normal_initializer, truncated_normal_initializer, variable_scope)
+
+##################################################################################
+# Initialization (ops.py:13-14)
+##################################################################################
+
+weight_init = truncated_normal_initializer(mean=0.0, stddev=0.02)
+gan_dtype = torch.float32
+
+_state = {"compute_dtype": F32, "force_simt": 0}
+
+
+def set_compute_dtype(dt):
+    _state["compute_dtype"] = dt
+
+
+def compute_dtype():
+    return _state["compute_dtype"]
+
+
+def set_force_simt(flag):
+    _state["force_simt"] = 1 if flag else 0
+
+
+class _Dist:
+    """Data-parallel hooks: cross-replica BN statistics + global-batch loss means."""
+    world_size = 1
+
+    @staticmethod
+    def all_reduce_sum(buf):
+        return buf
+
+
+dist = _Dist()
+
+
+def round_up(val, multiple):
+    return (int(val) + multiple - 1) // multiple * multiple
+
+
+##################################################################################
+# plumbing ops (views / casts / adds)
+##################################################################################
+
+def reshape(x, shape):
+    shape = [int(s) for s in shape]
+    y = Tensor(x.data.reshape(shape), requires_grad=x.requires_grad)
+    if recording(x):
+        def bw():
+            if y.grad is not None:
+                accumulate_grad(x, y.grad.reshape(x.data.shape), own=False)
+        record(bw)
+    return y
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    y = Tensor(empty(x.shape, dtype), requires_grad=x.requires_grad)
+    call("bg_cast", x.data, bg_dtype(x), y.data, bg_dtype(y), x.numel(), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            g = empty(x.shape, x.dtype)
+            call("bg_cast", y.grad, bg_dtype(y.grad), g, bg_dtype(g), g.numel(), stream())
+            accumulate_grad(x, g, own=True)
+        record(bw)
+    return y
+
+
+def add(a, b):
+    """x + x_init of ops.py:198/266/313 (and scalar loss sums)."""
+    y = Tensor(empty(a.shape, a.dtype), requires_grad=a.requires_grad or b.requires_grad)
+    call("bg_add", a.data, b.data, y.data, y.numel(), bg_dtype(y), stream())
+    if recording(a, b):
+        def bw():
+            if y.grad is None:
+                return
+            if a.requires_grad:
+                accumulate_grad(a, y.grad, own=False)
+            if b.requires_grad:
+                accumulate_grad(b, y.grad, own=False)
+        record(bw)
+    return y
+
+
+def scale(x, alpha):
+    """python-float * tensor (e.g. d_cls_loss_weight * cls_loss, BigGAN.py:853)."""
+    y = Tensor(empty(x.shape, x.dtype), requires_grad=x.requires_grad)
+    call("bg_axpby", x.data, None, None, float(alpha), 0.0, y.data, y.numel(), bg_dtype(y), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            g = torch.empty_like(y.grad)
+            call("bg_axpby", y.grad, None, None, float(alpha), 0.0, g, g.numel(), bg_dtype(g), stream())
+            accumulate_grad(x, g, own=True)
+        record(bw)
+    return y
+
+
+Tensor.__add__ = lambda a, b: add(a, b) if isinstance(b, Tensor) else (a if b == 0 else NotImplemented)
+Tensor.__radd__ = lambda a, b: a if b == 0 else NotImplemented
+Tensor.__mul__ = lambda a, b: scale(a, b)
+Tensor.__rmul__ = lambda a, b: scale(a, b)
+
+
+##################################################################################
+# Spectral norm (ops.py:718-747)
+##################################################################################
+
+def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False):
+    """w: Variable [..., C].  Returns W/sigma (same shape) after one power-iteration step; the
+    persistent `u` (created in the current scope, ops.py:722) is advanced in place (ops.py:743).
+    Evaluated once per update phase and variable (SURVEY 8a row 3 state semantics)."""
+    if iteration != 1:
+        raise ValueError("only iteration=1 is supported")
+    store = get_store()
+    w_shape = list(w.shape)
+    C = w_shape[-1]
+    K = w.numel() // C
+    u = get_variable("u", [1, C], initializer=random_normal_initializer(), trainable=False)
+    out_dtype = _out_dtype or F32
+    key = (u.name, out_dtype, bool(_want_t))
+    hit = store.sn_cache.get(key)
+    if hit is not None:
+        return hit
+    base = store.sn_cache.get(("pi", u.name))
+    if base is None:
+        v_hat = empty([K], F32)
+        sigma = empty([1], F32)
+        ws = workspace(query("bg_sn_workspace_bytes", K, C))
+        call("bg_sn_power_iter", w.data, u.data, u.data, v_hat, sigma, K, C, ws, ws.numel(), stream())
+        base = (v_hat, sigma)
+        store.sn_cache[("pi", u.name)] = base
+    v_hat, sigma = base
+    wn = Tensor(empty(w_shape, out_dtype), requires_grad=w.requires_grad)
+    w_t = empty(w_shape, out_dtype) if _want_t else None
+    rows = K // _taps
+    call("bg_sn_scale", w.data, sigma, wn.data, w_t, bg_dtype(out_dtype), _taps, rows, C, stream())
+    wn.aux = {"w_t": w_t, "sigma": sigma, "v_hat": v_hat, "u_hat": u.data}
+    store.sn_cache[key] = wn
+    if recording(w):
+        def bw():
+            if wn.grad is None:
+                return
+            dst, fin = grad_target(w)
+            ws2 = workspace(query("bg_sn_workspace_bytes", K, C))
+            call("bg_sn_bwd", w.data, wn.grad, u.data, v_hat, sigma, dst, K, C, ws2, ws2.numel(), stream())
+            if fin:
+                fin()
+        record(bw)
+    return wn
+
+
+##################################################################################
+# Convolution family (ops.py:49-139, :148-175)
+##################################################################################
+
+def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
+    """y = act(conv(x; wn) + bias + residual) and its tape entry (dgrad / wgrad / bias grad)."""
+    dt = bg_dtype(x)
+    fs = _state["force_simt"]
+    y = Tensor(empty([desc.B, desc.Ho, desc.Wo, desc.Co], x.dtype),
+               requires_grad=x.requires_grad or wn.requires_grad or (bias is not None and bias.requires_grad)
+               or (residual is not None and residual.requires_grad))
+    w_t = wn.aux.get("w_t") if wn.aux else None
+    call("bg_conv2d_fwd", desc, x.data, wn.data, w_t, bias.data if bias is not None else None,
+         residual.data if residual is not None else None, y.data, act, dt, fs, stream())
+    if recording(x, wn, bias, residual):
+        def bw():
+            dy = y.grad
+            if dy is None:
+                return
+            if act == _lib.ACT_TANH:
+                g = torch.empty_like(dy)
+                call("bg_tanh_bwd", y.data, dy, g, g.numel(), bg_dtype(g), stream())
+                dy = g
+            elif act == _lib.ACT_RELU:
+                g = torch.empty_like(dy)
+                call("bg_relu_bwd", y.data, dy, g, g.numel(), bg_dtype(g), stream())
+                dy = g
+            if residual is not None and residual.requires_grad:
+                accumulate_grad(residual, dy, own=False)
+            if wn.requires_grad:
+                dst, fin = grad_target(wn)
+                nb = query("bg_conv2d_wgrad_workspace_bytes", desc, dt)
+                ws = workspace(nb)
+                call("bg_conv2d_wgrad", desc, x.data, dy, dst, dt, ws, ws.numel(), fs, stream())
+                if fin:
+                    fin()
+            if bias is not None and bias.requires_grad:
+                rows = desc.B * desc.Ho * desc.Wo
+                dst, fin = grad_target(bias)
+                ws = workspace(query("bg_colsum_workspace_bytes", rows, desc.Co))
+                call("bg_colsum", dy, dst, rows, desc.Co, dt, ws, ws.numel(), stream())
+                if fin:
+                    fin()
+            if x.requires_grad:
+                nb = query("bg_conv2d_dgrad_workspace_bytes", desc, dt)
+                ws = workspace(nb) if nb else None
+                res = x.grad
+                if res is None:
+                    dx = torch.empty_like(x.data)
+                elif x.grad_owned:
+                    dx = res                      # fused accumulate in the dgrad epilogue
+                else:
+                    dx = torch.empty_like(x.data)
+                call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, res, dx, dt, ws, ws.numel() if nb else 0, fs, stream())
+                x.grad, x.grad_owned, x.grad_set = dx, True, True
+        record(bw)
+    return y
+
+
+def _sn_weight(w, taps, conv_like, x_dtype):
+    """Normalised weights in the layout(s) the conv kernels want."""
+    if x_dtype == BF16:
+        return spectral_norm(w, _out_dtype=BF16, _taps=taps, _want_t=True)
+    return spectral_norm(w, _out_dtype=F32, _taps=taps)
+
+
+def _conv_geometry(x, channels, kernel, stride, pad, opt):
+    """pad logic of ops.py:65-84."""
+    B, H, W, Cin = x.shape
+    pt = pb = pl = pr = 0
+    mode = _lib.PAD_ZERO
+    if pad > 0:
+        pad_type = opt.get("conv", {}).get("padding_type", "reflect")
+        if H % stride == 0:
+            pad = pad * 2
+        else:
+            pad = max(kernel - (H % stride), 0)
+        pt = int(pad // 2)
+        pb = int(pad - pt)
+        pl = int(pad // 2)
+        pr = int(pad - pl)
+        if pad_type == "zero":
+            # TF 'SAME' on the unpadded input (ops.py:80); pads follow the SAME rule
+            def same(n):
+                out = -(-n // stride)
+                tot = max((out - 1) * stride + kernel - n, 0)
+                return tot // 2, tot - tot // 2
+            pt, pb = same(H)
+            pl, pr = same(W)
+            mode = _lib.PAD_ZERO
+        elif pad_type == "reflect":
+            mode = _lib.PAD_REFLECT
+        else:
+            raise ValueError("Unsupported padding type: " + str(pad_type))
+    Ho = (H + pt + pb - kernel) // stride + 1
+    Wo = (W + pl + pr - kernel) // stride + 1
+    return ConvDesc(B, H, W, Cin, Ho, Wo, channels, kernel, kernel, stride, pt, pl, pb, pr, mode, 0)
+
+
+def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True, scope='conv_0',
+         _residual=None, _act=_lib.ACT_NONE):
+    """ops.py:49-113."""
+    with variable_scope(scope):
+        if isinstance(kernel, str):
+            raise ValueError("channel-sliced multi-kernel conv (ops.py:52-59) is out of scope")
+        if dilation != 1:
+            raise ValueError("dilation != 1 is not supported")
+        desc = _conv_geometry(x, channels, kernel, stride, pad, opt)
+        if not opt.get("conv", {}).get("sn", True):
+            raise ValueError("conv with sn=False (tf.layers.conv2d path) is not supported")
+        w = get_variable("kernel", shape=[kernel, kernel, x.shape[-1], channels], initializer=weight_init)
+        wn = _sn_weight(w, kernel * kernel, True, x.dtype)
+        bias = None
+        if use_bias:
+            bias = get_variable("bias", [channels], initializer=constant_initializer(0.0))
+        return _conv_op(x, wn, bias, desc, act=_act, residual=_residual)
+
+
+def deconv(x, channels, opt, kernel=4, stride=2, padding='SAME', use_bias=True, scope='deconv_0',
+           _residual=None):
+    """ops.py:116-139 (conv2d_transpose, SAME)."""
+    with variable_scope(scope):
+        B, H, W, Cin = x.shape
+        if padding != 'SAME':
+            raise ValueError("deconv padding %s is not supported" % padding)
+        if not opt.get("conv", {}).get("sn", True):
+            raise ValueError("deconv with sn=False (tf.layers.conv2d_transpose path) is not supported")
+        Ho, Wo = H * stride, W * stride
+        tot = max((H - 1) * stride + kernel - Ho, 0)       # SAME pad of the adjoint conv
+        p = tot // 2
+        desc = ConvDesc(B, H, W, Cin, Ho, Wo, channels, kernel, kernel, stride, p, p, tot - p, tot - p,
+                        _lib.PAD_ZERO, 1)
+        w = get_variable("kernel", shape=[kernel, kernel, channels, Cin], initializer=weight_init)
+        wn = _sn_weight(w, kernel * kernel, False, x.dtype)
+        bias = None
+        if use_bias:
+            bias = get_variable("bias", [channels], initializer=constant_initializer(0.0))
+        return _conv_op(x, wn, bias, desc, residual=_residual)
+
+
+def get_variable_with_custom_lr(name, shape, regularizer, lrmul):
+    """ops.py:141-146 (lrmul == 1 on the hot path)."""
+    w = get_variable(name, shape, initializer=truncated_normal_initializer(mean=0.0, stddev=0.02 / lrmul))
+    if lrmul == 1.0:
+        return w
+    return scale(w, lrmul)
+
+
+def flatten(x):
+    return reshape(x, [x.shape[0], -1])                                          # ops.py:177-178
+
+
+def hw_flatten(x):
+    return reshape(x, [x.shape[0], -1, x.shape[-1]])                             # ops.py:180-181
+
+
+def fully_connected(x, units, opt, use_bias=True, lrmul=1.0, scope='fully_0'):
+    """ops.py:148-175.  Always fp32 (M = batch rows only)."""
+    with variable_scope(scope):
+        x = flatten(x)
+        x = cast(x, F32)
+        Bn, channels = x.shape
+        desc = ConvDesc(Bn, 1, 1, channels, 1, 1, units, 1, 1, 1, 0, 0, 0, 0, _lib.PAD_ZERO, 0)
+        bias = None
+        if opt.get("conv", {}).get("sn", True):
+            w = get_variable_with_custom_lr("kernel", shape=[channels, units], regularizer=None, lrmul=lrmul)
+            if use_bias:
+                bias = get_variable("bias", [units], initializer=constant_initializer(0.0))
+            wn = spectral_norm(w, _out_dtype=F32)
+        else:
+            with variable_scope("dense"):                                      # tf.layers.dense (:167-173)
+                wn = get_variable("kernel", shape=[channels, units], initializer=weight_init)
+                if use_bias:
+                    bias = get_variable("bias", [units], initializer=constant_initializer(0.0))
+        x4 = reshape(x, [Bn, 1, 1, channels])
+        y = _conv_op(x4, wn, bias, desc)
+        return reshape(y, [Bn, units])
+
+
+##################################################################################
+# Residual-block, Self-Attention-block
+##################################################################################
+
+def resblock(x_init, channels, opt, use_bias=True, scope='resblock'):
+    """ops.py:187-198."""
+    with variable_scope(scope):
+        with variable_scope('res1'):
+            fuse = opt["act"] is relu and not opt["bn_in_d"]
+            x = conv(x_init, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt,
+                     _act=_lib.ACT_RELU if fuse else _lib.ACT_NONE)
+            if opt["bn_in_d"]:
+                x = bn(x, opt=opt)
+            if not fuse:
+                x = opt["act"](x)
+        with variable_scope('res2'):
+            if opt["bn_in_d"]:
+                x = conv(x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt)
+                x = bn(x, opt=opt)
+                return x + x_init
+            return conv(x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt, _residual=x_init)
+
+
+def upconv(x, channels, opt, use_bias=True, _residual=None):
+    """ops.py:200-218."""
+    m = opt["upsampling_method"]
+    if m == 'deconv3':
+        return deconv(x, channels, kernel=3, stride=2, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif m == 'deconv4':
+        return deconv(x, channels, kernel=4, stride=2, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif m == 'deconv6':
+        return deconv(x, channels, kernel=6, stride=2, use_bias=use_bias, opt=opt, _residual=_residual)
+    else:
+        raise ValueError("Invalid upsampling method specified: " + str(opt["upsampling_method"]))
+
+
+def g_conv(x, channels, opt, use_bias=True, _residual=None):
+    """ops.py:220-230."""
+    m = opt["g_conv"]
+    if m == 'deconv3':
+        return deconv(x, channels, kernel=3, stride=1, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif m == 'deconv4':
+        return deconv(x, channels, kernel=4, stride=1, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif m == 'conv3':
+        return conv(x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt, _residual=_residual)
+    else:
+        raise ValueError("Invalid generator convolution type specified: " + str(opt["g_conv"]))
+
+
+def resblock_up_condition(x_init, z, channels, opt, use_bias=True, scope='resblock_up'):
+    """ops.py:250-266.  cond_bn + act are one fused kernel; the residual add rides in the epilogue
+    of the res2 conv (the skip branch is computed first; the result is the same sum)."""
+    fuse = opt["act"] is relu
+    with variable_scope(scope):
+        with variable_scope('skip'):
+            skip = upconv(x_init, channels, use_bias=use_bias, opt=opt)
+        with variable_scope('res1'):
+            x = cond_bn(x_init, z, opt=opt, _act=_lib.ACT_RELU if fuse else _lib.ACT_NONE)
+            if not fuse:
+                x = opt["act"](x)
+            x = upconv(x, channels, use_bias=use_bias, opt=opt)
+        with variable_scope('res2'):
+            x = cond_bn(x, z, opt=opt, _act=_lib.ACT_RELU if fuse else _lib.ACT_NONE)
+            if not fuse:
+                x = opt["act"](x)
+            x = g_conv(x, channels, use_bias=use_bias, opt=opt, _residual=skip)
+    return x
+
+
+def downconv(x, channels, opt, use_bias=True, method=None, _residual=None):
+    """ops.py:269-291."""
+    if method is None:
+        method = opt["downsampling_method"]
+    if method == 'strided_conv3':
+        return conv(x, channels, kernel=3, stride=2, pad=1, use_bias=use_bias, opt=opt, _residual=_residual)
+    else:
+        raise ValueError("Invalid downsampling method specified: " + str(method))
+
+
+def resblock_down(x_init, channels, opt, use_bias=True, scope='resblock_down'):
+    """ops.py:293-313 (ReLU is applied to the raw image in the first block, :297-298)."""
+    with variable_scope(scope):
+        with variable_scope('skip'):
+            skip = downconv(x_init, channels, use_bias=use_bias, opt=opt, method=opt["downsampling_method"])
+        with variable_scope('res1'):
+            if opt["bn_in_d"]:
+                x = bn(x_init, opt=opt)
+            else:
+                x = x_init
+            x = opt["act"](x)
+            res_method = opt["downsampling_method"]
+            if res_method != 'strided_conv3':
+                res_method = 'resize_conv3'
+            fuse = opt["act"] is relu and not opt["bn_in_d"]
+            if fuse:
+                x = conv(x, channels, kernel=3, stride=2, pad=1, use_bias=use_bias, opt=opt, _act=_lib.ACT_RELU)
+            else:
+                x = downconv(x, channels, use_bias=use_bias, opt=opt, method=res_method)
+        with variable_scope('res2'):
+            if opt["bn_in_d"]:
+                x = bn(x, opt=opt)
+            if not fuse:
+                x = opt["act"](x)
+            x = conv(x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt, _residual=skip)
+    return x
+
+
+def matmul(a, b, transpose_b=False):
+    """Batched tf.matmul on [B, M, K] x [B, K, N] (or [B, N, K] with transpose_b) (ops.py:481,:485)."""
+    Bn, M, K = a.shape
+    N = b.shape[1] if transpose_b else b.shape[2]
+    dt = bg_dtype(a)
+    y = Tensor(empty([Bn, M, N], a.dtype), requires_grad=a.requires_grad or b.requires_grad)
+    if transpose_b:     # b [B, N, K]: element (k, n) at n*K + k
+        b_rs, b_cs = 1, K
+    else:               # b [B, K, N]
+        b_rs, b_cs = N, 1
+    call("bg_bgemm", a.data, b.data, y.data, Bn, M, N, K, K, 1, M * K, b_rs, b_cs, b.numel() // Bn,
+         N, M * N, 1.0, 0, dt, stream())
+    if recording(a, b):
+        def bw():
+            dy = y.grad
+            if dy is None:
+                return
+            if a.requires_grad:       # da[M,K] = dy[M,N] . B^T
+                dst, fin = grad_target(a)
+                if transpose_b:   # B^T (n,k) = b[n,k]
+                    call("bg_bgemm", dy, b.data, dst, Bn, M, K, N, N, 1, M * N, K, 1, N * K, K, M * K, 1.0, 0, dt, stream())
+                else:             # B^T (n,k) = b[k,n]
+                    call("bg_bgemm", dy, b.data, dst, Bn, M, K, N, N, 1, M * N, 1, N, K * N, K, M * K, 1.0, 0, dt, stream())
+                if fin:
+                    fin()
+            if b.requires_grad:
+                dst, fin = grad_target(b)
+                if transpose_b:   # db[N,K] = dy^T[N,M] . a[M,K]
+                    call("bg_bgemm", dy, a.data, dst, Bn, N, K, M, 1, N, M * N, K, 1, M * K, K, N * K, 1.0, 0, dt, stream())
+                else:             # db[K,N] = a^T[K,M] . dy[M,N]
+                    call("bg_bgemm", a.data, dy, dst, Bn, K, N, M, 1, K, M * K, N, 1, M * N, N, K * N, 1.0, 0, dt, stream())
+                if fin:
+                    fin()
+        record(bw)
+    return y
+
+
+def softmax(x):
+    """tf.nn.softmax over the last axis (ops.py:483)."""
+    n = x.shape[-1]
+    rows = x.numel() // n
+    y = Tensor(empty(x.shape, x.dtype), requires_grad=x.requires_grad)
+    call("bg_softmax_fwd", x.data, y.data, rows, n, bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_softmax_bwd", y.data, y.grad, dst, rows, n, bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+def _gamma_residual(gamma, o, x):
+    """x = gamma * o + x (ops.py:463, :490) with scalar trainable gamma."""
+    y = Tensor(empty(x.shape, x.dtype), requires_grad=gamma.requires_grad or o.requires_grad or x.requires_grad)
+    n = x.numel()
+    call("bg_axpby", o.data, x.data, gamma.data, 0.0, 1.0, y.data, n, bg_dtype(x), stream())
+    if recording(gamma, o, x):
+        def bw():
+            dy = y.grad
+            if dy is None:
+                return
+            if x.requires_grad:
+                accumulate_grad(x, dy, own=False)
+            if o.requires_grad:
+                g = torch.empty_like(dy)
+                call("bg_axpby", dy, None, gamma.data, 0.0, 0.0, g, n, bg_dtype(g), stream())
+                accumulate_grad(o, g, own=True)
+            if gamma.requires_grad:
+                dst, fin = grad_target(gamma)
+                ws = workspace(query("bg_dot_workspace_bytes", n))
+                call("bg_dot", dy, o.data, dst, n, bg_dtype(dy), ws, ws.numel(), stream())
+                if fin:
+                    fin()
+        record(bw)
+    return y
+
+
+def self_attention(x, channels, opt, scope='self_attention'):
+    """ops.py:445-465 (full N x N attention; dead code in the reference, kept as API surface)."""
+    with variable_scope(scope):
+        use_bias = opt.get("self_attention_bias", False)
+        f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias)
+        g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias)
+        h = conv(x, channels, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
+        s = matmul(hw_flatten(g), hw_flatten(f), transpose_b=True)
+        beta = softmax(s)
+        o = matmul(beta, hw_flatten(h))
+        gamma = get_variable("gamma", [1], initializer=constant_initializer(0.0))
+        o = reshape(o, x.shape)
+        return _gamma_residual(gamma, o, x)
+
+
+def self_attention_2(x, channels, opt, scope='self_attention'):
+    """ops.py:467-492 (the live block: 2x2 max-pooled keys/values, C/8 q/k, C/2 v, 1x1 out conv)."""
+    with variable_scope(scope):
+        use_bias = opt.get("self_attention_bias", False)
+        f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias)
+        f = max_pooling(f)
+        g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias)
+        h = conv(x, channels // 2, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
+        h = max_pooling(h)
+        s = matmul(hw_flatten(g), hw_flatten(f), transpose_b=True)      # [bs, N, N/4], no 1/sqrt(d)
+        beta = softmax(s)
+        o = matmul(beta, hw_flatten(h))                                 # [bs, N, C/2]
+        gamma = get_variable("gamma", [1], initializer=constant_initializer(0.0))
+        o = reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2])
+        o = conv(o, channels, kernel=1, stride=1, opt=opt, scope='attn_conv', use_bias=use_bias)
+        return _gamma_residual(gamma, o, x)
+
+
+##################################################################################
+# Sampling
+##################################################################################
+
+def global_sum_pooling(x, _relu_first=False):
+    """ops.py:503-506 (optionally fused with the preceding ReLU, BigGAN.py:669-671)."""
+    B, H, W, C = x.shape
+    y = Tensor(empty([B, C], x.dtype), requires_grad=x.requires_grad)
+    call("bg_sumpool_fwd", x.data, y.data, B, H * W, C, int(_relu_first), bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_sumpool_bwd", x.data, y.grad, dst, B, H * W, C, int(_relu_first), bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+def max_pooling(x):
+    """ops.py:508-510."""
+    B, H, W, C = x.shape
+    y = Tensor(empty([B, H // 2, W // 2, C], x.dtype), requires_grad=x.requires_grad)
+    call("bg_maxpool2_fwd", x.data, y.data, B, H, W, C, bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_maxpool2_bwd", x.data, y.grad, dst, B, H, W, C, bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+##################################################################################
+# Activation function
+##################################################################################
+
+def relu(x):
+    """ops.py:529-530."""
+    y = Tensor(empty(x.shape, x.dtype), requires_grad=x.requires_grad)
+    call("bg_relu_fwd", x.data, y.data, x.numel(), bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_relu_bwd", x.data, y.grad, dst, x.numel(), bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+def tanh(x):
+    """ops.py:539-540."""
+    raise NotImplementedError("standalone tanh: use conv(..., _act=ACT_TANH); see model.generator")
+
+
+##################################################################################
+# Normalization function
+##################################################################################
+
+def _bn_core(x, gamma, beta, gb_bstride, run_mean, run_var, momentum, var_correction_fn, opt, act):
+    """Shared (conditional) batch-norm forward/backward.  gamma/beta: fp32 Tensors [B,C] or [C]."""
+    B, H, W, C = x.shape
+    HW = H * W
+    dt = bg_dtype(x)
+    eps = 1e-05
+    y = Tensor(empty(x.shape, x.dtype), requires_grad=x.requires_grad or gamma.requires_grad or beta.requires_grad)
+    if opt["is_training"]:
+        sums = empty([2 * C], torch.float64)
+        ws = workspace(query("bg_bn_workspace_bytes", B, HW, C))
+        call("bg_bn_stats", x.data, sums, B, HW, C, dt, ws, ws.numel(), stream())
+        dist.all_reduce_sum(sums)                                  # cross-replica statistics
+        count = float(B * HW * dist.world_size)
+        mean = empty([C], F32)
+        var = empty([C], F32)
+        call("bg_bn_finalize", sums, count, mean, var, run_mean.data, run_var.data, float(momentum),
+             float(var_correction_fn(count)), C, stream())
+    else:
+        mean, var = run_mean.data, run_var.data
+        count = float(B * HW)
+    call("bg_bn_apply", x.data, mean, var, gamma.data, beta.data, gb_bstride, y.data, act, eps, B, HW, C, dt, stream())
+    if recording(x, gamma, beta):
+        def bw():
+            dy = y.grad
+            if dy is None:
+                return
+            dgamma = empty([B, C], F32)
+            dbeta = empty([B, C], F32)
+            ws2 = workspace(query("bg_bn_workspace_bytes", B, HW, C))
+            call("bg_bn_bwd_reduce", dy, x.data, mean, var, gamma.data, beta.data, gb_bstride, dgamma, dbeta, act, eps,
+                 B, HW, C, dt, ws2, ws2.numel(), stream())
+            if x.requires_grad:
+                s = empty([2 * C], torch.float64)
+                call("bg_bn_bwd_sums", dgamma, dbeta, gamma.data, gb_bstride, s, B, C, stream())
+                dist.all_reduce_sum(s)
+                dst, fin = grad_target(x)
+                call("bg_bn_bwd_apply", dy, x.data, mean, var, gamma.data, beta.data, gb_bstride, s, count, dst, act,
+                     eps, B, HW, C, dt, stream())
+                if fin:
+                    fin()
+            if gb_bstride:
+                if gamma.requires_grad:
+                    accumulate_grad(gamma, dgamma, own=True)
+                if beta.requires_grad:
+                    accumulate_grad(beta, dbeta, own=True)
+            else:
+                for p, d in ((gamma, dgamma), (beta, dbeta)):
+                    if p.requires_grad:
+                        dst, fin = grad_target(p)
+                        ws3 = workspace(query("bg_colsum_workspace_bytes", B, C))
+                        call("bg_colsum", d, dst, B, C, _lib.BG_F32, ws3, ws3.numel(), stream())
+                        if fin:
+                            fin()
+        record(bw)
+    return y
+
+
+def condition_batch_norm(x, z, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
+    """ops.py:611-643."""
+    with variable_scope(scope):
+        c = x.shape[-1]
+        decay = opt.get("bn", {}).get("momentum", 0.98)
+        test_mean = get_variable("pop_mean", shape=[c], initializer=constant_initializer(0.0), trainable=False)
+        test_var = get_variable("pop_var", shape=[c], initializer=constant_initializer(1.0), trainable=False)
+        beta = fully_connected(z, units=c, scope='beta', opt=opt)
+        gamma = fully_connected(z, units=c, scope='gamma', opt=opt)
+        return _bn_core(x, gamma, beta, c, test_mean, test_var, decay, lambda n: 1.0, opt, _act)
+
+
+def batch_norm(x, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
+    """ops.py:580-585 (tf.layers.batch_normalization; moving_variance takes the unbiased variance)."""
+    with variable_scope(scope):
+        c = x.shape[-1]
+        momentum = opt.get("bn", {}).get("momentum", 0.98)
+        gamma = get_variable("gamma", [c], initializer=constant_initializer(1.0))
+        beta = get_variable("beta", [c], initializer=constant_initializer(0.0))
+        mm = get_variable("moving_mean", [c], initializer=constant_initializer(0.0), trainable=False)
+        mv = get_variable("moving_variance", [c], initializer=constant_initializer(1.0), trainable=False)
+        return _bn_core(x, gamma, beta, 0, mm, mv, momentum, lambda n: n / max(n - 1.0, 1.0), opt, _act)
+
+
+def bn(x, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
+    """ops.py:546-561."""
+    type = opt.get("bn", {}).get("type", "bn")
+    if type == 'batch_norm_broken_renorm':
+        type = 'batch_norm'
+        if scope == 'batch_norm':
+            scope = 'batch_renorm'
+    if type == 'bn' or type == 'batch_norm':
+        return batch_norm(x, opt=opt, scope=scope, _act=_act)
+    elif type == 'batch_renorm':
+        raise ValueError("BN type batch_renorm is not supported (out of scope, SURVEY 8f rank 3)")
+    else:
+        raise ValueError("Unknown BN type: " + str(type))
+
+
+def cond_bn(x, z, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
+    """ops.py:563-578."""
+    type = opt.get("bn", {}).get("type", "bn")
+    if type == 'batch_norm_broken_renorm':
+        type = 'batch_norm'
+        if scope == 'batch_norm':
+            scope = 'batch_renorm'
+    if type == 'bn' or type == 'batch_norm':
+        return condition_batch_norm(x, z, opt=opt, scope=scope, _act=_act)
+    elif type == 'batch_renorm':
+        raise ValueError("BN type batch_renorm is not supported (out of scope, SURVEY 8f rank 3)")
+    else:
+        raise ValueError("Unknown BN type: " + str(type))
+
+
+##################################################################################
+# Loss function
+##################################################################################
+
+def _seed_scaled(t, g, upstream):
+    """t.grad += upstream[0] * g  (losses are scalar nodes; upstream is d(total)/d(loss))."""
+    out = torch.empty_like(g)
+    call("bg_axpby", g, None, upstream, 0.0, 0.0, out, out.numel(), bg_dtype(out), stream())
+    accumulate_grad(t, out, own=True)
+
+
+def flood_loss(loss, flood_level):
+    """ops.py:847-848 -- folded into the hinge kernels (flood argument)."""
+    raise NotImplementedError("flood is applied inside discriminator_loss / generator_loss")
+
+
+def discriminator_loss(loss_func, real, fake, flood_level=0):
+    """ops.py:753-797, 'hinge' (:788-790) + flood (:794-795).  Means are over the GLOBAL batch."""
+    if loss_func != 'hinge':
+        raise ValueError("loss '%s' is not supported (hinge only)" % loss_func)
+    if flood_level and dist.world_size > 1:
+        raise ValueError("flood_level with data parallelism needs the global loss first; unsupported")
+    real32, fake32 = cast(real, F32), cast(fake, F32)
+    n_r, n_f = real32.numel(), fake32.numel()
+    assert n_r == n_f
+    loss = Tensor(empty([1], F32), requires_grad=real.requires_grad or fake.requires_grad)
+    dreal, dfake = torch.empty_like(real32.data), torch.empty_like(fake32.data)
+    call("bg_hinge_d_fwd_bwd", real32.data, fake32.data, n_r, n_f, 1.0 / (n_r * dist.world_size), float(flood_level),
+         loss.data, dreal, dfake, _lib.BG_F32, stream())
+    if recording(real32, fake32):
+        def bw():
+            if loss.grad is None:
+                return
+            if real32.requires_grad:
+                _seed_scaled(real32, dreal, loss.grad)
+            if fake32.requires_grad:
+                _seed_scaled(fake32, dfake, loss.grad)
+        record(bw)
+    return loss
+
+
+def generator_loss(loss_func, fake, real, flood_level=0):
+    """ops.py:799-840, 'hinge' (:832-833): -mean(fake); `real` unused."""
+    if loss_func != 'hinge':
+        raise ValueError("loss '%s' is not supported (hinge only)" % loss_func)
+    if flood_level and dist.world_size > 1:
+        raise ValueError("flood_level with data parallelism needs the global loss first; unsupported")
+    fake32 = cast(fake, F32)
+    n = fake32.numel()
+    loss = Tensor(empty([1], F32), requires_grad=fake.requires_grad)
+    dfake = torch.empty_like(fake32.data)
+    call("bg_hinge_g_fwd_bwd", fake32.data, n, 1.0 / (n * dist.world_size), float(flood_level), loss.data, dfake,
+         _lib.BG_F32, stream())
+    if recording(fake32):
+        def bw():
+            if loss.grad is not None:
+                _seed_scaled(fake32, dfake, loss.grad)
+        record(bw)
+    return loss
+
+
+def cls_loss_fn(type, cls_weights):
+    """utils.py:339-375, 'logistic' (:366-369).  cls_weights: device fp32 [n_labels] buffer or None."""
+    if type != 'logistic':
+        raise ValueError("Invalid label loss type: " + type)
+
+    def loss(truth, answer):
+        a32 = cast(answer, F32)
+        Bn, nl = a32.shape
+        out = Tensor(empty([1], F32), requires_grad=answer.requires_grad)
+        dl = torch.empty_like(a32.data)
+        tdata = truth.data if isinstance(truth, Tensor) else truth
+        call("bg_logistic_cls_fwd_bwd", a32.data, tdata, cls_weights, Bn, nl, 1.0,
+             1.0 / (Bn * nl * dist.world_size), out.data, dl, 0, _lib.BG_F32, stream())
+        if recording(a32):
+            def bw():
+                if out.grad is not None:
+                    _seed_scaled(a32, dl, out.grad)
+            record(bw)
+        return out
+    return loss

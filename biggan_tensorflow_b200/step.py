@@ -1,0 +1,200 @@
+"""One BigGAN training iteration = D update then G update (BigGAN.train, BigGAN.py:1061-1084), with the
+loss / optimizer wiring of BigGAN.build_model (BigGAN.py:806-930) and utils.create_train_ops
+(utils.py:252-267): hinge losses (+ logistic class loss when n_labels > 0), Adam for D, Adam +
+MovingAverageOptimizer (EMA shadows) for G.
+
+Data parallel (new design): one process per GPU, the global batch is split contiguously
+across ranks; gradients are summed with one NCCL all-reduce per flat arena, BN statistics with
+small all-reduces inside ops._bn_core; losses are scaled by 1/global batch so summed gradients equal
+the single-device gradient of the global-batch mean.
+"""
+import math
+
+import torch
+
+from . import DiffAugment_tf, _lib, ops
+from ._lib import call
+from .model import Config, discriminator, generator
+from .tensor import (BF16, F32, Tensor, accumulate_grad, backward, bg_dtype, clear_tape, empty, no_grad, record,
+                     recording, stream)
+from .tf_shim import VariableStore, set_store
+
+
+def split_rows(t, sizes):
+    """Split [sum(sizes), ...] along axis 0 into views; backward reassembles the gradient."""
+    outs, o = [], 0
+    for s in sizes:
+        outs.append(Tensor(t.data[o:o + s], requires_grad=t.requires_grad))
+        o += s
+    if recording(t):
+        def bw():
+            if all(c.grad is None for c in outs):
+                return
+            g = torch.empty_like(t.data)
+            o2 = 0
+            for c, s in zip(outs, sizes):
+                if c.grad is None:
+                    g[o2:o2 + s].zero_()
+                else:
+                    g[o2:o2 + s].copy_(c.grad)
+                o2 += s
+            accumulate_grad(t, g, own=True)
+        record(bw)
+    return outs
+
+
+class Trainer:
+    def __init__(self, cfg: Config, compute_dtype=F32, rank=0, world_size=1, process_group=None):
+        self.cfg = cfg
+        self.compute_dtype = compute_dtype
+        self.rank, self.world = rank, world_size
+        self.pg = process_group
+        self.store = set_store(VariableStore())
+        ops.set_compute_dtype(compute_dtype)
+        assert cfg.batch_size % world_size == 0, "global batch must divide across ranks"
+        self.local_batch = cfg.batch_size // world_size
+        ops.dist.world_size = world_size
+        if world_size > 1:
+            import torch.distributed as dist
+
+            def allreduce(buf):
+                dist.all_reduce(buf, group=self.pg)
+                return buf
+            ops.dist.all_reduce_sum = allreduce
+        else:
+            ops.dist.all_reduce_sum = lambda b: b
+        self.t_d = 0
+        self.t_g = 0
+        self.opt = {}
+        self.cls_weights = None
+        self._built = False
+
+    # ------------------------------------------------------------------------------------------
+    def build(self):
+        """Create every variable (dry forward on one sample), then pack each network's trainables into
+        flat arenas (params / grads / Adam m, v / EMA shadows)."""
+        cfg = self.cfg
+        dev = torch.device("cuda", torch.cuda.current_device())
+        z = torch.zeros(2, 1, 1, cfg.z_dim, device=dev)
+        cls = torch.zeros(2, max(cfg.n_labels, 1), device=dev)
+        self.store.begin_phase()
+        with no_grad():
+            fake = generator(cfg, z, cls)
+            discriminator(cfg, fake)
+        snap = {k: v.data.clone() for k, v in self.store.vars.items() if not v.trainable}
+        for k, d in snap.items():       # undo the dry run's side effects on u / BN running stats
+            self.store.vars[k].data.copy_(torch.from_numpy(self._initial(k, d.shape)).to(dev))
+        for net in ("generator", "discriminator"):
+            ar = self.store.pack(net)
+            n = ar["params"].numel()
+            self.opt[net] = {"m": torch.zeros(n, device=dev), "v": torch.zeros(n, device=dev),
+                             "ema": ar["params"].clone() if net == "generator" else None}
+        if cfg.acgan:
+            self.cls_weights = torch.ones(cfg.n_labels, device=dev)            # BigGAN.py:100
+        self.store.begin_phase()
+        clear_tape()
+        self._built = True
+
+    def _initial(self, name, shape):
+        from .tf_shim import constant_initializer, random_normal_initializer
+        if name.endswith("/u"):
+            return random_normal_initializer()(name, shape)
+        if name.endswith("pop_var") or name.endswith("moving_variance"):
+            return constant_initializer(1.0)(name, shape)
+        return constant_initializer(0.0)(name, shape)
+
+    def load(self, params):
+        self.store.load(params)
+        if self.opt.get("generator") and self.opt["generator"]["ema"] is not None:
+            self.opt["generator"]["ema"].copy_(self.store.arenas["generator"]["params"])
+
+    # ------------------------------------------------------------------------------------------
+    def _set_phase(self, net):
+        for k, v in self.store.vars.items():
+            v.requires_grad = bool(v.trainable and net in k)
+            v.grad = None
+            v.grad_set = False
+            v.grad_owned = True
+        self.store.begin_phase()
+        clear_tape()
+
+    def _finish_grads(self, net):
+        ar = self.store.arenas[net]
+        for v in ar["vars"]:
+            if not v.grad_set:
+                v.grad_view.zero_()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ar["grads"], group=self.pg)          # NCCL over NVLink; sum == global-batch gradient
+        return ar
+
+    def _adam(self, net, lr, t):
+        cfg = self.cfg
+        ar = self.store.arenas[net]
+        o = self.opt[net]
+        lr_t = lr * math.sqrt(1.0 - cfg.beta2 ** t) / (1.0 - cfg.beta1 ** t)     # tf.train.AdamOptimizer
+        call("bg_adam_ema_step", ar["params"], ar["grads"], o["m"], o["v"], o["ema"], ar["params"].numel(),
+             float(lr_t), float(cfg.beta1), float(cfg.beta2), 1e-8, float(cfg.moving_decay), 1.0, stream())
+
+    def _as_input(self, img):
+        t = Tensor(img)
+        return ops.cast(t, self.compute_dtype)
+
+    # ------------------------------------------------------------------------------------------
+    def d_update(self, real, labels, z, cls_z, apply=True):
+        """d_train_op (BigGAN.py:1063): D(DiffAugment(real)), D(DiffAugment(G(z))), hinge + class loss."""
+        cfg = self.cfg
+        if not self._built:
+            self.build()
+        self._set_phase("discriminator")
+        Bl = real.shape[0]
+        with no_grad():                                   # no gradient flows into G in the D update
+            fake = generator(cfg, z, cls_z)
+            aug_real = DiffAugment_tf.DiffAugment(self._as_input(real), policy=cfg.da_policy)       # :806
+            aug_fake = DiffAugment_tf.DiffAugment(fake, policy=cfg.da_policy)                       # :857
+            x = Tensor(torch.cat([aug_real.data, aug_fake.data], dim=0))
+        # D(real) and D(fake) share weights and have no batch statistics -> one pass over [real; fake]
+        out = discriminator(cfg, x)
+        real_logits, fake_logits = split_rows(out["real"], [Bl, Bl])
+        d_loss = ops.discriminator_loss(cfg.gan_type, real=real_logits, fake=fake_logits, flood_level=cfg.d_flood)   # :879
+        if cfg.acgan:
+            real_cls, _ = split_rows(out["cls"], [Bl, Bl])
+            cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
+            d_loss = d_loss + cfg.d_cls_loss_weight * cls_loss(labels, real_cls)                   # :853
+        backward([(d_loss, torch.ones(1, device=real.device))])
+        self._finish_grads("discriminator")
+        if apply:
+            self.t_d += 1
+            self._adam("discriminator", cfg.d_lr, self.t_d)
+        return d_loss.data, {"fake": fake, "real_logits": real_logits, "fake_logits": fake_logits}
+
+    def g_update(self, z, cls_z, apply=True):
+        """g_train_op (BigGAN.py:1082): fresh z, G -> DiffAugment -> D, -mean(fake) + class loss."""
+        cfg = self.cfg
+        if not self._built:
+            self.build()
+        self._set_phase("generator")
+        fake = generator(cfg, z, cls_z)
+        aug = DiffAugment_tf.DiffAugment(fake, policy=cfg.da_policy)
+        out = discriminator(cfg, aug)
+        g_loss = ops.generator_loss(cfg.gan_type, fake=out["real"], real=None, flood_level=cfg.g_flood)   # :896
+        if cfg.acgan:
+            cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
+            g_loss = g_loss + cfg.g_cls_loss_weight * cls_loss(cls_z, out["cls"])                  # :894
+        backward([(g_loss, torch.ones(1, device=z.device))])
+        self._finish_grads("generator")
+        if apply:
+            self.t_g += 1
+            self._adam("generator", cfg.g_lr, self.t_g)
+        return g_loss.data, {"fake": fake, "fake_logits": out["real"]}
+
+    def train_step(self, real, labels, z_d, z_g, cls_z):
+        """One iteration: D update, then G update (n_critic = 1, BigGAN.py:1080)."""
+        d_loss, _ = self.d_update(real, labels, z_d, cls_z)
+        g_loss, _ = self.g_update(z_g, cls_z)
+        return d_loss, g_loss
+
+    def grads(self, net):
+        ar = self.store.arenas[net]
+        torch.cuda.synchronize()
+        return {v.name: v.grad_view.detach().cpu().numpy().copy() for v in ar["vars"]}

@@ -1,0 +1,206 @@
+/* biggan_b200.h -- C ABI of libbiggan_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the BigGAN G+D training step of david-jk/BigGAN-Tensorflow.  The reference
+ * has no FFI: its operator surface is the Python module ops.py / DiffAugment_tf.py, whose math is
+ * executed by stock TensorFlow kernels.  Each entry point below replaces the TF kernels behind one
+ * reference function (cited as file:line into /root/reference); biggan_tensorflow_b200/ops.py is the
+ * Python mirror that keeps the reference signatures and calls these through ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error (bg_status); bg_last_error() gives the text
+ *  - all pointers are DEVICE pointers owned by the caller; the library allocates nothing, keeps no
+ *    pointer after return, and only enqueues work on `stream` (a cudaStream_t passed as void*)
+ *  - activations are NHWC; `dtype` selects their storage: BG_F32 (parity mode) or BG_BF16
+ *    (performance mode, fp32 accumulate).  Master weights / gradients of weights are always fp32.
+ *  - workspaces are caller-allocated; query the *_workspace_bytes function first
+ */
+#ifndef BIGGAN_B200_H
+#define BIGGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { BG_OK = 0, BG_ERR_SHAPE = -1, BG_ERR_UNSUPPORTED = -2, BG_ERR_CUDA = -3,
+               BG_ERR_WORKSPACE = -4 } bg_status;
+typedef enum { BG_F32 = 0, BG_BF16 = 1 } bg_dtype;
+typedef enum { BG_ACT_NONE = 0, BG_ACT_RELU = 1, BG_ACT_TANH = 2 } bg_act;
+typedef enum { BG_PAD_ZERO = 0, BG_PAD_REFLECT = 1 } bg_pad_mode;
+
+const char* bg_last_error(void);
+int bg_abi_version(void);
+/* 1 if the tcgen05/TMA tensor-core path is usable on the current device (sm_100), else 0 */
+int bg_has_tensor_core_path(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spectral norm -- ops.py:718-747 (spectral_norm).  W is the [K, C] view `reshape(w, [-1, C])`.
+ * bg_sn_power_iter: v_hat = l2n(u W^T), u_hat = l2n(v_hat W), sigma = v_hat W u_hat^T; writes
+ *   v_hat -> v[K], u_hat -> u_out[C] (may alias u), sigma[0].   One HBM read of W (+ L2 re-read).
+ * bg_sn_scale: out = W / sigma in `dtype`; if out_t != NULL also writes the per-tap transposed copy
+ *   out_t[t][c][r] for W viewed as [taps][rows][C] (K = taps*rows) -- the K-major operand layout of
+ *   the tcgen05 conv kernels.
+ * bg_sn_bwd: dW = dWn/sigma - (<dWn,W>/sigma^2) v_hat^T u_hat  (gradient with u_hat, v_hat frozen,
+ *   ops.py:738-739).
+ * ------------------------------------------------------------------------------------------- */
+size_t bg_sn_workspace_bytes(int K, int C);
+int bg_sn_power_iter(const float* W, const float* u, float* u_out, float* v, float* sigma,
+                     int K, int C, void* ws, size_t ws_bytes, void* stream);
+int bg_sn_scale(const float* W, const float* sigma, void* out, void* out_t, int dtype,
+                int taps, int rows, int C, void* stream);
+int bg_sn_bwd(const float* W, const float* dWn, const float* u_hat, const float* v_hat,
+              const float* sigma, float* dW, int K, int C, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution family -- ops.py:49-113 (conv), ops.py:116-139 (deconv), ops.py:148-175
+ * (fully_connected == 1x1 conv on a 1x1 map).
+ *   transposed == 0: y = conv2d(pad(x), w[kh,kw,Ci,Co], stride), pad = explicit (pad_t,pad_l,pad_b,
+ *                    pad_r) with REFLECT (tf.pad, ops.py:82) or ZERO fill; w is HWIO.
+ *   transposed == 1: y = tf.nn.conv2d_transpose(x, w[kh,kw,Co,Ci], stride, 'SAME'), output
+ *                    Ho = Hi*stride; pad_t/pad_l = pad_before of the adjoint SAME conv.
+ * (Hi,Wi,Ci) always describe x and (Ho,Wo,Co) describe y, for fwd, dgrad and wgrad alike.
+ * w   : normalised weights in the TF-native layout above, fp32 (BG_F32) or bf16 (BG_BF16)
+ * w_t : per-tap transposed copy (see bg_sn_scale), may be NULL (then only the SIMT path is used)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, Hi, Wi, Ci;
+  int Ho, Wo, Co;
+  int kh, kw, stride;
+  int pad_t, pad_l, pad_b, pad_r;
+  int pad_mode;      /* bg_pad_mode */
+  int transposed;    /* 0 conv, 1 conv2d_transpose */
+} bg_conv_desc;
+
+/* y = act(conv(x) + bias + residual);  bias [Co] fp32 or NULL; residual same shape as y or NULL
+ * (residual may alias y).  force_simt != 0 disables the tensor-core path (testing). */
+int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const void* w_t,
+                  const float* bias, const void* residual, void* y, int act, int dtype,
+                  int force_simt, void* stream);
+/* dx = conv_dgrad(dy) (+ residual).  For pad_mode REFLECT with padding the caller gets the gradient
+ * w.r.t. the *unpadded* x (the reflect-pad adjoint is folded inside; ws holds the padded gradient). */
+size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype);
+int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void* w, const void* w_t,
+                    const void* residual, void* dx, int dtype, void* ws, size_t ws_bytes,
+                    int force_simt, void* stream);
+/* dw (fp32, TF-native layout of w) = wgrad(x, dy); deterministic split-K through ws. */
+size_t bg_conv2d_wgrad_workspace_bytes(const bg_conv_desc* d, int dtype);
+int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x, const void* dy, float* dw, int dtype,
+                    void* ws, size_t ws_bytes, int force_simt, void* stream);
+/* db[C] = sum over rows of dy[rows, C] (bias gradient; tf.nn.bias_add adjoint) */
+size_t bg_colsum_workspace_bytes(long rows, int C);
+int bg_colsum(const void* dy, float* db, long rows, int C, int dtype, void* ws, size_t ws_bytes,
+              void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batch norm family -- ops.py:611-643 (condition_batch_norm), ops.py:580-585 (batch_norm).
+ * x [B, HW, C].  Per-sample partial statistics so that the same kernels serve the local batch and,
+ * after an all-reduce of (sum, sumsq) across ranks, the cross-replica (global batch) statistics.
+ *   bg_bn_stats   : sums[0:C] = sum x, sums[C:2C] = sum x^2 over (B,HW)        (double precision)
+ *   bg_bn_finalize: mean, var(biased) from sums / count; EMA update of the running stats
+ *                   run_mean = run_mean*momentum + mean*(1-momentum); run_var likewise with
+ *                   var*var_correction (1 for ops.py:631-632, n/(n-1) for tf.layers fused BN)
+ *   bg_bn_apply   : y = act((x-mean)*rsqrt(var+eps)*gamma[b] + beta[b]); gamma/beta [B,C] when
+ *                   gb_bstride == C (conditional) or [C] when gb_bstride == 0
+ *   bg_bn_bwd_reduce: dgamma[b,c] = sum_hw g*xhat, dbeta[b,c] = sum_hw g, g = dy*act'(y)
+ *   bg_bn_bwd_sums  : s[0:C] = sum_b gamma*dbeta, s[C:2C] = sum_b gamma*dgamma   (double; all-reduce
+ *                     these across ranks for sync-BN)
+ *   bg_bn_bwd_apply : dx = rstd*(gamma*g - s1/count - xhat*s2/count)
+ * ------------------------------------------------------------------------------------------- */
+size_t bg_bn_workspace_bytes(int B, long HW, int C);
+int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, int dtype, void* ws,
+                size_t ws_bytes, void* stream);
+int bg_bn_finalize(const double* sums, double count, float* mean, float* var, float* run_mean,
+                   float* run_var, float momentum, float var_correction, int C, void* stream);
+int bg_bn_apply(const void* x, const float* mean, const float* var, const float* gamma,
+                const float* beta, int gb_bstride, void* y, int act, float eps, int B, long HW,
+                int C, int dtype, void* stream);
+int bg_bn_bwd_reduce(const void* dy, const void* x, const float* mean, const float* var,
+                     const float* gamma, const float* beta, int gb_bstride, float* dgamma,
+                     float* dbeta, int act, float eps, int B, long HW, int C, int dtype, void* ws,
+                     size_t ws_bytes, void* stream);
+int bg_bn_bwd_sums(const float* dgamma, const float* dbeta, const float* gamma, int gb_bstride,
+                   double* s, int B, int C, void* stream);
+int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* var,
+                    const float* gamma, const float* beta, int gb_bstride, const double* s,
+                    double count, void* dx, int act, float eps, int B, long HW, int C, int dtype,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-attention pieces -- ops.py:467-492 (self_attention_2), ops.py:445-465, ops.py:508-510.
+ * bg_maxpool2_fwd/bwd : 2x2/2 max pooling on [B,H,W,C] (H,W even); bwd routes to the first maximum
+ * bg_bgemm            : C[b] = alpha * op(A[b]) op(B[b]) (+ C[b] if accumulate); generic strides in
+ *                       elements (row stride, col stride, batch stride); fp32 accumulate
+ * bg_softmax_fwd/bwd  : rows of [rows, n]: y = softmax(x);  dx = y*(dy - sum(dy*y))
+ * bg_attn2_fwd/bwd    : fused flash-style softmax(g f^T) h without materialising the scores
+ * ------------------------------------------------------------------------------------------- */
+int bg_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+int bg_maxpool2_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype,
+                    void* stream);
+int bg_bgemm(const void* A, const void* Bm, void* C, int batch, int M, int N, int K,
+             long a_rs, long a_cs, long a_bs, long b_rs, long b_cs, long b_bs, long c_rs, long c_bs,
+             float alpha, int accumulate, int dtype, void* stream);
+int bg_softmax_fwd(const void* x, void* y, long rows, int n, int dtype, void* stream);
+int bg_softmax_bwd(const void* y, const void* dy, void* dx, long rows, int n, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise / small reductions -- ops.py:529-530 (relu), :539-540 (tanh), :503-506
+ * (global_sum_pooling), :490 (gamma*o + x), residual adds of ops.py:198/266/313.
+ * ------------------------------------------------------------------------------------------- */
+int bg_relu_fwd(const void* x, void* y, long n, int dtype, void* stream);
+int bg_relu_bwd(const void* x, const void* dy, void* dx, long n, int dtype, void* stream);   /* dx = dy*(x>0) */
+int bg_tanh_bwd(const void* y, const void* dy, void* dx, long n, int dtype, void* stream);   /* dx = dy*(1-y^2) */
+int bg_add(const void* a, const void* b, void* out, long n, int dtype, void* stream);
+int bg_axpby(const void* x, const void* y, const float* alpha_dev, float alpha, float beta,
+             void* out, long n, int dtype, void* stream);   /* out = (alpha_dev?*alpha_dev:alpha)*x + beta*y */
+int bg_dot(const void* a, const void* b, float* out, long n, int dtype, void* ws, size_t ws_bytes,
+           void* stream);                                    /* out[0] = <a,b> (deterministic) */
+size_t bg_dot_workspace_bytes(long n);
+int bg_sumpool_fwd(const void* x, void* y, int B, long HW, int C, int relu_first, int dtype, void* stream);
+int bg_sumpool_bwd(const void* x, const void* dy, void* dx, int B, long HW, int C, int relu_first,
+                   int dtype, void* stream);
+int bg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long n, void* stream);
+int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr,
+                   int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses -- ops.py:753-797 (discriminator_loss 'hinge'), :799-840 (generator_loss 'hinge'),
+ * :847-848 (flood_loss), utils.py:366-369 (cls_loss_fn 'logistic').  Each writes the scalar loss
+ * (loss[0], fp32) and the gradient w.r.t. its logits; `inv_count` = 1/global batch (data parallel:
+ * local sums scaled by the global count).
+ * ------------------------------------------------------------------------------------------- */
+int bg_hinge_d_fwd_bwd(const void* real, const void* fake, int n_real, int n_fake, float inv_count,
+                       float flood, float* loss, void* dreal, void* dfake, int dtype, void* stream);
+int bg_hinge_g_fwd_bwd(const void* fake, int n, float inv_count, float flood, float* loss,
+                       void* dfake, int dtype, void* stream);
+int bg_logistic_cls_fwd_bwd(const void* logits, const float* labels, const float* cls_w, int B,
+                            int n_labels, float weight, float inv_count, float* loss, void* dlogits,
+                            int accumulate_loss, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DiffAugment -- DiffAugment_tf.py:8-73.  x [B,H,W,C]; per-sample randoms are INPUTS:
+ * rnd_f [3,B] = U[0,1) for brightness, saturation, contrast; rnd_i [4,B] = translation_x,
+ * translation_y, cutout_x, cutout_y (int32, ranges of DiffAugment_tf.py:44-45,:57-58).
+ * flags: bit0 color, bit1 translation, bit2 cutout (applied in that order = policy
+ * 'color,translation,cutout').  mean_ws [B] fp32 scratch for the contrast mean.
+ * ------------------------------------------------------------------------------------------- */
+int bg_diffaug_fwd(const void* x, void* y, const float* rnd_f, const int* rnd_i, int flags, int B,
+                   int H, int W, int C, float* mean_ws, int dtype, void* stream);
+int bg_diffaug_bwd(const void* dy, void* dx, const float* rnd_f, const int* rnd_i, int flags, int B,
+                   int H, int W, int C, float* mean_ws, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer -- tf.train.AdamOptimizer + contrib MovingAverageOptimizer (BigGAN.py:923-926).
+ * One launch over a flat parameter arena: m,v,p(,ema) updated in place from g.
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is computed by the caller.  grad_scale multiplies g first.
+ * ------------------------------------------------------------------------------------------- */
+int bg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float lr_t,
+                     float beta1, float beta2, float eps, float ema_decay, float grad_scale,
+                     void* stream);
+int bg_fill(void* p, float value, long n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIGGAN_B200_H */
