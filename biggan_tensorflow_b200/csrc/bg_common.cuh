@@ -128,7 +128,8 @@ __device__ __forceinline__ double bg_block_sum_d(double v, double* sh /* >= 33 d
 
 // ---------------- gather-GEMM geometry shared by the SIMT and tcgen05 conv kernels -------------
 struct BgTap { short dy, dx; int widx; };
-struct BgPhase { int oy0, ox0, Hp, Wp, ntaps; BgTap taps[16]; };
+#define BG_MAX_TAPS 36
+struct BgPhase { int oy0, ox0, Hp, Wp, ntaps; BgTap taps[BG_MAX_TAPS]; };
 struct BgGeom {
   int B, Hi, Wi, Ci;      // tensor the gather reads (k runs over Ci)
   int Ho, Wo, Co;         // tensor the kernel writes / pairs with (n runs over Co)

@@ -36,7 +36,7 @@ static int build_tconv_phases(BgGeom* g, int Hout, int Wout, int kh, int kw, int
         if (pymod(py + off_y - a, s) != 0) continue;
         for (int c = 0; c < kw; ++c) {
           if (pymod(px + off_x - c, s) != 0) continue;
-          if (p.ntaps >= 16) { bg_set_error("more than 16 taps per phase (k=%dx%d s=%d)", kh, kw, s); return BG_ERR_UNSUPPORTED; }
+          if (p.ntaps >= BG_MAX_TAPS) { bg_set_error("more than %d taps per phase (k=%dx%d s=%d)", BG_MAX_TAPS, kh, kw, s); return BG_ERR_UNSUPPORTED; }
           BgTap& t = p.taps[p.ntaps++];
           t.dy = (short)floordiv(py + off_y - a, s);
           t.dx = (short)floordiv(px + off_x - c, s);
@@ -50,7 +50,7 @@ static int build_tconv_phases(BgGeom* g, int Hout, int Wout, int kh, int kw, int
 
 // plain conv style gather: out[o] = sum_a in[o*s + a - p]
 static int build_conv_phase(BgGeom* g, int Hout, int Wout, int kh, int kw, int s, int pt, int pl) {
-  if (kh * kw > 16) { bg_set_error("kernel %dx%d has more than 16 taps", kh, kw); return BG_ERR_UNSUPPORTED; }
+  if (kh * kw > BG_MAX_TAPS) { bg_set_error("kernel %dx%d has more than %d taps", kh, kw, BG_MAX_TAPS); return BG_ERR_UNSUPPORTED; }
   g->ostep = 1;
   g->istep = s;
   g->nphase = 1;

@@ -307,11 +307,18 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int bg_tc_conv_fwd_type(const BgGeom& g, const bg_conv_desc* d, int op, const void* in, const void* w_k_major,
-                        const float* bias, const void* residual, void* out, int act, cudaStream_t st, int* taken);
+int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
+                     const float* bias, const void* residual, void* out, int act, cudaStream_t st, int* taken);
 int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw,
                      void* ws, size_t ws_bytes, cudaStream_t st, int* taken);
 size_t bg_tc_conv_wgrad_ws(const BgGeom& g, const bg_conv_desc* d);
+
+static bool reflect_padded(const bg_conv_desc* d) {
+  return !d->transposed && d->pad_mode == BG_PAD_REFLECT && (d->pad_t | d->pad_b | d->pad_l | d->pad_r);
+}
+static size_t padded_bytes(const bg_conv_desc* d, size_t es) {
+  return (size_t)d->B * (d->Hi + d->pad_t + d->pad_b) * (d->Wi + d->pad_l + d->pad_r) * d->Ci * es + 256;
+}
 
 template <typename T>
 static int launch_fwd_type(const BgGeom& g, const T* in, const T* w, const float* bias, const T* residual, T* out,
@@ -325,20 +332,35 @@ static int launch_fwd_type(const BgGeom& g, const T* in, const T* w, const float
   return BG_OK;
 }
 
+extern "C" size_t bg_conv2d_fwd_workspace_bytes(const bg_conv_desc* d, int dtype) {
+  return (dtype == BG_BF16 && reflect_padded(d)) ? padded_bytes(d, 2) : 0;
+}
+
 extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const void* w_t, const float* bias,
-                             const void* residual, void* y, int act, int dtype, int force_simt, void* stream) {
+                             const void* residual, void* y, int act, int dtype, void* ws, size_t ws_bytes, int force_simt,
+                             void* stream) {
   BgGeom g;
   int rc = bg_build_geom(d, BG_OP_FWD, &g);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!force_simt && dtype == BG_BF16) {
+  if (!force_simt && dtype == BG_BF16 && bg_has_tensor_core_path()) {
     // K-major B operand [tap][n][k]: transposed conv has it natively, plain conv needs w_t
     const void* wk = d->transposed ? w : w_t;
-    if (wk) {
-      int taken = 0;
-      rc = bg_tc_conv_fwd_type(g, d, BG_OP_FWD, x, wk, bias, residual, y, act, st, &taken);
-      if (rc) return rc;
-      if (taken) return BG_OK;
+    const bool pad = reflect_padded(d);
+    if (wk && (!pad || (ws && ws_bytes >= padded_bytes(d, 2)))) {
+      const void* in = x;
+      int inH = d->Hi, inW = d->Wi, sy = 0, sx = 0;
+      if (pad && g.Ci % 8 == 0 && g.Ci >= 16 && g.Co % 16 == 0) {
+        rc = bg_reflect_pad(x, ws, d->B, d->Hi, d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r, dtype, stream);
+        if (rc) return rc;
+        in = ws; inH += d->pad_t + d->pad_b; inW += d->pad_l + d->pad_r; sy = d->pad_t; sx = d->pad_l;
+      }
+      if (!pad || in == ws) {
+        int taken = 0;
+        rc = bg_tc_fwd_launch(g, in, inH, inW, sy, sx, wk, bias, residual, y, act, st, &taken);
+        if (rc) return rc;
+        if (taken) return BG_OK;
+      }
     }
   }
   BG_DISPATCH_DTYPE(dtype, T, return launch_fwd_type<T>(g, (const T*)x, (const T*)w, bias, (const T*)residual, (T*)y, act, st));
@@ -369,7 +391,7 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
     const void* wk = d->transposed ? w_t : w;     // dgrad contracts over Co: HWIO [tap][ci][co] is K-major natively
     if (wk) {
       int taken = 0;
-      rc = bg_tc_conv_fwd_type(g, d, BG_OP_DGRAD, dy, wk, nullptr, gres, gout, BG_ACT_NONE, st, &taken);
+      rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, gres, gout, BG_ACT_NONE, st, &taken);
       if (rc) return rc;
       done = taken != 0;
     }

@@ -1,8 +1,415 @@
-// placeholder until the tcgen05 path lands
+// tcgen05 / TMEM / TMA implicit-GEMM kernels (bf16 operands, fp32 accumulate) for the dense
+// contractions of the BigGAN step: conv, conv2d_transpose and their dgrad (ops.py:49-139) share ONE
+// forward-type kernel driven by the phase/tap geometry of bg_common.cuh; wgrad has its own kernel.
+//
+// forward-type tile: D[128 output pixels, BN channels] (fp32, TMEM) = sum over taps, 64-channel
+// k-blocks of  A[128 pixels, 64 ch] (TMA box of the NHWC activation, OOB zero-fill = zero padding,
+// SWIZZLE_128B)  x  B[BN, 64 ch] (TMA box of the K-major weights [tap][n][k]).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issue,
+// warps 2-5 = epilogue (tcgen05.ld -> bias / residual / act -> bf16 -> global).
+#include <cuda.h>
+#include <stdlib.h>
 #include "bg_common.cuh"
-int bg_tc_conv_fwd_type(const BgGeom& g, const bg_conv_desc* d, int op, const void* in, const void* w_k_major,
-                        const float* bias, const void* residual, void* out, int act, cudaStream_t st, int* taken) { *taken = 0; return BG_OK; }
-int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw,
-                     void* ws, size_t ws_bytes, cudaStream_t st, int* taken) { *taken = 0; return BG_OK; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i gets row (lane base + i)
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+// K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (=1)
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major, SWIZZLE_128B: 64 MN-elements (128 B) contiguous, K rows 128 B apart, 8-row K groups SBO
+// apart, next 64-element MN block LBO apart
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, M=128
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward-type kernel
+// ------------------------------------------------------------------------------------------------
+#define TC_MAX_TAPS 16
+struct TcTap { int map, dy, dx, widx; };
+struct TcFwdParams {
+  CUtensorMap amap[4];
+  CUtensorMap bmap;
+  int B, Ho, Wo, Co;
+  int nphase, ostep;
+  int bw, bh, bb;            // pixel box (bw*bh*bb == 128)
+  int tw, th, tb;            // tiles per phase
+  int nkb, BN, act, stages;
+  int oy0[4], ox0[4], Hp[4], Wp[4], ntaps[4];
+  TcTap taps[4][TC_MAX_TAPS];
+  const float* bias;
+  const bf16* residual;
+  bf16* out;
+};
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(192, 1) tc_fwd_kernel(const __grid_constant__ TcFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = 16384u + (uint32_t)p.BN * 128u;
+
+  const int tiles_pp = p.tw * p.th * p.tb;
+  const int phase = blockIdx.x / tiles_pp;
+  int t = blockIdx.x - phase * tiles_pp;
+  const int j0 = (t % p.tw) * p.bw; t /= p.tw;
+  const int i0 = (t % p.th) * p.bh; t /= p.th;
+  const int b0 = t * p.bb;
+  const int n0 = blockIdx.y * p.BN;
+  const int ntaps = p.ntaps[phase];
+  const int total = ntaps * p.nkb;
+
+  if (warp == 0 && lane == 0) {
+    for (int m = 0; m < 4; ++m) tma_prefetch_desc(&p.amap[m]);
+    tma_prefetch_desc(&p.bmap);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&accum_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tp = 0; tp < ntaps; ++tp) {
+        const TcTap tap = p.taps[phase][tp];
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t par = (uint32_t)((it / p.stages) & 1);
+          mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          tma_load_4d(sa, &p.amap[tap.map], fb, kb * 64, j0 + tap.dx, i0 + tap.dy, b0);
+          tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.stages;
+        const uint32_t par = (uint32_t)((it / p.stages) & 1);
+        mbar_wait(smem_u32(&full_bar[s]), par);
+        tc_fence_after();
+        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = umma_desc_kmajor_sw128(sa + k * 32);
+          const uint64_t bd = umma_desc_kmajor_sw128(sa + 16384u + k * 32);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int w = row % p.bw, h = (row / p.bw) % p.bh, bl = row / (p.bw * p.bh);
+    const int pi = i0 + h, pj = j0 + w, b = b0 + bl;
+    const bool valid = (b < p.B) && (pi < p.Hp[phase]) && (pj < p.Wp[phase]);
+    const int oy = p.oy0[phase] + pi * p.ostep, ox = p.ox0[phase] + pj * p.ostep;
+    const long obase = (((long)b * p.Ho + oy) * p.Wo + ox) * p.Co + n0;
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (valid) {
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+        if (p.bias) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
+        }
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+          uint4 r0 = rp[0], r1 = rp[1];
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
+            v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
+          }
+        }
+        if (p.act == BG_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (p.act == BG_ACT_TANH) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+        op[0] = o0;
+        op[1] = o1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)f;
+  }
+  return fn;
+}
+
+static bool tc_device_ok() {
+  static int ok = -1;
+  if (ok < 0) {
+    ok = 0;
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+        major == 10 && get_encode() != nullptr)
+      ok = 1;
+    const char* e = getenv("BG_DISABLE_TC");
+    if (e && e[0] == '1') ok = 0;
+  }
+  return ok == 1;
+}
+
+extern "C" int bg_has_tensor_core_path(void) { return tc_device_ok() ? 1 : 0; }
+
+// activation map [B,H,W,C] bf16 sampled with step s starting at parity (pa,pb); box (64, bw, bh, bb)
+static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int s, int pa, int pb, int bw, int bh, int bb) {
+  const int Hs = (H - pa + s - 1) / s, Ws = (W - pb + s - 1) / s;
+  if (Hs <= 0 || Ws <= 0) { memset(m, 0, sizeof(*m)); return BG_OK; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)s * C * 2, (cuuint64_t)s * W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const char* ptr = (const char*)base + ((long)pa * W + pb) * C * 2;
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { bg_set_error("cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d B=%d s=%d)", (int)r, C, Ws, Hs, B, s); return BG_ERR_CUDA; }
+  return BG_OK;
+}
+
+// weights [taps][N][K] bf16, K contiguous; box (64, BN, 1)
+static int make_w_map(CUtensorMap* m, const void* base, int taps, int N, int K, int BN) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { bg_set_error("cuTensorMapEncodeTiled(w) failed: %d (K=%d N=%d taps=%d)", (int)r, K, N, taps); return BG_ERR_CUDA; }
+  return BG_OK;
+}
+
+// pixel box (bw,bh,bb), product `npix`, maximising the fraction of useful rows
+static void choose_box(int Wp, int Hp, int B, int npix, int* bw, int* bh, int* bb) {
+  double best = -1.0;
+  for (int w = 1; w <= npix; w *= 2)
+    for (int h = 1; w * h <= npix; h *= 2) {
+      const int b = npix / (w * h);
+      if (w > 256 || h > 256 || b > 256) continue;
+      const double cover = (double)bg_cdiv(Wp, w) * w * (double)bg_cdiv(Hp, h) * h * (double)bg_cdiv(B, b) * b;
+      const double util = (double)Wp * Hp * B / cover + 1e-9 * w + 1e-12 * h;   // ties: wider boxes
+      if (util > best) { best = util; *bw = w; *bh = h; *bb = b; }
+    }
+}
+
+static int pick_bn(int Co) {
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (Co % bn == 0) return bn;
+  return 0;
+}
+
+static inline int floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
+
+// `in` must already be zero-pad semantics (reflect inputs are pre-padded by the caller, with
+// tap offsets shifted accordingly through pad_shift_y/x).
+int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
+                     const float* bias, const void* residual, void* out, int act, cudaStream_t st, int* taken) {
+  *taken = 0;
+  if (!tc_device_ok()) return BG_OK;
+  if (g.Ci % 8 != 0 || g.Ci < 16 || g.Co % 16 != 0 || g.nphase < 1) return BG_OK;
+  for (int ph = 0; ph < g.nphase; ++ph) {
+    if (g.ph[ph].Hp != g.ph[0].Hp || g.ph[ph].Wp != g.ph[0].Wp) return BG_OK;
+    if (g.ph[ph].ntaps < 1 || g.ph[ph].ntaps > TC_MAX_TAPS) return BG_OK;
+  }
+  if (((uintptr_t)in | (uintptr_t)w_kmajor | (uintptr_t)out | (uintptr_t)residual) & 15) return BG_OK;
+  static TcFwdParams P;      // large struct: keep it off the stack (host calls are single-threaded per process)
+  memset(&P, 0, sizeof(P));
+  const int BN = pick_bn(g.Co);
+  if (BN == 0) return BG_OK;
+  int bw = 128, bh = 1, bb = 1;
+  choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 128, &bw, &bh, &bb);
+  const int s = g.istep;
+  int rc;
+  for (int pa = 0; pa < s; ++pa)
+    for (int pb = 0; pb < s; ++pb)
+      if ((rc = make_act_map(&P.amap[pa * s + pb], in, g.B, in_H, in_W, g.Ci, s, pa, pb, bw, bh, bb))) return rc;
+  for (int m = s * s; m < 4; ++m) P.amap[m] = P.amap[0];
+  int maxw = 0;
+  for (int ph = 0; ph < g.nphase; ++ph)
+    for (int t = 0; t < g.ph[ph].ntaps; ++t) maxw = max(maxw, g.ph[ph].taps[t].widx);
+  if ((rc = make_w_map(&P.bmap, w_kmajor, maxw + 1, g.Co, g.Ci, BN))) return rc;
+  P.B = g.B; P.Ho = g.Ho; P.Wo = g.Wo; P.Co = g.Co;
+  P.nphase = g.nphase; P.ostep = g.ostep;
+  P.bw = bw; P.bh = bh; P.bb = bb;
+  P.tw = (int)bg_cdiv(g.ph[0].Wp, bw); P.th = (int)bg_cdiv(g.ph[0].Hp, bh); P.tb = (int)bg_cdiv(g.B, bb);
+  P.nkb = (int)bg_cdiv(g.Ci, 64);
+  P.BN = BN; P.act = act;
+  const int stage_bytes = 16384 + BN * 128;
+  int stages = (220 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return BG_OK;
+  P.stages = stages;
+  for (int ph = 0; ph < g.nphase; ++ph) {
+    P.oy0[ph] = g.ph[ph].oy0; P.ox0[ph] = g.ph[ph].ox0; P.Hp[ph] = g.ph[ph].Hp; P.Wp[ph] = g.ph[ph].Wp;
+    P.ntaps[ph] = g.ph[ph].ntaps;
+    for (int t = 0; t < g.ph[ph].ntaps; ++t) {
+      const int dy = g.ph[ph].taps[t].dy + shift_y, dx = g.ph[ph].taps[t].dx + shift_x;
+      TcTap& tt = P.taps[ph][t];
+      if (s == 1) { tt.map = 0; tt.dy = dy; tt.dx = dx; }
+      else { const int pa = dy & 1, pb = dx & 1; tt.map = pa * 2 + pb; tt.dy = floordiv2(dy); tt.dx = floordiv2(dx); }
+      tt.widx = g.ph[ph].taps[t].widx;
+    }
+  }
+  P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  dim3 grid((unsigned)(P.tw * P.th * P.tb * g.nphase), (unsigned)(g.Co / BN));
+#define TC_LAUNCH(COLS)                                                                                          \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      BG_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    tc_fwd_kernel<COLS><<<grid, 192, smem, st>>>(P);                                                             \
+  } while (0)
+  if (BN <= 32) TC_LAUNCH(32);
+  else if (BN <= 64) TC_LAUNCH(64);
+  else if (BN <= 128) TC_LAUNCH(128);
+  else TC_LAUNCH(256);
+#undef TC_LAUNCH
+  BG_LAUNCH_CHECK();
+  *taken = 1;
+  return BG_OK;
+}
+
+int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw, void* ws, size_t ws_bytes,
+                     cudaStream_t st, int* taken) {
+  *taken = 0;
+  return BG_OK;
+}
 size_t bg_tc_conv_wgrad_ws(const BgGeom& g, const bg_conv_desc* d) { return 0; }
-extern "C" int bg_has_tensor_core_path(void) { return 0; }

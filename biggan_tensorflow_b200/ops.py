@@ -184,8 +184,10 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
                requires_grad=x.requires_grad or wn.requires_grad or (bias is not None and bias.requires_grad)
                or (residual is not None and residual.requires_grad))
     w_t = wn.aux.get("w_t") if wn.aux else None
+    nbf = query("bg_conv2d_fwd_workspace_bytes", desc, dt)
+    wsf = workspace(nbf) if nbf else None
     call("bg_conv2d_fwd", desc, x.data, wn.data, w_t, bias.data if bias is not None else None,
-         residual.data if residual is not None else None, y.data, act, dt, fs, stream())
+         residual.data if residual is not None else None, y.data, act, dt, wsf, wsf.numel() if nbf else 0, fs, stream())
     if recording(x, wn, bias, residual):
         def bw():
             dy = y.grad
@@ -202,7 +204,7 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
             if residual is not None and residual.requires_grad:
                 accumulate_grad(residual, dy, own=False)
             if wn.requires_grad:
-                dst, fin = grad_target(wn)
+                dst, fin = grad_target(wn, dtype=F32)          # weight gradients are fp32 in every mode
                 nb = query("bg_conv2d_wgrad_workspace_bytes", desc, dt)
                 ws = workspace(nb)
                 call("bg_conv2d_wgrad", desc, x.data, dy, dst, dt, ws, ws.numel(), fs, stream())
@@ -546,11 +548,11 @@ def self_attention(x, channels, opt, scope='self_attention'):
         f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias)
         g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias)
         h = conv(x, channels, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
-        s = matmul(hw_flatten(g), hw_flatten(f), transpose_b=True)
+        s = matmul(cast(hw_flatten(g), F32), cast(hw_flatten(f), F32), transpose_b=True)
         beta = softmax(s)
-        o = matmul(beta, hw_flatten(h))
+        o = matmul(beta, cast(hw_flatten(h), F32))
         gamma = get_variable("gamma", [1], initializer=constant_initializer(0.0))
-        o = reshape(o, x.shape)
+        o = cast(reshape(o, x.shape), x.dtype)
         return _gamma_residual(gamma, o, x)
 
 
@@ -563,11 +565,13 @@ def self_attention_2(x, channels, opt, scope='self_attention'):
         g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias)
         h = conv(x, channels // 2, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
         h = max_pooling(h)
-        s = matmul(hw_flatten(g), hw_flatten(f), transpose_b=True)      # [bs, N, N/4], no 1/sqrt(d)
+        # scores / softmax / PV stay in fp32 in every mode (bf16 storage of the logits would put a
+        # ~|s| * 2^-8 error into the exponent)
+        s = matmul(cast(hw_flatten(g), F32), cast(hw_flatten(f), F32), transpose_b=True)   # [bs, N, N/4], no 1/sqrt(d)
         beta = softmax(s)
-        o = matmul(beta, hw_flatten(h))                                 # [bs, N, C/2]
+        o = matmul(beta, cast(hw_flatten(h), F32))                      # [bs, N, C/2]
         gamma = get_variable("gamma", [1], initializer=constant_initializer(0.0))
-        o = reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2])
+        o = cast(reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2]), x.dtype)
         o = conv(o, channels, kernel=1, stride=1, opt=opt, scope='attn_conv', use_bias=use_bias)
         return _gamma_residual(gamma, o, x)
 
@@ -672,8 +676,11 @@ def _bn_core(x, gamma, beta, gb_bstride, run_mean, run_var, momentum, var_correc
                  B, HW, C, dt, ws2, ws2.numel(), stream())
             if x.requires_grad:
                 s = empty([2 * C], torch.float64)
-                call("bg_bn_bwd_sums", dgamma, dbeta, gamma.data, gb_bstride, s, B, C, stream())
-                dist.all_reduce_sum(s)
+                if opt["is_training"]:
+                    call("bg_bn_bwd_sums", dgamma, dbeta, gamma.data, gb_bstride, s, B, C, stream())
+                    dist.all_reduce_sum(s)
+                else:
+                    s.zero_()                                      # population statistics are constants
                 dst, fin = grad_target(x)
                 call("bg_bn_bwd_apply", dy, x.data, mean, var, gamma.data, beta.data, gb_bstride, s, count, dst, act,
                      eps, B, HW, C, dt, stream())

@@ -123,8 +123,9 @@ def _add_into_grad(t, g):
         t.grad_owned = True
 
 
-def grad_target(t):
+def grad_target(t, dtype=None):
     """Buffer a backward kernel should write d(loss)/d(t) into, and a finisher to call afterwards.
+    `dtype` overrides the gradient storage type (weight gradients are always fp32).
 
     First contribution: written in place (into the parameter's arena slice when it has one).
     Later contributions: written to a temporary and accumulated with bg_add."""
@@ -134,11 +135,11 @@ def grad_target(t):
         t.grad_owned = True
         return t.grad_view, None
     if t.grad is None:
-        t.grad = torch.empty_like(t.data)
+        t.grad = torch.empty_like(t.data, dtype=dtype or t.data.dtype)
         t.grad_set = True
         t.grad_owned = True
         return t.grad, None
-    tmp = torch.empty_like(t.data)
+    tmp = torch.empty_like(t.grad)
     return tmp, (lambda: _add_into_grad(t, tmp))
 
 

@@ -74,10 +74,12 @@ typedef struct {
 } bg_conv_desc;
 
 /* y = act(conv(x) + bias + residual);  bias [Co] fp32 or NULL; residual same shape as y or NULL
- * (residual may alias y).  force_simt != 0 disables the tensor-core path (testing). */
+ * (residual may alias y).  ws: scratch for the reflect-padded bf16 input of the tensor-core path.
+ * force_simt != 0 disables the tensor-core path (testing). */
+size_t bg_conv2d_fwd_workspace_bytes(const bg_conv_desc* d, int dtype);
 int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const void* w_t,
                   const float* bias, const void* residual, void* y, int act, int dtype,
-                  int force_simt, void* stream);
+                  void* ws, size_t ws_bytes, int force_simt, void* stream);
 /* dx = conv_dgrad(dy) (+ residual).  For pad_mode REFLECT with padding the caller gets the gradient
  * w.r.t. the *unpadded* x (the reflect-pad adjoint is folded inside; ws holds the padded gradient). */
 size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype);

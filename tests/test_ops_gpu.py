@@ -50,16 +50,23 @@ def run_case(prod_fn, ref_fn, inputs, dtype, tol=None, fp32_inputs=(), check_sta
         assert xs[k].grad is not None, "no gradient reached input " + k
         assert_close(xs[k].grad.float().cpu().numpy(), g.numpy(), tol, "d/d" + k)
     assert set(st.vars.keys()) == set(rs.vars.keys()), (sorted(set(st.vars) ^ set(rs.vars)))
+    gscale = max([float(g.abs().max()) for g in grads[len(xr):] if g is not None] + [0.0])
     for n, g in zip(tnames, grads[len(xr):]):
         if g is None:
             continue
         pv = st.vars[n]
         assert pv.grad is not None, "no gradient reached variable " + n
+        if n.endswith("f_conv/bias"):
+            # softmax is invariant to a shift of all keys: this gradient is analytically zero and both
+            # sides only hold summation noise
+            assert float(g.abs().max()) <= 1e-9 * max(gscale, 1.0)
+            assert float(pv.grad.float().abs().max()) <= 1e-3 * gscale, n
+            continue
         assert_close(pv.grad.float().cpu().numpy(), g.numpy(), tol, "d/d" + n)
     if check_state:
         for n, v in rs.vars.items():
             if not rs.trainable.get(n, False):
-                assert_close(st.vars[n].data.float().cpu().numpy(), v.detach().numpy(), 1e-4, "state " + n)
+                assert_close(st.vars[n].data.float().cpu().numpy(), v.detach().numpy(), max(TOL[dtype], 1e-4), "state " + n)
     return st, rs
 
 
@@ -112,6 +119,12 @@ CONV_CASES = [
     (2, 8, 16, 16, 3, 2, 1, False, "zero"),
     (1, 4, 128, 128, 3, 1, 1, False, "reflect"),
     (2, 6, 8, 8, 4, 2, 1, False, "reflect"),
+    (4, 16, 128, 192, 3, 1, 1, True, "reflect"),    # tensor-core shapes (bf16 mode): 2 k-blocks, N=192
+    (4, 16, 96, 96, 3, 2, 1, False, "reflect"),     # stride 2 (parity maps), Cin=96 (partial k-block)
+    (2, 32, 64, 64, 3, 1, 1, False, "zero"),
+    (8, 4, 256, 512, 3, 1, 1, False, "reflect"),    # 4x4 map, N tiles of 256
+    (2, 16, 192, 24, 1, 1, 0, True, "reflect"),     # attention 1x1, N=24 (not a multiple of 16 -> SIMT)
+    (2, 16, 192, 96, 1, 1, 0, True, "reflect"),
 ]
 
 
@@ -128,8 +141,9 @@ def test_conv(case, dtype):
              {"x": x}, dtype)
 
 
-DECONV_CASES = [(2, 4, 32, 16, 4, 2), (2, 8, 16, 16, 3, 1), (2, 4, 16, 8, 3, 2), (1, 4, 8, 8, 6, 2),
-                (2, 5, 64, 64, 4, 2), (2, 4, 128, 64, 4, 2), (2, 4, 16, 16, 4, 1)]
+DECONV_CASES = [(2, 4, 32, 16, 4, 2), (2, 8, 16, 16, 3, 1), (2, 4, 16, 8, 3, 2), (1, 4, 8, 8, 6, 2),   # deconv4/3/6
+                (2, 5, 64, 64, 4, 2), (2, 4, 128, 64, 4, 2), (2, 4, 16, 16, 4, 1),
+                (4, 8, 256, 128, 4, 2), (2, 16, 128, 128, 3, 1), (3, 4, 512, 512, 4, 2), (2, 32, 96, 96, 3, 1)]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -256,7 +270,7 @@ def test_resblock_up_condition(dtype):
     z = rng.standard_normal((2, 1, 1, 24)).astype(np.float32)
     run_case(lambda xs: ops.resblock_up_condition(xs["x"], xs["z"], 32, po, use_bias=False, scope="resblock_up_4"),
              lambda rs, xs: R.resblock_up_condition(rs, xs["x"], xs["z"], 32, ro, use_bias=False, scope="resblock_up_4"),
-             {"x": x, "z": z}, dtype, fp32_inputs=("z",), tol_scale=3.0)
+             {"x": x, "z": z}, dtype, fp32_inputs=("z",), tol_scale=4.0)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

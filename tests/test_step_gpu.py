@@ -53,11 +53,15 @@ def test_train_step_matches_oracle(dtype, da_policy):
     assert set(r["prod"].keys()) == set(r["rs"].vars.keys())
     assert abs(r["d_loss"] - r["rd_loss"]) <= tol * max(abs(r["rd_loss"]), 1.0)
     assert abs(r["g_loss"] - r["rg_loss"]) <= tol * max(abs(r["rg_loss"]), 1.0)
-    gtol = tol * (3.0 if dtype == torch.float32 else 4.0)
-    for name, g in r["rd_grads"].items():
-        assert_close(r["d_grads"][name], g.numpy(), gtol, "D grad " + name)
-    for name, g in r["rg_grads"].items():
-        assert_close(r["g_grads"][name], g.numpy(), gtol, "G grad " + name)
+    # whole-network gradients compound the per-op error: 3e-4 (fp32, max-abs) / 4e-2 (bf16, relative L2)
+    gtol = tol * (3.0 if dtype == torch.float32 else 2.0)
+    for which, ref, got in (("D", r["rd_grads"], r["d_grads"]), ("G", r["rg_grads"], r["g_grads"])):
+        gscale = max(float(g.abs().max()) for g in ref.values())
+        for name, g in ref.items():
+            if name.endswith("f_conv/bias"):      # analytically zero (softmax shift invariance)
+                assert np.abs(got[name]).max() <= 1e-3 * gscale, name
+                continue
+            assert_close(got[name], g.numpy(), gtol, which + " grad " + name)
     # state after the iteration: SN u vectors, BN running stats
     for name, v in r["rs"].vars.items():
         if not r["rs"].trainable.get(name, False):
