@@ -335,6 +335,7 @@ static int pick_bn(int Co) {
 
 static inline int floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 
+static int g_cnt_tc_fwd = 0, g_cnt_tc_wgrad = 0;   // launches taken by the tensor-core kernels (tests / bench)
 // `in` must already be zero-pad semantics (reflect inputs are pre-padded by the caller, with
 // tap offsets shifted accordingly through pad_shift_y/x).
 int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
@@ -403,13 +404,250 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   else TC_LAUNCH(256);
 #undef TC_LAUNCH
   BG_LAUNCH_CHECK();
+  g_cnt_tc_fwd++;
   *taken = 1;
   return BG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad kernel: D[128 in-channels, BN out-channels] (fp32, TMEM) = sum over pixel boxes of
+//   A^T[64 pixels, 128 ch] (two 64-channel TMA boxes of the gathered tensor, tap-shifted, OOB = 0)
+//   x B[64 pixels, BN ch] (ceil(BN/64) boxes of the paired tensor).  Both operands are MN-major
+// (the contraction runs over pixels, channels are contiguous): SWIZZLE_128B, LBO = 8192 (next
+// 64-channel block), SBO = 1024 (next 8 pixels).  Deterministic split-K over pixel boxes (grid.z).
+// ------------------------------------------------------------------------------------------------
+struct TcWgParams {
+  CUtensorMap amap[4];
+  CUtensorMap bmap;
+  int bw, bh, bb, tw, th, tb;   // pixel box (product 64) and boxes per grid
+  int Ci, Co, BN, nblkB;        // M total, N total, N tile, 64-channel blocks per B tile
+  int ntile_n, nsplit, nboxes, stages;
+  int ntaps;
+  TcTap taps[TC_MAX_TAPS];
+  float* part;
+  long zstride, wtap, wk;
+};
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant__ TcWgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = 16384u + (uint32_t)p.nblkB * 8192u;
+  const int m0 = (blockIdx.x / p.ntile_n) * 128, n0 = (blockIdx.x % p.ntile_n) * p.BN;
+  const TcTap tap = p.taps[blockIdx.y];
+  const int box_beg = (int)(((long)blockIdx.z * p.nboxes) / p.nsplit);
+  const int box_end = (int)(((long)(blockIdx.z + 1) * p.nboxes) / p.nsplit);
+  const int total = box_end - box_beg;
+
+  if (warp == 0 && lane == 0) {
+    for (int m = 0; m < 4; ++m) tma_prefetch_desc(&p.amap[m]);
+    tma_prefetch_desc(&p.bmap);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&accum_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        int t = box_beg + it;
+        const int j0 = (t % p.tw) * p.bw; t /= p.tw;
+        const int i0 = (t % p.th) * p.bh; t /= p.th;
+        const int b0 = t * p.bb;
+        const int s = it % p.stages;
+        const uint32_t par = (uint32_t)((it / p.stages) & 1);
+        mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, stage_bytes);
+        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+        tma_load_4d(sa, &p.amap[tap.map], fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
+        tma_load_4d(sa + 8192u, &p.amap[tap.map], fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
+        for (int nb = 0; nb < p.nblkB; ++nb)
+          tma_load_4d(sa + 16384u + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.stages;
+        const uint32_t par = (uint32_t)((it / p.stages) & 1);
+        mbar_wait(smem_u32(&full_bar[s]), par);
+        tc_fence_after();
+        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {     // 16 pixels (2 swizzle atoms of 8 rows) per MMA
+          const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, 8192, 1024);
+          const uint64_t bd = umma_desc_mnmajor_sw128(sa + 16384u + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    float* dst = p.part + (long)blockIdx.z * p.zstride + (long)tap.widx * p.wtap + (long)m * p.wk + n0;
+    if (total > 0) {
+      mbar_wait(smem_u32(&accum_bar), 0);
+      tc_fence_after();
+    }
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t r[16];
+      if (total > 0) tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+      }
+      if (m < p.Ci) {
+        float4* o = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                             __uint_as_float(r[4 * e + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+extern "C" int bg_debug_counters(int* tc_fwd, int* tc_wgrad) {
+  if (tc_fwd) *tc_fwd = g_cnt_tc_fwd;
+  if (tc_wgrad) *tc_wgrad = g_cnt_tc_wgrad;
+  return BG_OK;
+}
+
+static int wg_nsplit(int tiles, int nboxes) {
+  long ns = bg_cdiv(2L * bg_num_sms(), tiles);
+  if (ns > nboxes / 4) ns = nboxes / 4;      // keep >= 4 boxes (256 pixels) per CTA
+  if (ns > 64) ns = 64;
+  if (ns < 1) ns = 1;
+  return (int)ns;
+}
+
+struct WgPlan { int ok, BN, bw, bh, bb, tw, th, tb, nboxes, tiles, nsplit; };
+
+static WgPlan wg_plan(const BgGeom& g) {
+  WgPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  if (!tc_device_ok()) return pl;
+  if (g.nphase != 1 || g.ostep != 1 || g.wn != 1) return pl;
+  if (g.Ci % 8 != 0 || g.Ci < 16 || g.Co % 16 != 0 || g.wk % 4 != 0) return pl;
+  if (g.ph[0].ntaps < 1 || g.ph[0].ntaps > TC_MAX_TAPS) return pl;
+  pl.BN = pick_bn(g.Co);
+  if (!pl.BN) return pl;
+  pl.bw = 64; pl.bh = 1; pl.bb = 1;
+  choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 64, &pl.bw, &pl.bh, &pl.bb);
+  pl.tw = (int)bg_cdiv(g.ph[0].Wp, pl.bw); pl.th = (int)bg_cdiv(g.ph[0].Hp, pl.bh); pl.tb = (int)bg_cdiv(g.B, pl.bb);
+  pl.nboxes = pl.tw * pl.th * pl.tb;
+  pl.tiles = (int)(bg_cdiv(g.Ci, 128) * (g.Co / pl.BN) * g.ph[0].ntaps);
+  pl.nsplit = wg_nsplit(pl.tiles, pl.nboxes);
+  pl.ok = 1;
+  return pl;
+}
+
+size_t bg_tc_conv_wgrad_ws(const BgGeom& g, const bg_conv_desc* d) {
+  WgPlan pl = wg_plan(g);
+  if (!pl.ok) return 0;
+  size_t pad = 0;
+  if (!d->transposed && d->pad_mode == BG_PAD_REFLECT && (d->pad_t | d->pad_b | d->pad_l | d->pad_r))
+    pad = ((size_t)d->B * (d->Hi + d->pad_t + d->pad_b) * (d->Wi + d->pad_l + d->pad_r) * d->Ci * 2 + 1023) / 1024 * 1024;
+  size_t part = pl.nsplit > 1 ? (size_t)pl.nsplit * d->kh * d->kw * d->Ci * d->Co * sizeof(float) : 0;
+  return pad + part + 1024;
+}
+
+__global__ void splitk_reduce_kernel2(const float* __restrict__ part, float* __restrict__ dw, long n, long zstride, int nsplit) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float s = 0.f;
+    for (int z = 0; z < nsplit; ++z) s += part[(long)z * zstride + i];
+    dw[i] = s;
+  }
 }
 
 int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw, void* ws, size_t ws_bytes,
                      cudaStream_t st, int* taken) {
   *taken = 0;
+  WgPlan pl = wg_plan(g);
+  if (!pl.ok) return BG_OK;
+  if (((uintptr_t)in | (uintptr_t)og | (uintptr_t)dw) & 15) return BG_OK;
+  if (ws_bytes < bg_tc_conv_wgrad_ws(g, d) || (!ws && bg_tc_conv_wgrad_ws(g, d) > 1024)) return BG_OK;
+  static TcWgParams P;
+  memset(&P, 0, sizeof(P));
+  int rc;
+  // reflect-padded input: pre-pad (the gathered tensor is x for a plain conv)
+  const void* in_ptr = in;
+  int inH = g.Hi, inW = g.Wi, sy = 0, sx = 0;
+  char* wsp = (char*)ws;
+  if (!d->transposed && d->pad_mode == BG_PAD_REFLECT && (d->pad_t | d->pad_b | d->pad_l | d->pad_r)) {
+    rc = bg_reflect_pad(in, wsp, d->B, d->Hi, d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r, BG_BF16, (void*)st);
+    if (rc) return rc;
+    in_ptr = wsp;
+    inH += d->pad_t + d->pad_b; inW += d->pad_l + d->pad_r; sy = d->pad_t; sx = d->pad_l;
+    wsp += ((size_t)d->B * inH * inW * d->Ci * 2 + 1023) / 1024 * 1024;
+  }
+  const int s = g.istep;
+  for (int pa = 0; pa < s; ++pa)
+    for (int pb = 0; pb < s; ++pb)
+      if ((rc = make_act_map(&P.amap[pa * s + pb], in_ptr, g.B, inH, inW, g.Ci, s, pa, pb, pl.bw, pl.bh, pl.bb))) return rc;
+  for (int m = s * s; m < 4; ++m) P.amap[m] = P.amap[0];
+  if ((rc = make_act_map(&P.bmap, og, g.B, g.Ho, g.Wo, g.Co, 1, 0, 0, pl.bw, pl.bh, pl.bb))) return rc;
+  P.bw = pl.bw; P.bh = pl.bh; P.bb = pl.bb; P.tw = pl.tw; P.th = pl.th; P.tb = pl.tb;
+  P.Ci = g.Ci; P.Co = g.Co; P.BN = pl.BN; P.nblkB = (pl.BN + 63) / 64;
+  P.ntile_n = g.Co / pl.BN; P.nsplit = pl.nsplit; P.nboxes = pl.nboxes;
+  const int stage_bytes = 16384 + P.nblkB * 8192;
+  int stages = (220 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  P.stages = stages;
+  P.ntaps = g.ph[0].ntaps;
+  for (int t = 0; t < P.ntaps; ++t) {
+    const int dy = g.ph[0].taps[t].dy + sy, dx = g.ph[0].taps[t].dx + sx;
+    TcTap& tt = P.taps[t];
+    if (s == 1) { tt.map = 0; tt.dy = dy; tt.dx = dx; }
+    else { const int pa = dy & 1, pb = dx & 1; tt.map = pa * 2 + pb; tt.dy = floordiv2(dy); tt.dx = floordiv2(dx); }
+    tt.widx = g.ph[0].taps[t].widx;
+  }
+  const long numel = (long)d->kh * d->kw * d->Ci * d->Co;
+  P.part = pl.nsplit > 1 ? (float*)wsp : dw;
+  P.zstride = numel; P.wtap = g.wtap; P.wk = g.wk;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  dim3 grid((unsigned)(bg_cdiv(g.Ci, 128) * P.ntile_n), (unsigned)P.ntaps, (unsigned)pl.nsplit);
+#define TC_LAUNCH_WG(COLS)                                                                                       \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      BG_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    tc_wgrad_kernel<COLS><<<grid, 192, smem, st>>>(P);                                                           \
+  } while (0)
+  if (pl.BN <= 32) TC_LAUNCH_WG(32);
+  else if (pl.BN <= 64) TC_LAUNCH_WG(64);
+  else if (pl.BN <= 128) TC_LAUNCH_WG(128);
+  else TC_LAUNCH_WG(256);
+#undef TC_LAUNCH_WG
+  BG_LAUNCH_CHECK();
+  if (pl.nsplit > 1) {
+    const int blocks = (int)min(bg_cdiv(numel, 256), (long)bg_num_sms() * 8);
+    splitk_reduce_kernel2<<<blocks, 256, 0, st>>>(P.part, dw, numel, numel, pl.nsplit);
+    BG_LAUNCH_CHECK();
+  }
+  g_cnt_tc_wgrad++;
+  *taken = 1;
   return BG_OK;
 }
-size_t bg_tc_conv_wgrad_ws(const BgGeom& g, const bg_conv_desc* d) { return 0; }

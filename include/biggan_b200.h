@@ -34,6 +34,8 @@ const char* bg_last_error(void);
 int bg_abi_version(void);
 /* 1 if the tcgen05/TMA tensor-core path is usable on the current device (sm_100), else 0 */
 int bg_has_tensor_core_path(void);
+/* number of conv launches served by the tcgen05 forward-type / wgrad kernels so far (tests, bench) */
+int bg_debug_counters(int* tc_fwd, int* tc_wgrad);
 
 /* ---------------------------------------------------------------------------------------------
  * Spectral norm -- ops.py:718-747 (spectral_norm).  W is the [K, C] view `reshape(w, [-1, C])`.

@@ -376,3 +376,41 @@ def test_adam_ema_matches_tf_formula():
     assert_close(tp.cpu().numpy(), p64, 1e-6, "param")
     assert_close(te.cpu().numpy(), e64, 1e-6, "ema")
     assert_close(tv.cpu().numpy(), v64, 1e-6, "v")
+
+
+def _tc_counters():
+    import ctypes
+    from biggan_tensorflow_b200 import _lib
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.lib.bg_debug_counters(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def test_tensor_core_path_is_taken_in_bf16_mode():
+    """The bf16 conv path must run on the tcgen05 kernels (fwd, dgrad, wgrad), not on the SIMT fallback,
+    and must agree with the SIMT kernels on the same bf16 inputs."""
+    from biggan_tensorflow_b200 import _lib, ops
+    assert _lib.lib.bg_has_tensor_core_path() == 1
+    po, _ = _opt()
+    x = np.random.default_rng(20).standard_normal((4, 16, 16, 128)).astype(np.float32)
+    dy = np.random.default_rng(21).standard_normal((4, 16, 16, 192)).astype(np.float32)
+    res = {}
+    for simt in (0, 1):
+        new_product_store(torch.bfloat16)
+        ops.set_force_simt(simt)
+        try:
+            f0, w0 = _tc_counters()
+            tx = dev_tensor(x, torch.bfloat16)
+            y = ops.conv(tx, 192, po, kernel=3, stride=1, pad=1, use_bias=False)
+            seed_backward(y, dy)
+            f1, w1 = _tc_counters()
+        finally:
+            ops.set_force_simt(0)
+        from biggan_tensorflow_b200.tf_shim import get_store
+        res[simt] = (y.numpy(), tx.grad.float().cpu().numpy(), get_store().vars["conv_0/kernel"].grad.cpu().numpy())
+        if simt == 0:
+            assert f1 - f0 == 2 and w1 - w0 == 1, (f0, f1, w0, w1)      # fwd + dgrad, wgrad
+        else:
+            assert f1 == f0 and w1 == w0
+    for a, b, what in zip(res[0], res[1], ("y", "dx", "dw")):
+        assert_close(a, b, 1e-2, "tcgen05 vs SIMT " + what)
