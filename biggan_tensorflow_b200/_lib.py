@@ -89,11 +89,43 @@ def _conv(a):
     return a
 
 
-def call(name, *args):
+_prof = None       # when a list: per-call CUDA-event timing records (name, start, end, flops, tag)
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {name: {"calls", "ms", "flops"}} aggregated over the recorded calls (synchronises)."""
+    global _prof
+    import torch
+    recs, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, flops in recs:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+    return out
+
+
+def call(name, *args, flops=0.0, tag=None):
     """Invoke a status-returning entry point; raise with bg_last_error() on failure."""
     global launch_count
     fn = getattr(lib, name)
-    rc = fn(*[_conv(a) for a in args])
+    cargs = [_conv(a) for a in args]
+    if _prof is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*cargs)
+        e1.record()
+        _prof.append((tag or name, e0, e1, flops))
+    else:
+        rc = fn(*cargs)
     launch_count += 1
     if rc != 0:
         msg = lib.bg_last_error().decode("utf-8", "replace")

@@ -1,0 +1,243 @@
+// Flash-style fused attention core of self_attention_2 (ops.py:481-485): O = softmax(Q K^T) V without
+// materialising the [N, N/4] score / probability tensors, on tcgen05 tensor cores with TMEM accumulators.
+//   Q = hw_flatten(g) [B, Nq, dq], K = hw_flatten(maxpool(f)) [B, Nk, dq], V = hw_flatten(maxpool(h)) [B, Nk, dv]
+// (bf16; dq zero-padded to a multiple of 16).  No 1/sqrt(d) scale (ops.py:481).
+//
+// Forward, one CTA per (image, 128 queries), two passes over the key blocks (Nk <= a few thousand):
+//   pass 1: S_j = Q K_j^T (TMEM) -> row max;   pass 2: S_j again, P_j = exp(S_j - max) -> bf16 tile in
+//   shared memory (128B-swizzled K-major) -> O += P_j V_j (TMEM), row sums.  No accumulator rescaling.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue (one row per thread).
+#include "tc_ptx.cuh"
+
+#define AT_KB 128          // keys per block
+struct AttnFwdParams {
+  CUtensorMap qmap, kmap, vmap;    // (C, rows, B) bf16, box (64, 128, 1)
+  int B, Nq, Nk, dq, dv;
+  int nkb;                         // key blocks
+  int nvblk;                       // 64-channel blocks of V
+  bf16* o;
+  float* lse;
+};
+
+__device__ __forceinline__ void tma_load_3d_g(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  tma_load_3d(dst, tmap, bar, c0, c1, c2);
+}
+
+__global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full, p_empty, o_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t vstage = (uint32_t)p.nvblk * 16384u;
+  const uint32_t Qs = base, Ks = base + 16384u, Vs = Ks + 2u * 16384u, Ps = Vs + 2u * vstage;
+  const int b = blockIdx.y, q0 = blockIdx.x * 128;
+  const int T = 2 * p.nkb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap);
+    mbar_init(smem_u32(&q_full), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&k_full[i]), 1); mbar_init(smem_u32(&k_empty[i]), 1);
+      mbar_init(smem_u32(&v_full[i]), 1); mbar_init(smem_u32(&v_empty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 4);
+    }
+    mbar_init(smem_u32(&p_full), 4); mbar_init(smem_u32(&p_empty), 1); mbar_init(smem_u32(&o_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tS[2] = {tmem, tmem + 128u};
+  const uint32_t tO = tmem + 256u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&q_full), 16384u);
+      tma_load_3d(Qs, &p.qmap, smem_u32(&q_full), 0, q0, b);
+      for (int it = 0; it < T; ++it) {
+        const int j = it % p.nkb, s = it & 1;
+        mbar_wait(smem_u32(&k_empty[s]), (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_expect_tx(smem_u32(&k_full[s]), 16384u);
+        tma_load_3d(Ks + (uint32_t)s * 16384u, &p.kmap, smem_u32(&k_full[s]), 0, j * AT_KB, b);
+        if (it >= p.nkb) {
+          const int jj = it - p.nkb, vs = jj & 1;
+          mbar_wait(smem_u32(&v_empty[vs]), (uint32_t)(((jj >> 1) & 1) ^ 1));
+          mbar_expect_tx(smem_u32(&v_full[vs]), vstage);
+          for (int c = 0; c < p.nvblk; ++c)
+            tma_load_3d(Vs + (uint32_t)vs * vstage + (uint32_t)c * 16384u, &p.vmap, smem_u32(&v_full[vs]), c * 64, j * AT_KB, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, AT_KB, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, p.dv, 0, 1);
+      const int ksteps = p.dq / 16;
+      mbar_wait(smem_u32(&q_full), 0);
+      for (int it = 0; it <= T; ++it) {
+        if (it < T) {
+          const int s = it & 1;
+          mbar_wait(smem_u32(&k_full[s]), (uint32_t)((it >> 1) & 1));
+          mbar_wait(smem_u32(&s_empty[s]), (uint32_t)(((it >> 1) & 1) ^ 1));
+          tc_fence_after();
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tS[s], umma_desc_kmajor_sw128(Qs + k * 32), umma_desc_kmajor_sw128(Ks + (uint32_t)s * 16384u + k * 32), idesc_s,
+                      k ? 1u : 0u);
+          umma_commit(smem_u32(&s_full[s]));
+          umma_commit(smem_u32(&k_empty[s]));
+        }
+        const int pv = it - 1 - p.nkb;            // the P V product of the previous (pass-2) iteration
+        if (pv >= 0) {
+          const int vs = pv & 1;
+          mbar_wait(smem_u32(&v_full[vs]), (uint32_t)((pv >> 1) & 1));
+          mbar_wait(smem_u32(&p_full), (uint32_t)(pv & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < AT_KB / 16; ++k) {
+            const uint64_t ad = umma_desc_kmajor_sw128(Ps + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
+            const uint64_t bd = umma_desc_mnmajor_sw128(Vs + (uint32_t)vs * vstage + (uint32_t)k * 2048u, 16384u, 1024u);
+            umma_bf16(tO, ad, bd, idesc_o, (pv | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&p_empty));
+          umma_commit(smem_u32(&v_empty[vs]));
+        }
+      }
+      umma_commit(smem_u32(&o_full));
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    float m = -INFINITY, sum = 0.f, sum_true = 0.f;
+    for (int it = 0; it < T; ++it) {
+      const int j = it % p.nkb, s = it & 1;
+      const bool pass2 = it >= p.nkb;
+      mbar_wait(smem_u32(&s_full[s]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      if (pass2) mbar_wait(smem_u32(&p_empty), (uint32_t)(((it - p.nkb) & 1) ^ 1));
+      for (int c0 = 0; c0 < AT_KB; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(tS[s] + lane_base + (uint32_t)c0, r);
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          v[e] = __uint_as_float(r[e]);
+          if (j * AT_KB + c0 + e >= p.Nk) v[e] = -INFINITY;
+        }
+        if (!pass2) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) m = fmaxf(m, v[e]);
+        } else {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float p0 = exp2f((v[2 * e] - m) * LOG2E), p1 = exp2f((v[2 * e + 1] - m) * LOG2E);
+            __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            sum += __low2float(h) + __high2float(h);       // normalise O by what the MMA actually sees
+            sum_true += p0 + p1;                            // exact normaliser for the saved log-sum-exp
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          // P[row][c0..c0+15] -> K-major SWIZZLE_128B tile(s): 16-byte chunk index XOR (row & 7)
+          const uint32_t kb = (uint32_t)(c0 >> 6), ch = (uint32_t)((c0 & 63) >> 3);
+          const uint32_t rbase = Ps + kb * 16384u + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+          const uint32_t a0 = rbase + ((ch ^ (uint32_t)(row & 7)) << 4), a1 = rbase + (((ch + 1) ^ (uint32_t)(row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        }
+      }
+      tc_fence_before();
+      if (pass2) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&s_empty[s]));
+        if (pass2) mbar_arrive(smem_u32(&p_full));
+      }
+    }
+    mbar_wait(smem_u32(&o_full), 0);
+    tc_fence_after();
+    const int qi = q0 + row;
+    const float inv = 1.f / sum;
+    for (int c0 = 0; c0 < p.dv; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_x16(tO + lane_base + (uint32_t)c0, r);
+      if (qi < p.Nq) {
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h0[e] = __floats2bfloat162_rn(__uint_as_float(r[2 * e]) * inv, __uint_as_float(r[2 * e + 1]) * inv);
+          h1[e] = __floats2bfloat162_rn(__uint_as_float(r[8 + 2 * e]) * inv, __uint_as_float(r[8 + 2 * e + 1]) * inv);
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.o + ((long)b * p.Nq + qi) * p.dv + c0);
+        op[0] = o0; op[1] = o1;
+      }
+    }
+    if (qi < p.Nq) p.lse[(long)b * p.Nq + qi] = m + logf(sum_true);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled2 attn_encode() {
+  static PFN_tmapEncodeTiled2 fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled2)f;
+  }
+  return fn;
+}
+
+// [B, rows, C] bf16 -> 3D map (C, rows, B), box (64, box_rows, 1), 128B swizzle, zero OOB fill
+int bg_attn_make_map(CUtensorMap* m, const void* base, int B, int rows, int C, int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  PFN_tmapEncodeTiled2 enc = attn_encode();
+  if (!enc) { bg_set_error("cuTensorMapEncodeTiled unavailable"); return BG_ERR_CUDA; }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { bg_set_error("cuTensorMapEncodeTiled(attn) failed: %d (C=%d rows=%d B=%d)", (int)r, C, rows, B); return BG_ERR_CUDA; }
+  return BG_OK;
+}
+
+extern "C" int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk, int dq, int dv,
+                            void* stream) {
+  BG_REQUIRE(bg_has_tensor_core_path(), BG_ERR_UNSUPPORTED, "attn2: tensor-core path unavailable on this device");
+  BG_REQUIRE(dq % 16 == 0 && dq >= 16 && dq <= 64, BG_ERR_UNSUPPORTED, "attn2: dq=%d must be 16..64, multiple of 16", dq);
+  BG_REQUIRE(dv % 16 == 0 && dv >= 16 && dv <= 256, BG_ERR_UNSUPPORTED, "attn2: dv=%d must be 16..256, multiple of 16", dv);
+  BG_REQUIRE(B > 0 && Nq > 0 && Nk > 0 && B <= 65535, BG_ERR_SHAPE, "attn2: bad shape");
+  static AttnFwdParams P;
+  memset(&P, 0, sizeof(P));
+  int rc;
+  if ((rc = bg_attn_make_map(&P.qmap, q, B, Nq, dq, 128))) return rc;
+  if ((rc = bg_attn_make_map(&P.kmap, k, B, Nk, dq, AT_KB))) return rc;
+  if ((rc = bg_attn_make_map(&P.vmap, v, B, Nk, dv, AT_KB))) return rc;
+  P.B = B; P.Nq = Nq; P.Nk = Nk; P.dq = dq; P.dv = dv;
+  P.nkb = (int)bg_cdiv(Nk, AT_KB);
+  P.nvblk = (dv + 63) / 64;
+  P.o = (bf16*)o; P.lse = lse;
+  const size_t smem = 16384 + 2 * 16384 + 2 * (size_t)P.nvblk * 16384 + 32768 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)bg_cdiv(Nq, 128), (unsigned)B);
+  attn_fwd_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(P);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

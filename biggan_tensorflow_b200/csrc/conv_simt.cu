@@ -320,9 +320,21 @@ static size_t padded_bytes(const bg_conv_desc* d, size_t es) {
   return (size_t)d->B * (d->Hi + d->pad_t + d->pad_b) * (d->Wi + d->pad_l + d->pad_r) * d->Ci * es + 256;
 }
 
+int bg_small_fwd(const BgGeom& g, const void* in, const void* w, const float* bias, const void* residual, void* out, int act, int dtype,
+                 cudaStream_t st, int* taken);
+size_t bg_small_wgrad_ws(const BgGeom& g, long numel);
+int bg_small_wgrad(const BgGeom& g, const void* in, const void* og, float* dw, long numel, int dtype, void* ws, size_t ws_bytes,
+                   cudaStream_t st, int* taken);
+
 template <typename T>
 static int launch_fwd_type(const BgGeom& g, const T* in, const T* w, const float* bias, const T* residual, T* out,
                            int act, cudaStream_t st) {
+  if (g.Co <= 4 || g.Ci <= 4) {      // RGB layers: memory-bound direct kernels (conv_small.cu)
+    int taken = 0;
+    int rc = bg_small_fwd(g, in, w, bias, residual, out, act, sizeof(T) == 4 ? BG_F32 : BG_BF16, st, &taken);
+    if (rc) return rc;
+    if (taken) return BG_OK;
+  }
   long maxM = 0;
   for (int p = 0; p < g.nphase; ++p) maxM = max(maxM, (long)g.B * g.ph[p].Hp * g.ph[p].Wp);
   const int tiles = (int)bg_cdiv(maxM, GF_BM);
@@ -427,6 +439,8 @@ extern "C" size_t bg_conv2d_wgrad_workspace_bytes(const bg_conv_desc* d, int dty
   if (bg_build_geom(d, BG_OP_WGRAD, &g)) return 0;
   size_t simt = (size_t)wgrad_nsplit(g) * wgrad_numel(d) * sizeof(float);
   size_t tc = dtype == BG_BF16 ? bg_tc_conv_wgrad_ws(g, d) : 0;
+  size_t sm = bg_small_wgrad_ws(g, wgrad_numel(d));
+  if (sm > simt) simt = sm;
   return (simt > tc ? simt : tc) + 256;
 }
 
@@ -444,8 +458,14 @@ extern "C" int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x, const void*
     if (rc) return rc;
     if (taken) return BG_OK;
   }
-  const int ns = wgrad_nsplit(g);
   const long numel = wgrad_numel(d);
+  if (g.Co <= 4 || g.Ci <= 4) {
+    int taken = 0;
+    rc = bg_small_wgrad(g, in, og, dw, numel, dtype, ws, ws_bytes, st, &taken);
+    if (rc) return rc;
+    if (taken) return BG_OK;
+  }
+  const int ns = wgrad_nsplit(g);
   float* part = dw;
   if (ns > 1) {
     BG_REQUIRE(ws && ws_bytes >= (size_t)ns * numel * sizeof(float), BG_ERR_WORKSPACE, "wgrad workspace too small");

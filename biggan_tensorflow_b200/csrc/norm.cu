@@ -6,8 +6,9 @@
 
 #define BN_CPB 128   // channels per block (32 lanes x 4)
 
-static inline int bn_nchunk(long rows, int C) {
-  long want = bg_cdiv(8L * bg_num_sms(), bg_cdiv(C, BN_CPB));
+static inline int bn_nchunk(int B, long rows, int C) {
+  // chunks of one sample's HW rows; B * nchunk * channel-blocks ~ 8 CTAs per SM
+  long want = bg_cdiv(8L * bg_num_sms(), (long)B * bg_cdiv(C, BN_CPB));
   long mx = bg_cdiv(rows, 32);
   long n = want < mx ? want : mx;
   if (n < 1) n = 1;
@@ -102,7 +103,7 @@ __global__ void bn_bwd_final_kernel(const float* __restrict__ part, float* __res
 }
 
 extern "C" size_t bg_bn_workspace_bytes(int B, long HW, int C) {
-  return (size_t)B * bn_nchunk(HW, C) * 2 * C * sizeof(float) + 256;
+  return (size_t)B * bn_nchunk(B, HW, C) * 2 * C * sizeof(float) + 256;
 }
 
 extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, int dtype, void* ws, size_t ws_bytes,
@@ -110,7 +111,7 @@ extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, i
   BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
   BG_REQUIRE(ws && ws_bytes >= bg_bn_workspace_bytes(B, HW, C), BG_ERR_WORKSPACE, "bn workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nchunk = bn_nchunk(HW, C);
+  const int nchunk = bn_nchunk(B, HW, C);
   dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
   BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0,
                                                                         0.f, (float*)ws, HW, C, nchunk));
@@ -184,7 +185,7 @@ extern "C" int bg_bn_bwd_reduce(const void* dy, const void* x, const float* mean
   BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
   BG_REQUIRE(ws && ws_bytes >= bg_bn_workspace_bytes(B, HW, C), BG_ERR_WORKSPACE, "bn workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nchunk = bn_nchunk(HW, C);
+  const int nchunk = bn_nchunk(B, HW, C);
   dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
   BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, mean, var, gamma, beta, gb_bstride,
                                                                         act, eps, (float*)ws, HW, C, nchunk));

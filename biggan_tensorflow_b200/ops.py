@@ -176,6 +176,18 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False):
 # Convolution family (ops.py:49-139, :148-175)
 ##################################################################################
 
+def _conv_flops(d):
+    """Algorithmic FLOPs: conv 2 k^2 Cin Cout Hout Wout, deconv 2 k^2 Cin Cout Hin Win."""
+    pix = d.B * (d.Hi * d.Wi if d.transposed else d.Ho * d.Wo)
+    return 2.0 * d.kh * d.kw * d.Ci * d.Co * pix
+
+
+def _conv_tag(d):
+    if d.Hi == 1 and d.Wi == 1 and d.kh == 1:
+        return "[fc]"
+    return "[%s k%d s%d %dx%d %d>%d b%d]" % ("deconv" if d.transposed else "conv", d.kh, d.stride, d.Hi, d.Wi, d.Ci, d.Co, d.B)
+
+
 def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
     """y = act(conv(x; wn) + bias + residual) and its tape entry (dgrad / wgrad / bias grad)."""
     dt = bg_dtype(x)
@@ -187,7 +199,8 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
     nbf = query("bg_conv2d_fwd_workspace_bytes", desc, dt)
     wsf = workspace(nbf) if nbf else None
     call("bg_conv2d_fwd", desc, x.data, wn.data, w_t, bias.data if bias is not None else None,
-         residual.data if residual is not None else None, y.data, act, dt, wsf, wsf.numel() if nbf else 0, fs, stream())
+         residual.data if residual is not None else None, y.data, act, dt, wsf, wsf.numel() if nbf else 0, fs, stream(),
+         flops=_conv_flops(desc), tag="conv_fwd" + _conv_tag(desc))
     if recording(x, wn, bias, residual):
         def bw():
             dy = y.grad
@@ -207,7 +220,8 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
                 dst, fin = grad_target(wn, dtype=F32)          # weight gradients are fp32 in every mode
                 nb = query("bg_conv2d_wgrad_workspace_bytes", desc, dt)
                 ws = workspace(nb)
-                call("bg_conv2d_wgrad", desc, x.data, dy, dst, dt, ws, ws.numel(), fs, stream())
+                call("bg_conv2d_wgrad", desc, x.data, dy, dst, dt, ws, ws.numel(), fs, stream(),
+                     flops=_conv_flops(desc), tag="conv_wgrad" + _conv_tag(desc))
                 if fin:
                     fin()
             if bias is not None and bias.requires_grad:
@@ -227,7 +241,8 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
                     dx = res                      # fused accumulate in the dgrad epilogue
                 else:
                     dx = torch.empty_like(x.data)
-                call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, res, dx, dt, ws, ws.numel() if nb else 0, fs, stream())
+                call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, res, dx, dt, ws, ws.numel() if nb else 0, fs, stream(),
+                     flops=_conv_flops(desc), tag="conv_dgrad" + _conv_tag(desc))
                 x.grad, x.grad_owned, x.grad_set = dx, True, True
         record(bw)
     return y
@@ -471,7 +486,7 @@ def matmul(a, b, transpose_b=False):
     else:               # b [B, K, N]
         b_rs, b_cs = N, 1
     call("bg_bgemm", a.data, b.data, y.data, Bn, M, N, K, K, 1, M * K, b_rs, b_cs, b.numel() // Bn,
-         N, M * N, 1.0, 0, dt, stream())
+         N, M * N, 1.0, 0, dt, stream(), flops=2.0 * Bn * M * N * K, tag="attn_bgemm_fwd")
     if recording(a, b):
         def bw():
             dy = y.grad

@@ -137,8 +137,13 @@ int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const floa
  * bg_bgemm            : C[b] = alpha * op(A[b]) op(B[b]) (+ C[b] if accumulate); generic strides in
  *                       elements (row stride, col stride, batch stride); fp32 accumulate
  * bg_softmax_fwd/bwd  : rows of [rows, n]: y = softmax(x);  dx = y*(dy - sum(dy*y))
- * bg_attn2_fwd/bwd    : fused flash-style softmax(g f^T) h without materialising the scores
+ * bg_attn2_fwd/bwd    : fused flash-style softmax(g f^T) h without materialising the scores (bf16 mode)
  * ------------------------------------------------------------------------------------------- */
+/* q [B,Nq,dq], k [B,Nk,dq], v [B,Nk,dv] bf16 (dq a multiple of 16 <= 64: zero-pad the channels; dv a
+ * multiple of 16 <= 128).  o [B,Nq,dv] bf16 = softmax(q k^T) v, lse [B,Nq] fp32 = log sum exp of the scores
+ * (saved for the backward).  tcgen05 kernels only (no fallback): BG_ERR_UNSUPPORTED elsewhere. */
+int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk,
+                 int dq, int dv, void* stream);
 int bg_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 int bg_maxpool2_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype,
                     void* stream);

@@ -1,0 +1,32 @@
+"""Fused flash-style attention core (tcgen05) of self_attention_2 (ops.py:481-485) vs a float64 reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v):
+    s = torch.einsum("bic,bjc->bij", q, k)
+    p = torch.softmax(s, dim=-1)
+    return p @ v, torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("B,Nq,Nk,dq,dv", [(2, 256, 64, 16, 16), (3, 1024, 256, 32, 96), (2, 4096, 1024, 32, 96),
+                                           (2, 4096, 1024, 16, 48), (1, 64, 16, 16, 32), (2, 320, 80, 32, 64)])
+def test_attn2_forward(B, Nq, Nk, dq, dv):
+    from biggan_tensorflow_b200._lib import call
+    from biggan_tensorflow_b200.tensor import stream
+    rng = np.random.default_rng(0)
+    q = torch.from_numpy(rng.standard_normal((B, Nq, dq)).astype(np.float32)).cuda().bfloat16()
+    k = torch.from_numpy(rng.standard_normal((B, Nk, dq)).astype(np.float32)).cuda().bfloat16()
+    v = torch.from_numpy(rng.standard_normal((B, Nk, dv)).astype(np.float32)).cuda().bfloat16()
+    o = torch.empty(B, Nq, dv, dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty(B, Nq, dtype=torch.float32, device="cuda")
+    call("bg_attn2_fwd", q, k, v, o, lse, B, Nq, Nk, dq, dv, stream())
+    torch.cuda.synchronize()
+    ro, rl = _ref(q.double().cpu(), k.double().cpu(), v.double().cpu())
+    assert_close(lse.cpu().numpy(), rl.numpy(), 1e-5, "lse")
+    assert_close(o.float().cpu().numpy(), ro.numpy(), 2e-2, "o")
