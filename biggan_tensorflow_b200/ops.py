@@ -128,7 +128,7 @@ Tensor.__rmul__ = lambda a, b: scale(a, b)
 # Spectral norm (ops.py:718-747)
 ##################################################################################
 
-def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False):
+def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_c=0):
     """w: Variable [..., C].  Returns W/sigma (same shape) after one power-iteration step; the
     persistent `u` (created in the current scope, ops.py:722) is advanced in place (ops.py:743).
     Evaluated once per update phase and variable (SURVEY 8a row 3 state semantics)."""
@@ -140,7 +140,8 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False):
     K = w.numel() // C
     u = get_variable("u", [1, C], initializer=random_normal_initializer(), trainable=False)
     out_dtype = _out_dtype or F32
-    key = (u.name, out_dtype, bool(_want_t))
+    c_pad = max(int(_pad_c), C)      # zero-padded output channels (tensor-core eligibility of narrow convs)
+    key = (u.name, out_dtype, bool(_want_t), c_pad)
     hit = store.sn_cache.get(key)
     if hit is not None:
         return hit
@@ -153,10 +154,12 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False):
         base = (v_hat, sigma)
         store.sn_cache[("pi", u.name)] = base
     v_hat, sigma = base
-    wn = Tensor(empty(w_shape, out_dtype), requires_grad=w.requires_grad)
-    w_t = empty(w_shape, out_dtype) if _want_t else None
+    p_shape = w_shape[:-1] + [c_pad]
+    alloc = empty if c_pad == C else (lambda sh, dt: torch.zeros(tuple(sh), dtype=dt, device=w.data.device))
+    wn = Tensor(alloc(p_shape, out_dtype), requires_grad=w.requires_grad)
+    w_t = alloc(p_shape, out_dtype) if _want_t else None
     rows = K // _taps
-    call("bg_sn_scale", w.data, sigma, wn.data, w_t, bg_dtype(out_dtype), _taps, rows, C, stream())
+    call("bg_sn_scale", w.data, sigma, wn.data, w_t, bg_dtype(out_dtype), _taps, rows, C, c_pad, stream())
     wn.aux = {"w_t": w_t, "sigma": sigma, "v_hat": v_hat, "u_hat": u.data}
     store.sn_cache[key] = wn
     if recording(w):
@@ -165,7 +168,7 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False):
                 return
             dst, fin = grad_target(w)
             ws2 = workspace(query("bg_sn_workspace_bytes", K, C))
-            call("bg_sn_bwd", w.data, wn.grad, u.data, v_hat, sigma, dst, K, C, ws2, ws2.numel(), stream())
+            call("bg_sn_bwd", w.data, wn.grad, c_pad, u.data, v_hat, sigma, dst, K, C, ws2, ws2.numel(), stream())
             if fin:
                 fin()
         record(bw)
@@ -248,11 +251,24 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
     return y
 
 
-def _sn_weight(w, taps, conv_like, x_dtype):
+def _sn_weight(w, taps, conv_like, x_dtype, pad_c=0):
     """Normalised weights in the layout(s) the conv kernels want."""
     if x_dtype == BF16:
-        return spectral_norm(w, _out_dtype=BF16, _taps=taps, _want_t=True)
-    return spectral_norm(w, _out_dtype=F32, _taps=taps)
+        return spectral_norm(w, _out_dtype=BF16, _taps=taps, _want_t=True, _pad_c=pad_c)
+    return spectral_norm(w, _out_dtype=F32, _taps=taps, _pad_c=pad_c)
+
+
+def _padded_bias(bias, c_pad):
+    """Zero-padded copy of a bias vector (plumbing) whose gradient flows back to the first C entries."""
+    C = bias.shape[0]
+    pb = Tensor(torch.zeros(c_pad, dtype=F32, device=bias.data.device), requires_grad=bias.requires_grad)
+    pb.data[:C].copy_(bias.data)
+    if recording(bias):
+        def bw():
+            if pb.grad is not None:
+                accumulate_grad(bias, pb.grad[:C].contiguous(), own=True)
+        record(bw)
+    return pb
 
 
 def _conv_geometry(x, channels, kernel, stride, pad, opt):
@@ -289,7 +305,7 @@ def _conv_geometry(x, channels, kernel, stride, pad, opt):
 
 
 def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True, scope='conv_0',
-         _residual=None, _act=_lib.ACT_NONE):
+         _residual=None, _act=_lib.ACT_NONE, _pad_cout_to=0):
     """ops.py:49-113."""
     with variable_scope(scope):
         if isinstance(kernel, str):
@@ -300,10 +316,14 @@ def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True,
         if not opt.get("conv", {}).get("sn", True):
             raise ValueError("conv with sn=False (tf.layers.conv2d path) is not supported")
         w = get_variable("kernel", shape=[kernel, kernel, x.shape[-1], channels], initializer=weight_init)
-        wn = _sn_weight(w, kernel * kernel, True, x.dtype)
+        c_pad = round_up(channels, _pad_cout_to) if _pad_cout_to else channels
+        wn = _sn_weight(w, kernel * kernel, True, x.dtype, pad_c=c_pad)
         bias = None
         if use_bias:
             bias = get_variable("bias", [channels], initializer=constant_initializer(0.0))
+            if c_pad != channels:
+                bias = _padded_bias(bias, c_pad)
+        desc.Co = c_pad          # extra output channels are exactly zero (zero weights, zero bias)
         return _conv_op(x, wn, bias, desc, act=_act, residual=_residual)
 
 
@@ -571,22 +591,52 @@ def self_attention(x, channels, opt, scope='self_attention'):
         return _gamma_residual(gamma, o, x)
 
 
+def _attn2_fused(q, k, v):
+    """softmax(q k^T) v with the flash-style tcgen05 kernels (no [N, N/4] tensor is materialised)."""
+    Bn, Nq, dq = q.shape
+    Nk, dv = k.shape[1], v.shape[2]
+    o = Tensor(empty([Bn, Nq, dv], BF16), requires_grad=q.requires_grad or k.requires_grad or v.requires_grad)
+    lse = empty([Bn, Nq], F32)
+    call("bg_attn2_fwd", q.data, k.data, v.data, o.data, lse, Bn, Nq, Nk, dq, dv, stream(),
+         flops=2.0 * Bn * Nq * Nk * (dq + dv), tag="attn2_fwd")
+    if recording(q, k, v):
+        def bw():
+            if o.grad is None:
+                return
+            gq, gk, gv = torch.empty_like(q.data), torch.empty_like(k.data), torch.empty_like(v.data)
+            delta = empty([Bn, Nq], F32)
+            call("bg_attn2_bwd", q.data, k.data, v.data, o.data, o.grad.contiguous(), lse, delta, gq, gk, gv, Bn, Nq, Nk, dq, dv,
+                 stream(), flops=2.0 * Bn * Nq * Nk * (3 * dq + 4 * dv), tag="attn2_bwd")
+            for t, g in ((q, gq), (k, gk), (v, gv)):
+                if t.requires_grad:
+                    accumulate_grad(t, g, own=True)
+        record(bw)
+    return o
+
+
 def self_attention_2(x, channels, opt, scope='self_attention'):
     """ops.py:467-492 (the live block: 2x2 max-pooled keys/values, C/8 q/k, C/2 v, 1x1 out conv)."""
     with variable_scope(scope):
         use_bias = opt.get("self_attention_bias", False)
-        f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias)
+        fused = (x.dtype == BF16 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1
+                 and (channels // 2) % 16 == 0 and channels // 2 <= 128 and channels // 8 <= 64)
+        pad = 16 if fused else 0      # q/k channels zero-padded to a multiple of 16 for the tensor cores
+        f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias, _pad_cout_to=pad)
         f = max_pooling(f)
-        g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias)
+        g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias, _pad_cout_to=pad)
         h = conv(x, channels // 2, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
         h = max_pooling(h)
-        # scores / softmax / PV stay in fp32 in every mode (bf16 storage of the logits would put a
-        # ~|s| * 2^-8 error into the exponent)
-        s = matmul(cast(hw_flatten(g), F32), cast(hw_flatten(f), F32), transpose_b=True)   # [bs, N, N/4], no 1/sqrt(d)
-        beta = softmax(s)
-        o = matmul(beta, cast(hw_flatten(h), F32))                      # [bs, N, C/2]
+        if fused:
+            o = _attn2_fused(hw_flatten(g), hw_flatten(f), hw_flatten(h))           # [bs, N, C/2]
+            o = reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2])
+        else:
+            # scores / softmax / PV in fp32 (bf16 storage of the logits would put a ~|s| * 2^-8 error
+            # into the exponent)
+            s = matmul(cast(hw_flatten(g), F32), cast(hw_flatten(f), F32), transpose_b=True)   # [bs, N, N/4], no 1/sqrt(d)
+            beta = softmax(s)
+            o = matmul(beta, cast(hw_flatten(h), F32))                      # [bs, N, C/2]
+            o = cast(reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2]), x.dtype)
         gamma = get_variable("gamma", [1], initializer=constant_initializer(0.0))
-        o = cast(reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2]), x.dtype)
         o = conv(o, channels, kernel=1, stride=1, opt=opt, scope='attn_conv', use_bias=use_bias)
         return _gamma_residual(gamma, o, x)
 

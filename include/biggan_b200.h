@@ -43,16 +43,18 @@ int bg_debug_counters(int* tc_fwd, int* tc_wgrad);
  *   v_hat -> v[K], u_hat -> u_out[C] (may alias u), sigma[0].   One HBM read of W (+ L2 re-read).
  * bg_sn_scale: out = W / sigma in `dtype`; if out_t != NULL also writes the per-tap transposed copy
  *   out_t[t][c][r] for W viewed as [taps][rows][C] (K = taps*rows) -- the K-major operand layout of
- *   the tcgen05 conv kernels.
+ *   the tcgen05 conv kernels.  c_pad >= C: output channel count of the (pre-zeroed) destination
+ *   buffers -- out rows are c_pad wide, out_t taps are c_pad*rows apart (zero-padded output channels
+ *   make narrow 1x1 convs, e.g. the C/8 attention projections, tensor-core eligible).
  * bg_sn_bwd: dW = dWn/sigma - (<dWn,W>/sigma^2) v_hat^T u_hat  (gradient with u_hat, v_hat frozen,
- *   ops.py:738-739).
+ *   ops.py:738-739).  g_ld = row stride of dWn (c_pad of the forward).
  * ------------------------------------------------------------------------------------------- */
 size_t bg_sn_workspace_bytes(int K, int C);
 int bg_sn_power_iter(const float* W, const float* u, float* u_out, float* v, float* sigma,
                      int K, int C, void* ws, size_t ws_bytes, void* stream);
 int bg_sn_scale(const float* W, const float* sigma, void* out, void* out_t, int dtype,
-                int taps, int rows, int C, void* stream);
-int bg_sn_bwd(const float* W, const float* dWn, const float* u_hat, const float* v_hat,
+                int taps, int rows, int C, int c_pad, void* stream);
+int bg_sn_bwd(const float* W, const float* dWn, int g_ld, const float* u_hat, const float* v_hat,
               const float* sigma, float* dW, int K, int C, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -144,6 +146,11 @@ int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const floa
  * (saved for the backward).  tcgen05 kernels only (no fallback): BG_ERR_UNSUPPORTED elsewhere. */
 int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk,
                  int dq, int dv, void* stream);
+/* backward of bg_attn2_fwd: d_o [B,Nq,dv] -> dq [B,Nq,dq], dk [B,Nk,dq], dv [B,Nk,dv] (bf16);
+ * delta [B,Nq] fp32 scratch (row-wise <d_o, o>).  Recomputes the probabilities from lse. */
+int bg_attn2_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                 const float* lse, float* delta, void* dq_out, void* dk_out, void* dv_out, int B, int Nq,
+                 int Nk, int dq, int dv, void* stream);
 int bg_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 int bg_maxpool2_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype,
                     void* stream);

@@ -30,3 +30,25 @@ def test_attn2_forward(B, Nq, Nk, dq, dv):
     ro, rl = _ref(q.double().cpu(), k.double().cpu(), v.double().cpu())
     assert_close(lse.cpu().numpy(), rl.numpy(), 1e-5, "lse")
     assert_close(o.float().cpu().numpy(), ro.numpy(), 2e-2, "o")
+
+
+@pytest.mark.parametrize("B,Nq,Nk,dq,dv", [(2, 256, 64, 16, 16), (2, 1024, 256, 32, 96), (1, 4096, 1024, 32, 96),
+                                           (2, 4096, 1024, 16, 48), (1, 64, 16, 16, 32), (2, 320, 80, 32, 64), (1, 512, 128, 64, 128)])
+def test_attn2_backward(B, Nq, Nk, dq, dv):
+    from biggan_tensorflow_b200._lib import call
+    from biggan_tensorflow_b200.tensor import stream
+    rng = np.random.default_rng(1)
+    mk = lambda *sh: torch.from_numpy(rng.standard_normal(sh).astype(np.float32)).cuda().bfloat16()
+    q, k, v, do = mk(B, Nq, dq), mk(B, Nk, dq), mk(B, Nk, dv), mk(B, Nq, dv)
+    o = torch.empty(B, Nq, dv, dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty(B, Nq, dtype=torch.float32, device="cuda")
+    call("bg_attn2_fwd", q, k, v, o, lse, B, Nq, Nk, dq, dv, stream())
+    gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty(B, Nq, dtype=torch.float32, device="cuda")
+    call("bg_attn2_bwd", q, k, v, o, do, lse, delta, gq, gk, gv, B, Nq, Nk, dq, dv, stream())
+    torch.cuda.synchronize()
+    rq, rk, rv = [t.double().cpu().requires_grad_(True) for t in (q, k, v)]
+    ro, _ = _ref(rq, rk, rv)
+    g = torch.autograd.grad((ro * do.double().cpu()).sum(), [rq, rk, rv])
+    for got, ref, name in zip((gq, gk, gv), g, ("dq", "dk", "dv")):
+        assert_close(got.float().cpu().numpy(), ref.numpy(), 2e-2, name)
