@@ -63,6 +63,8 @@ class Trainer:
             ops.dist.all_reduce_sum = allreduce
         else:
             ops.dist.all_reduce_sum = lambda b: b
+        import numpy as _np
+        DiffAugment_tf.random_source = _np.random.Generator(_np.random.PCG64(4 + rank))   # per-rank augmentation draws
         self.t_d = 0
         self.t_g = 0
         self.opt = {}
