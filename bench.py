@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-entry-point timing breakdown here")
+    ap.add_argument("--quick", action="store_true", help="warm-up + timed steps only (for ncu captures): no e2e / breakdown pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -233,6 +234,10 @@ def main():
     ms_step, _ = timed(step_resident, args.steps)
     launches = (_lib.launch_count - l0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_step, "value": B / (ms_step * 1e-3), "gpu_launches": launches}))
+        return
     step_e2e()
     ms_e2e, losses = timed(step_e2e, max(2, args.steps // 2))
 

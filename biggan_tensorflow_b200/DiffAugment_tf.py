@@ -85,6 +85,10 @@ def DiffAugment(x, policy='', channels_first=False):
         for p in parts:
             if p not in AUGMENT_FNS:
                 raise KeyError(p)
+        from . import ops as _ops
+        c_pad, c_log = x.shape[-1], _ops.c_real(x)
+        if c_pad != c_log:                       # zero-padded image tensor: augment the logical channels only
+            x = _ops.slice_channels(x, c_log)
         B, H, W, C = x.shape
         rnd = _queue.pop(0) if _queue else draw_randoms(random_source, B, H, W)
         rnd_f, rnd_i = _upload(rnd, B)
@@ -97,4 +101,6 @@ def DiffAugment(x, policy='', channels_first=False):
                 last = _FLAG[parts[i]]
                 i += 1
             x = _apply(x, flags, rnd_f, rnd_i)
+        if c_pad != c_log:
+            x = _ops.pad_channels(x, c_pad)
     return x

@@ -306,3 +306,25 @@ extern "C" int bg_bgemm(const void* A, const void* Bm, void* C, int batch, int M
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
+
+// channel pad / slice of an NHWC tensor viewed as [npix, C]: dst[p, c] = c < min(Cs, Cd) ? src[p, c] : 0
+template <typename S, typename D>
+__global__ void pad_channels_kernel(const S* __restrict__ src, D* __restrict__ dst, long npix, int Cs, int Cd) {
+  const long n = npix * Cd;
+  EW_LOOP(i, n) {
+    const int c = (int)(i % Cd);
+    const long p = i / Cd;
+    bg_st(dst, i, c < Cs ? bg_ld(src, p * Cs + c) : 0.f);
+  }
+}
+extern "C" int bg_pad_channels(const void* src, int src_dtype, void* dst, int dst_dtype, long npix, int Cs, int Cd, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long n = npix * Cd;
+  if (src_dtype == BG_F32 && dst_dtype == BG_BF16) pad_channels_kernel<float, bf16><<<ew_blocks(n), 256, 0, st>>>((const float*)src, (bf16*)dst, npix, Cs, Cd);
+  else if (src_dtype == BG_BF16 && dst_dtype == BG_F32) pad_channels_kernel<bf16, float><<<ew_blocks(n), 256, 0, st>>>((const bf16*)src, (float*)dst, npix, Cs, Cd);
+  else if (src_dtype == BG_F32 && dst_dtype == BG_F32) pad_channels_kernel<float, float><<<ew_blocks(n), 256, 0, st>>>((const float*)src, (float*)dst, npix, Cs, Cd);
+  else if (src_dtype == BG_BF16 && dst_dtype == BG_BF16) pad_channels_kernel<bf16, bf16><<<ew_blocks(n), 256, 0, st>>>((const bf16*)src, (bf16*)dst, npix, Cs, Cd);
+  else { bg_set_error("bad dtypes"); return BG_ERR_UNSUPPORTED; }
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

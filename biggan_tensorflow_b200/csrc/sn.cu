@@ -127,12 +127,14 @@ __global__ void sn_scale_kernel(const float* __restrict__ W, const float* __rest
   }
 }
 
+// generic writer: out[(t*r_pad + r)*c_pad + c] and out_t[t][c][r] (tap stride c_pad*r_pad, row stride r_pad);
+// destinations with r_pad > rows or c_pad > C are pre-zeroed by the caller (zero-padded channels)
 template <typename T>
 __global__ void sn_scale_t_kernel(const float* __restrict__ W, const float* __restrict__ sigma, T* __restrict__ out,
-                                  T* __restrict__ out_t, int rows, int C, int c_pad) {
+                                  T* __restrict__ out_t, int rows, int C, int r_pad, int c_pad) {
   __shared__ float tile[32][33];
   const float sg = sigma[0];
-  const long tapoff = (long)blockIdx.z * rows * C, tapoff_p = (long)blockIdx.z * rows * c_pad;
+  const long tapoff = (long)blockIdx.z * rows * C, tapoff_p = (long)blockIdx.z * r_pad * c_pad;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + threadIdx.x;
@@ -146,21 +148,21 @@ __global__ void sn_scale_t_kernel(const float* __restrict__ W, const float* __re
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < C) bg_st(out_t, tapoff_p + (long)c * rows + r, tile[threadIdx.x][i]);
+    if (r < rows && c < C) bg_st(out_t, tapoff_p + (long)c * r_pad + r, tile[threadIdx.x][i]);
   }
 }
 
 extern "C" int bg_sn_scale(const float* W, const float* sigma, void* out, void* out_t, int dtype, int taps, int rows,
-                           int C, int c_pad, void* stream) {
+                           int C, int r_pad, int c_pad, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long n = (long)taps * rows * C;
-  BG_REQUIRE(n > 0 && c_pad >= C, BG_ERR_SHAPE, "sn_scale: bad shape");
-  if (!out_t && c_pad == C) {
+  BG_REQUIRE(n > 0 && c_pad >= C && r_pad >= rows, BG_ERR_SHAPE, "sn_scale: bad shape");
+  if (!out_t && c_pad == C && r_pad == rows) {
     const int blocks = (int)min(bg_cdiv(n, 1024), (long)bg_num_sms() * 8);
     BG_DISPATCH_DTYPE(dtype, T, sn_scale_kernel<T><<<blocks, 256, 0, st>>>(W, sigma, (T*)out, n));
   } else {
     dim3 grid((unsigned)bg_cdiv(C, 32), (unsigned)bg_cdiv(rows, 32), taps), block(32, 8);
-    BG_DISPATCH_DTYPE(dtype, T, sn_scale_t_kernel<T><<<grid, block, 0, st>>>(W, sigma, (T*)out, (T*)out_t, rows, C, c_pad));
+    BG_DISPATCH_DTYPE(dtype, T, sn_scale_t_kernel<T><<<grid, block, 0, st>>>(W, sigma, (T*)out, (T*)out_t, rows, C, r_pad, c_pad));
   }
   BG_LAUNCH_CHECK();
   return BG_OK;
@@ -168,13 +170,14 @@ extern "C" int bg_sn_scale(const float* W, const float* sigma, void* out, void* 
 
 // backward: dW = G/sigma - (<G,W>/sigma^2) v_hat[k] u_hat[c]
 __global__ void __launch_bounds__(256)
-sn_dot_partial_kernel(const float* __restrict__ G, const float* __restrict__ W, float* __restrict__ part, long n, int C, int g_ld) {
+sn_dot_partial_kernel(const float* __restrict__ G, const float* __restrict__ W, float* __restrict__ part, long n, int C, int g_ld, int rows, int r_pad) {
   __shared__ float sh[33];
   float s = 0.f;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    const long gi = (g_ld == C) ? i : (i / C) * g_ld + (i % C);
+    const long k = i / C;
+    const long gi = ((k / rows) * r_pad + (k % rows)) * g_ld + (i % C);
     s = fmaf(G[gi], W[i], s);
   }
   s = bg_block_sum(s, sh);
@@ -183,7 +186,7 @@ sn_dot_partial_kernel(const float* __restrict__ G, const float* __restrict__ W, 
 
 __global__ void __launch_bounds__(256)
 sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ part, int npart, const float* __restrict__ u_hat,
-                    const float* __restrict__ v_hat, const float* __restrict__ sigma, float* __restrict__ dW, int K, int C, int g_ld) {
+                    const float* __restrict__ v_hat, const float* __restrict__ sigma, float* __restrict__ dW, int K, int C, int g_ld, int rows, int r_pad) {
   __shared__ float sh[33];
   float s = 0.f;
   for (int i = threadIdx.x; i < npart; i += blockDim.x) s += part[i];
@@ -195,21 +198,21 @@ sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ part,
   const long stride = (long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     const int k = (int)(i / C), c = (int)(i - (long)k * C);
-    dW[i] = G[(long)k * g_ld + c] / sg - coef * v_hat[k] * u_hat[c];
+    dW[i] = G[((long)(k / rows) * r_pad + (k % rows)) * g_ld + c] / sg - coef * v_hat[k] * u_hat[c];
   }
 }
 
-extern "C" int bg_sn_bwd(const float* W, const float* dWn, int g_ld, const float* u_hat, const float* v_hat, const float* sigma,
-                         float* dW, int K, int C, void* ws, size_t ws_bytes, void* stream) {
-  BG_REQUIRE(g_ld >= C, BG_ERR_SHAPE, "sn_bwd: g_ld < C");
+extern "C" int bg_sn_bwd(const float* W, const float* dWn, int rows, int r_pad, int g_ld, const float* u_hat, const float* v_hat,
+                         const float* sigma, float* dW, int K, int C, void* ws, size_t ws_bytes, void* stream) {
+  BG_REQUIRE(g_ld >= C && rows > 0 && r_pad >= rows && K % rows == 0, BG_ERR_SHAPE, "sn_bwd: bad gradient layout");
   BG_REQUIRE(ws && ws_bytes >= 1024 * sizeof(float), BG_ERR_WORKSPACE, "sn_bwd workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const long n = (long)K * C;
   const int npart = (int)min(bg_cdiv(n, 1024), 1024L);
-  sn_dot_partial_kernel<<<npart, 256, 0, st>>>(dWn, W, (float*)ws, n, C, g_ld);
+  sn_dot_partial_kernel<<<npart, 256, 0, st>>>(dWn, W, (float*)ws, n, C, g_ld, rows, r_pad);
   BG_LAUNCH_CHECK();
   const int blocks = (int)min(bg_cdiv(n, 256), (long)bg_num_sms() * 8);
-  sn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dWn, (const float*)ws, npart, u_hat, v_hat, sigma, dW, K, C, g_ld);
+  sn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dWn, (const float*)ws, npart, u_hat, v_hat, sigma, dW, K, C, g_ld, rows, r_pad);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

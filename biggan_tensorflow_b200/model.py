@@ -8,7 +8,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from .ops import (bn, cast, compute_dtype, constant_initializer, conv, fully_connected, get_variable,
+from .ops import (bn, cast, compute_dtype, rgb_pad, constant_initializer, conv, fully_connected, get_variable,
                   global_sum_pooling, relu, reshape, resblock, resblock_down, resblock_up_condition,
                   round_up, self_attention_2, variable_scope)
 from .tensor import F32, Tensor
@@ -138,8 +138,10 @@ def generator(cfg, z, cls_z, is_training=True):
             ch = round_up(int(cfg.ch * 2.0 ** (n_blocks - b_i - 1)), 8)
             ch_mul = ch_mul // 2
         x = bn(x, opt=opt, _act=_lib.ACT_RELU)                                  # :491-492 (BN + act fused)
+        # bf16 tensor-core mode: the image is produced with zero-padded channels (3 -> 16) so that G_logit and
+        # D's first convs are tcgen05 GEMMs; `ops.slice_channels(x, 3)` gives the plain RGB tensor
         x = conv(x, channels=cfg.c_dim, kernel=3, stride=1, pad=1, use_bias=False, opt=opt, scope='G_logit',
-                 _act=_lib.ACT_TANH)                                            # :570 + tanh :580
+                 _act=_lib.ACT_TANH, _pad_cout_to=rgb_pad())                    # :570 + tanh :580
         return x
 
 

@@ -128,7 +128,7 @@ Tensor.__rmul__ = lambda a, b: scale(a, b)
 # Spectral norm (ops.py:718-747)
 ##################################################################################
 
-def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_c=0):
+def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_c=0, _pad_r=0):
     """w: Variable [..., C].  Returns W/sigma (same shape) after one power-iteration step; the
     persistent `u` (created in the current scope, ops.py:722) is advanced in place (ops.py:743).
     Evaluated once per update phase and variable (SURVEY 8a row 3 state semantics)."""
@@ -141,7 +141,9 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_
     u = get_variable("u", [1, C], initializer=random_normal_initializer(), trainable=False)
     out_dtype = _out_dtype or F32
     c_pad = max(int(_pad_c), C)      # zero-padded output channels (tensor-core eligibility of narrow convs)
-    key = (u.name, out_dtype, bool(_want_t), c_pad)
+    rows = K // _taps
+    r_pad = max(int(_pad_r), rows)   # zero-padded input channels per tap (RGB layers)
+    key = (u.name, out_dtype, bool(_want_t), c_pad, r_pad)
     hit = store.sn_cache.get(key)
     if hit is not None:
         return hit
@@ -154,12 +156,11 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_
         base = (v_hat, sigma)
         store.sn_cache[("pi", u.name)] = base
     v_hat, sigma = base
-    p_shape = w_shape[:-1] + [c_pad]
-    alloc = empty if c_pad == C else (lambda sh, dt: torch.zeros(tuple(sh), dtype=dt, device=w.data.device))
+    p_shape = w_shape[:-2] + [r_pad, c_pad]
+    alloc = empty if (c_pad == C and r_pad == rows) else (lambda sh, dt: torch.zeros(tuple(sh), dtype=dt, device=w.data.device))
     wn = Tensor(alloc(p_shape, out_dtype), requires_grad=w.requires_grad)
     w_t = alloc(p_shape, out_dtype) if _want_t else None
-    rows = K // _taps
-    call("bg_sn_scale", w.data, sigma, wn.data, w_t, bg_dtype(out_dtype), _taps, rows, C, c_pad, stream())
+    call("bg_sn_scale", w.data, sigma, wn.data, w_t, bg_dtype(out_dtype), _taps, rows, C, r_pad, c_pad, stream())
     wn.aux = {"w_t": w_t, "sigma": sigma, "v_hat": v_hat, "u_hat": u.data}
     store.sn_cache[key] = wn
     if recording(w):
@@ -168,7 +169,7 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_
                 return
             dst, fin = grad_target(w)
             ws2 = workspace(query("bg_sn_workspace_bytes", K, C))
-            call("bg_sn_bwd", w.data, wn.grad, c_pad, u.data, v_hat, sigma, dst, K, C, ws2, ws2.numel(), stream())
+            call("bg_sn_bwd", w.data, wn.grad, rows, r_pad, c_pad, u.data, v_hat, sigma, dst, K, C, ws2, ws2.numel(), stream())
             if fin:
                 fin()
         record(bw)
@@ -251,11 +252,63 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
     return y
 
 
-def _sn_weight(w, taps, conv_like, x_dtype, pad_c=0):
+def _sn_weight(w, taps, conv_like, x_dtype, pad_c=0, pad_r=0):
     """Normalised weights in the layout(s) the conv kernels want."""
     if x_dtype == BF16:
-        return spectral_norm(w, _out_dtype=BF16, _taps=taps, _want_t=True, _pad_c=pad_c)
-    return spectral_norm(w, _out_dtype=F32, _taps=taps, _pad_c=pad_c)
+        return spectral_norm(w, _out_dtype=BF16, _taps=taps, _want_t=True, _pad_c=pad_c, _pad_r=pad_r)
+    return spectral_norm(w, _out_dtype=F32, _taps=taps, _pad_c=pad_c, _pad_r=pad_r)
+
+
+def rgb_pad():
+    """Channel count the 3-channel image tensors are zero-padded to in bf16 tensor-core mode (0 = no padding):
+    with 16 channels the RGB convs (3 -> ch in D, ch -> 3 `G_logit`) run on the tcgen05 kernels."""
+    if _state["compute_dtype"] == BF16 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1:
+        return 16
+    return 0
+
+
+def c_real(x):
+    """Logical channel count of a (possibly zero-padded) NHWC tensor."""
+    a = x.aux
+    return a["c_real"] if isinstance(a, dict) and "c_real" in a else x.shape[-1]
+
+
+def pad_channels(x, c_pad, dtype=None):
+    """[.., C] -> [.., c_pad] with zero fill (and optional cast); the result remembers C as its logical width."""
+    C = x.shape[-1]
+    dtype = dtype or x.dtype
+    y = Tensor(empty(list(x.shape[:-1]) + [c_pad], dtype), requires_grad=x.requires_grad)
+    y.aux = {"c_real": C}
+    npix = x.numel() // C
+    call("bg_pad_channels", x.data, bg_dtype(x), y.data, bg_dtype(y), npix, C, c_pad, stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            g = torch.empty_like(x.data)
+            call("bg_pad_channels", y.grad, bg_dtype(y.grad), g, bg_dtype(g), npix, c_pad, C, stream())
+            accumulate_grad(x, g, own=True)
+        record(bw)
+    return y
+
+
+def slice_channels(x, C):
+    """[.., Cp] -> [.., C] (first C channels)."""
+    Cp = x.shape[-1]
+    if Cp == C:
+        return x
+    y = Tensor(empty(list(x.shape[:-1]) + [C], x.dtype), requires_grad=x.requires_grad)
+    npix = x.numel() // Cp
+    call("bg_pad_channels", x.data, bg_dtype(x), y.data, bg_dtype(y), npix, Cp, C, stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            g = torch.empty_like(x.data)
+            call("bg_pad_channels", y.grad, bg_dtype(y.grad), g, bg_dtype(g), npix, C, Cp, stream())
+            accumulate_grad(x, g, own=True)
+        record(bw)
+    return y
 
 
 def _padded_bias(bias, c_pad):
@@ -315,16 +368,20 @@ def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True,
         desc = _conv_geometry(x, channels, kernel, stride, pad, opt)
         if not opt.get("conv", {}).get("sn", True):
             raise ValueError("conv with sn=False (tf.layers.conv2d path) is not supported")
-        w = get_variable("kernel", shape=[kernel, kernel, x.shape[-1], channels], initializer=weight_init)
+        cin_x, cin = x.shape[-1], c_real(x)          # x may carry zero-padded channels (RGB tensors)
+        w = get_variable("kernel", shape=[kernel, kernel, cin, channels], initializer=weight_init)
         c_pad = round_up(channels, _pad_cout_to) if _pad_cout_to else channels
-        wn = _sn_weight(w, kernel * kernel, True, x.dtype, pad_c=c_pad)
+        wn = _sn_weight(w, kernel * kernel, True, x.dtype, pad_c=c_pad, pad_r=cin_x if cin_x != cin else 0)
         bias = None
         if use_bias:
             bias = get_variable("bias", [channels], initializer=constant_initializer(0.0))
             if c_pad != channels:
                 bias = _padded_bias(bias, c_pad)
         desc.Co = c_pad          # extra output channels are exactly zero (zero weights, zero bias)
-        return _conv_op(x, wn, bias, desc, act=_act, residual=_residual)
+        y = _conv_op(x, wn, bias, desc, act=_act, residual=_residual)
+        if c_pad != channels:
+            y.aux = {"c_real": channels}
+        return y
 
 
 def deconv(x, channels, opt, kernel=4, stride=2, padding='SAME', use_bias=True, scope='deconv_0',
@@ -686,6 +743,7 @@ def max_pooling(x):
 def relu(x):
     """ops.py:529-530."""
     y = Tensor(empty(x.shape, x.dtype), requires_grad=x.requires_grad)
+    y.aux = x.aux if isinstance(x.aux, dict) and "c_real" in x.aux else None
     call("bg_relu_fwd", x.data, y.data, x.numel(), bg_dtype(x), stream())
     if recording(x):
         def bw():

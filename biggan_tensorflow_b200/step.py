@@ -140,6 +140,8 @@ class Trainer:
 
     def _as_input(self, img):
         t = Tensor(img)
+        if ops.rgb_pad():
+            return ops.pad_channels(t, ops.rgb_pad(), dtype=self.compute_dtype)     # cast + zero-pad 3 -> 16 channels
         return ops.cast(t, self.compute_dtype)
 
     # ------------------------------------------------------------------------------------------
@@ -155,6 +157,7 @@ class Trainer:
             aug_real = DiffAugment_tf.DiffAugment(self._as_input(real), policy=cfg.da_policy)       # :806
             aug_fake = DiffAugment_tf.DiffAugment(fake, policy=cfg.da_policy)                       # :857
             x = Tensor(torch.cat([aug_real.data, aug_fake.data], dim=0))
+            x.aux = aug_fake.aux
         # D(real) and D(fake) share weights and have no batch statistics -> one pass over [real; fake]
         out = discriminator(cfg, x)
         real_logits, fake_logits = split_rows(out["real"], [Bl, Bl])

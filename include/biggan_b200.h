@@ -44,18 +44,20 @@ int bg_debug_counters(int* tc_fwd, int* tc_wgrad);
  * bg_sn_scale: out = W / sigma in `dtype`; if out_t != NULL also writes the per-tap transposed copy
  *   out_t[t][c][r] for W viewed as [taps][rows][C] (K = taps*rows) -- the K-major operand layout of
  *   the tcgen05 conv kernels.  c_pad >= C: output channel count of the (pre-zeroed) destination
- *   buffers -- out rows are c_pad wide, out_t taps are c_pad*rows apart (zero-padded output channels
- *   make narrow 1x1 convs, e.g. the C/8 attention projections, tensor-core eligible).
+ *   buffers, r_pad >= rows: input channel count per tap there -- out is [taps][r_pad][c_pad], out_t is
+ *   [taps][c_pad][r_pad] (zero-padded channels make the narrow layers -- C/8 attention projections, the RGB
+ *   convs -- tensor-core eligible).
  * bg_sn_bwd: dW = dWn/sigma - (<dWn,W>/sigma^2) v_hat^T u_hat  (gradient with u_hat, v_hat frozen,
- *   ops.py:738-739).  g_ld = row stride of dWn (c_pad of the forward).
+ *   ops.py:738-739).  dWn is laid out [K/rows][r_pad][g_ld] (the padded layout of the forward).
  * ------------------------------------------------------------------------------------------- */
 size_t bg_sn_workspace_bytes(int K, int C);
 int bg_sn_power_iter(const float* W, const float* u, float* u_out, float* v, float* sigma,
                      int K, int C, void* ws, size_t ws_bytes, void* stream);
 int bg_sn_scale(const float* W, const float* sigma, void* out, void* out_t, int dtype,
-                int taps, int rows, int C, int c_pad, void* stream);
-int bg_sn_bwd(const float* W, const float* dWn, int g_ld, const float* u_hat, const float* v_hat,
-              const float* sigma, float* dW, int K, int C, void* ws, size_t ws_bytes, void* stream);
+                int taps, int rows, int C, int r_pad, int c_pad, void* stream);
+int bg_sn_bwd(const float* W, const float* dWn, int rows, int r_pad, int g_ld, const float* u_hat,
+              const float* v_hat, const float* sigma, float* dW, int K, int C, void* ws, size_t ws_bytes,
+              void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution family -- ops.py:49-113 (conv), ops.py:116-139 (deconv), ops.py:148-175
@@ -177,6 +179,9 @@ int bg_sumpool_fwd(const void* x, void* y, int B, long HW, int C, int relu_first
 int bg_sumpool_bwd(const void* x, const void* dy, void* dx, int B, long HW, int C, int relu_first,
                    int dtype, void* stream);
 int bg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long n, void* stream);
+/* [npix, Cs] -> [npix, Cd]: copies min(Cs, Cd) channels, zero-fills the rest (channel pad / slice + cast) */
+int bg_pad_channels(const void* src, int src_dtype, void* dst, int dst_dtype, long npix, int Cs, int Cd,
+                    void* stream);
 int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr,
                    int dtype, void* stream);
 

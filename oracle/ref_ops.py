@@ -118,6 +118,16 @@ class RefStore:
 # ops.py
 # --------------------------------------------------------------------------------------------
 
+# Optional storage-precision emulation (tests only): when set, every activation tensor the CUDA bf16 mode
+# stores in bf16 is rounded (forward value and backward gradient) while the arithmetic stays in the store dtype.
+# Used to show which error levels are inherent to bf16 storage (tests/test_bf16_conditioning.py).
+ACT_ROUND = None
+
+
+def _r(x):
+    return ACT_ROUND(x) if ACT_ROUND is not None else x
+
+
 def l2_normalize(x, eps=1e-12):
     # tf.nn.l2_normalize(axis=None): x * rsqrt(max(sum(x^2), eps))
     return x * torch.rsqrt(torch.clamp((x * x).sum(), min=eps))
@@ -200,7 +210,7 @@ def conv(store, x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bia
         if use_bias:
             b = store.get_variable("bias", [channels], kind="const", value=0.0)  # :97
             y = y + b
-        return y
+        return _r(y)
 
 
 def deconv(store, x, channels, opt, kernel=4, stride=2, padding="SAME", use_bias=True, scope="deconv_0"):
@@ -225,7 +235,7 @@ def deconv(store, x, channels, opt, kernel=4, stride=2, padding="SAME", use_bias
         if use_bias:
             b = store.get_variable("bias", [channels], kind="const", value=0.0)
             y = y + b
-        return y
+        return _r(y)
 
 
 def fully_connected(store, x, units, opt, use_bias=True, lrmul=1.0, scope="fully_0"):
@@ -286,7 +296,7 @@ def condition_batch_norm(store, x, z, opt={}, scope="batch_norm"):
         else:
             mean, var = test_mean, test_var
         inv = torch.rsqrt(var + epsilon) * gamma                                # tf.nn.batch_normalization
-        return x * inv + (beta - mean * inv)                                    # :638
+        return _r(x * inv + (beta - mean * inv))                                # :638
 
 
 def cond_bn(store, x, z, opt={}, scope="batch_norm"):
@@ -317,7 +327,7 @@ def batch_norm(store, x, opt={}, scope="batch_norm"):
         else:
             mean, var = mm, mv
         inv = torch.rsqrt(var + 1e-05) * gamma
-        return x * inv + (beta - mean * inv)
+        return _r(x * inv + (beta - mean * inv))
 
 
 def bn(store, x, opt={}, scope="batch_norm"):
@@ -358,11 +368,11 @@ def self_attention_2(store, x, channels, opt, scope="self_attention"):
         h = max_pooling(h)                                                      # :478
         s = hw_flatten(g) @ hw_flatten(f).transpose(1, 2)                       # :481  [bs, N, N/4]
         beta = torch.softmax(s, dim=-1)                                         # :483
-        o = beta @ hw_flatten(h)                                                # :485
+        o = _r(beta @ hw_flatten(h))                                            # :485
         gamma = store.get_variable("gamma", [1], kind="const", value=0.0)       # :486
         o = o.reshape(x.shape[0], x.shape[1], x.shape[2], channels // 2)        # :488
         o = conv(store, o, channels, kernel=1, stride=1, opt=opt, scope="attn_conv", use_bias=use_bias)
-        return gamma * o + x                                                    # :490
+        return _r(gamma * o + x)                                                # :490
 
 
 def upconv(store, x, channels, opt, use_bias=True):
@@ -428,7 +438,7 @@ def resblock_up_condition(store, x_init, z, channels, opt, use_bias=True, scope=
             x = g_conv(store, x, channels, use_bias=use_bias, opt=opt)
         with store.variable_scope("skip"):
             x_init = upconv(store, x_init, channels, use_bias=use_bias, opt=opt)
-    return x + x_init
+    return _r(x + x_init)
 
 
 def resblock_down(store, x_init, channels, opt, use_bias=True, scope="resblock_down"):
@@ -452,7 +462,7 @@ def resblock_down(store, x_init, channels, opt, use_bias=True, scope="resblock_d
         with store.variable_scope("skip"):
             x_init = downconv(store, x_init, channels, use_bias=use_bias, opt=opt,
                               method=opt["downsampling_method"])
-    return x + x_init
+    return _r(x + x_init)
 
 
 def flood_loss(loss, flood_level):

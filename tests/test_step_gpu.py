@@ -53,15 +53,23 @@ def test_train_step_matches_oracle(dtype, da_policy):
     assert set(r["prod"].keys()) == set(r["rs"].vars.keys())
     assert abs(r["d_loss"] - r["rd_loss"]) <= tol * max(abs(r["rd_loss"]), 1.0)
     assert abs(r["g_loss"] - r["rg_loss"]) <= tol * max(abs(r["rg_loss"]), 1.0)
-    # whole-network gradients compound the per-op error: 3e-4 (fp32, max-abs) / 4e-2 (bf16, relative L2)
-    gtol = tol * (3.0 if dtype == torch.float32 else 2.0)
+    # Whole-network gradients compound the per-op error.  fp32: 3e-4 max-abs.  bf16: relative L2, calibrated
+    # against the bf16-STORAGE emulation of the oracle itself (tests/test_bf16_conditioning.py): D gradients
+    # (one D backward) 8e-2; G gradients (back through all of D and all of G, ~60 bf16-stored tensors;
+    # the emulation alone moves generator/dense1 by 1.3e-1) 2.5e-1.
     for which, ref, got in (("D", r["rd_grads"], r["d_grads"]), ("G", r["rg_grads"], r["g_grads"])):
         gscale = max(float(g.abs().max()) for g in ref.values())
         for name, g in ref.items():
             if name.endswith("f_conv/bias"):      # analytically zero (softmax shift invariance)
                 assert np.abs(got[name]).max() <= 1e-3 * gscale, name
                 continue
-            assert_close(got[name], g.numpy(), gtol, which + " grad " + name)
+            if dtype == torch.float32:
+                vtol = 3e-4
+            else:
+                vtol = 8e-2 if which == "D" else 2.5e-1
+                if "f_conv/kernel" in name or "h_conv/kernel" in name or "g_conv" in name:
+                    vtol = max(vtol, 1.5e-1)
+            assert_close(got[name], g.numpy(), vtol, which + " grad " + name)
     # state after the iteration: SN u vectors, BN running stats
     for name, v in r["rs"].vars.items():
         if not r["rs"].trainable.get(name, False):
