@@ -232,15 +232,50 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   }
 }
 
-// adjoint of tf.pad(mode='REFLECT') (ops.py:82): fold the padded gradient back (+ residual)
+// adjoint of tf.pad(mode='REFLECT') (ops.py:82): fold the padded gradient back (+ residual).
+// One thread per (pixel, VEC channels): 16-byte accesses when C % VEC == 0 (VEC = 8 bf16 / 4 fp32).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, int H, int W, int C, int pt, int pl, int pb, int pr) {
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  const int CV = C / VEC;
+  const long total = (long)B * H * W * CV;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV); const long pix = idx / CV;
+    const int x = (int)(pix % W); const long r = pix / W;
+    const int y = (int)(r % H); const int b = (int)(r / H);
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = y + pt;
+    if (y >= 1 && y <= pt) ys[ny++] = pt - y;
+    if (y >= H - 1 - pb && y <= H - 2) ys[ny++] = 2 * (H - 1) - y + pt;
+    xs[nx++] = x + pl;
+    if (x >= 1 && x <= pl) xs[nx++] = pl - x;
+    if (x >= W - 1 - pr && x <= W - 2) xs[nx++] = 2 * (W - 1) - x + pl;
+    float acc[VEC];
+    const long o = pix * C + (long)cv * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+    if (residual) {
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(residual, o + e); acc[e] += v.x; acc[e + 1] += v.y; acc[e + 2] += v.z; acc[e + 3] += v.w; }
+    }
+    for (int a = 0; a < ny; ++a)
+      for (int q = 0; q < nx; ++q) {
+        const long src = (((long)b * Hp + ys[a]) * Wp + xs[q]) * C + (long)cv * VEC;
+#pragma unroll
+        for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(dxp, src + e); acc[e] += v.x; acc[e + 1] += v.y; acc[e + 2] += v.z; acc[e + 3] += v.w; }
+      }
+#pragma unroll
+    for (int e = 0; e < VEC; e += 4) bg_st4(dx, o + e, f4{acc[e], acc[e + 1], acc[e + 2], acc[e + 3]});
+  }
+}
+
 template <typename T>
-__global__ void reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, int H, int W, int C,
-                                    int pt, int pl, int pb, int pr) {
+__global__ void reflect_fold_scalar_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, int H, int W, int C,
+                                           int pt, int pl, int pb, int pr) {
   const int Hp = H + pt + pb, Wp = W + pl + pr;
   const long total = (long)B * H * W * C;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (; idx < total; idx += stride) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C); long r = idx / C;
     const int x = (int)(r % W); r /= W;
     const int y = (int)(r % H); const int b = (int)(r / H);
@@ -258,14 +293,33 @@ __global__ void reflect_fold_kernel(const T* __restrict__ dxp, const T* residual
   }
 }
 
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+reflect_pad_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int pt, int pl, int pb, int pr) {
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  const int CV = C / VEC;
+  const long total = (long)B * Hp * Wp * CV;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV); const long pix = idx / CV;
+    const int xp = (int)(pix % Wp); const long r = pix / Wp;
+    const int yp = (int)(r % Hp); const int b = (int)(r / Hp);
+    int iy = yp - pt, ix = xp - pl;
+    if (iy < 0) iy = -iy;
+    if (iy >= H) iy = 2 * (H - 1) - iy;
+    if (ix < 0) ix = -ix;
+    if (ix >= W) ix = 2 * (W - 1) - ix;
+    const long src = (((long)b * H + iy) * W + ix) * C + (long)cv * VEC, dst = pix * C + (long)cv * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; e += 4) bg_st4(y, dst + e, bg_ld4(x, src + e));
+  }
+}
+
 template <typename T>
-__global__ void reflect_pad_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C,
-                                   int pt, int pl, int pb, int pr) {
+__global__ void reflect_pad_scalar_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int pt, int pl,
+                                          int pb, int pr) {
   const int Hp = H + pt + pb, Wp = W + pl + pr;
   const long total = (long)B * Hp * Wp * C;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (; idx < total; idx += stride) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C); long r = idx / C;
     const int xp = (int)(r % Wp); r /= Wp;
     const int yp = (int)(r % Hp); const int b = (int)(r / Hp);
@@ -414,9 +468,20 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
   }
   if (padded) {
     const long total = (long)d->B * d->Hi * d->Wi * d->Ci;
-    const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
-    BG_DISPATCH_DTYPE(dtype, T, reflect_fold_kernel<T><<<blocks, 256, 0, st>>>((const T*)ws, (const T*)residual, (T*)dx, d->B, d->Hi,
-                                                                            d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r));
+    const int vec = dtype == BG_F32 ? 4 : 8;
+    if (d->Ci % vec == 0) {
+      const int blocks = (int)min(bg_cdiv(total / vec, 256), (long)bg_num_sms() * 32);
+      if (dtype == BG_F32)
+        reflect_fold_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)ws, (const float*)residual, (float*)dx, d->B, d->Hi, d->Wi, d->Ci,
+                                                            d->pad_t, d->pad_l, d->pad_b, d->pad_r);
+      else
+        reflect_fold_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)ws, (const bf16*)residual, (bf16*)dx, d->B, d->Hi, d->Wi, d->Ci,
+                                                           d->pad_t, d->pad_l, d->pad_b, d->pad_r);
+    } else {
+      const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
+      BG_DISPATCH_DTYPE(dtype, T, reflect_fold_scalar_kernel<T><<<blocks, 256, 0, st>>>((const T*)ws, (const T*)residual, (T*)dx, d->B, d->Hi,
+                                                                                     d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r));
+    }
     BG_LAUNCH_CHECK();
   }
   return BG_OK;
@@ -505,8 +570,15 @@ extern "C" int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C
                               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long total = (long)B * (H + pt + pb) * (W + pl + pr) * C;
-  const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
-  BG_DISPATCH_DTYPE(dtype, T, reflect_pad_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, pt, pl, pb, pr));
+  const int vec = dtype == BG_F32 ? 4 : 8;
+  if (C % vec == 0) {
+    const int blocks = (int)min(bg_cdiv(total / vec, 256), (long)bg_num_sms() * 32);
+    if (dtype == BG_F32) reflect_pad_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, B, H, W, C, pt, pl, pb, pr);
+    else reflect_pad_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, pt, pl, pb, pr);
+  } else {
+    const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
+    BG_DISPATCH_DTYPE(dtype, T, reflect_pad_scalar_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, pt, pl, pb, pr));
+  }
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

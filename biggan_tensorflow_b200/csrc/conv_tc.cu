@@ -23,7 +23,8 @@ struct TcFwdParams {
   CUtensorMap bmap;
   int B, Ho, Wo, Co;
   int nphase, ostep;
-  int bw, bh, bb;            // pixel box (bw*bh*bb == 128)
+  int bw, bh, bb;            // pixel box (bw*bh*bb == 128*MT)
+  int MT;                    // 128-pixel sub-tiles per CTA sharing every weight tile (B operand)
   int tw, th, tb;            // tiles per phase
   int nkb, BN, act, stages;
   int oy0[4], ox0[4], Hp[4], Wp[4], ntaps[4];
@@ -33,33 +34,30 @@ struct TcFwdParams {
   bf16* out;
 };
 
+// Persistent: one CTA per SM walks the tile list (n-tile fastest, so concurrently running CTAs share the
+// activation tile in L2).  The TMA ring never drains between tiles, and the accumulator is double-buffered
+// in TMEM so the 8 epilogue warps drain tile i while the MMA warp already accumulates tile i+1.
 template <int TMEM_COLS>
-__global__ void __launch_bounds__(192, 1) tc_fwd_kernel(const __grid_constant__ TcFwdParams p) {
+__global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ TcFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = 16384u + (uint32_t)p.BN * 128u;
-
   const int tiles_pp = p.tw * p.th * p.tb;
-  const int phase = blockIdx.x / tiles_pp;
-  int t = blockIdx.x - phase * tiles_pp;
-  const int j0 = (t % p.tw) * p.bw; t /= p.tw;
-  const int i0 = (t % p.th) * p.bh; t /= p.th;
-  const int b0 = t * p.bb;
-  const int n0 = blockIdx.y * p.BN;
-  const int ntaps = p.ntaps[phase];
-  const int total = ntaps * p.nkb;
+  const int ntn = p.Co / p.BN;
+  const int ntiles = tiles_pp * p.nphase * ntn;
 
   if (warp == 0 && lane == 0) {
     for (int m = 0; m < 4; ++m) tma_prefetch_desc(&p.amap[m]);
     tma_prefetch_desc(&p.bmap);
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    mbar_init(smem_u32(&accum_bar), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
@@ -71,90 +69,125 @@ __global__ void __launch_bounds__(192, 1) tc_fwd_kernel(const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tp = 0; tp < ntaps; ++tp) {
-        const TcTap tap = p.taps[phase][tp];
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t par = (uint32_t)((it / p.stages) & 1);
-          mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, stage_bytes);
-          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-          tma_load_4d(sa, &p.amap[tap.map], fb, kb * 64, j0 + tap.dx, i0 + tap.dy, b0);
-          tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = tile % ntn; int t = tile / ntn;
+        const int phase = t / tiles_pp; t -= phase * tiles_pp;
+        const int j0 = (t % p.tw) * p.bw; t /= p.tw;
+        const int i0 = (t % p.th) * p.bh; t /= p.th;
+        const int b0 = t * p.bb;
+        const int n0 = nt * p.BN;
+        const int ntaps = p.ntaps[phase];
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const TcTap tap = p.taps[phase][tp];
+          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t par = (uint32_t)((it / p.stages) & 1);
+            mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            mbar_expect_tx(fb, stage_bytes);
+            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+            tma_load_4d(sa, &p.amap[tap.map], fb, kb * 64, j0 + tap.dx, i0 + tap.dy, b0);
+            tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % p.stages;
-        const uint32_t par = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(smem_u32(&full_bar[s]), par);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+        const int phase = (tile / ntn) / tiles_pp;
+        const int total = p.ntaps[phase] * p.nkb;
+        const int buf = lt & 1;
+        mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
+        for (int li = 0; li < total; ++li, ++it) {
+          const int s = it % p.stages;
+          const uint32_t par = (uint32_t)((it / p.stages) & 1);
+          mbar_wait(smem_u32(&full_bar[s]), par);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = umma_desc_kmajor_sw128(sa + k * 32);
-          const uint64_t bd = umma_desc_kmajor_sw128(sa + 16384u + k * 32);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_desc_kmajor_sw128(sa + k * 32);
+            const uint64_t bd = umma_desc_kmajor_sw128(sa + 16384u + k * 32);
+            umma_bf16(tacc, ad, bd, idesc, (li | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
         }
-        umma_commit(smem_u32(&empty_bar[s]));
+        umma_commit(smem_u32(&tfull_bar[buf]));
       }
-      umma_commit(smem_u32(&accum_bar));
     }
   } else {
+    const int ew = warp - 2;                      // 0..7
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                     // which half of the BN columns
+    const int csplit = ((p.BN / 16 + 1) / 2) * 16;
+    const int cbeg = half ? csplit : 0, cend = half ? p.BN : csplit;
     const int row = q * 32 + lane;
     const int w = row % p.bw, h = (row / p.bw) % p.bh, bl = row / (p.bw * p.bh);
-    const int pi = i0 + h, pj = j0 + w, b = b0 + bl;
-    const bool valid = (b < p.B) && (pi < p.Hp[phase]) && (pj < p.Wp[phase]);
-    const int oy = p.oy0[phase] + pi * p.ostep, ox = p.ox0[phase] + pj * p.ostep;
-    const long obase = (((long)b * p.Ho + oy) * p.Wo + ox) * p.Co + n0;
-    mbar_wait(smem_u32(&accum_bar), 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (valid) {
-        float v[16];
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int nt = tile % ntn; int t = tile / ntn;
+      const int phase = t / tiles_pp; t -= phase * tiles_pp;
+      const int j0 = (t % p.tw) * p.bw; t /= p.tw;
+      const int i0 = (t % p.th) * p.bh; t /= p.th;
+      const int b0 = t * p.bb;
+      const int n0 = nt * p.BN;
+      const int pi = i0 + h, pj = j0 + w, b = b0 + bl;
+      const bool valid = (b < p.B) && (pi < p.Hp[phase]) && (pj < p.Wp[phase]);
+      const int oy = p.oy0[phase] + pi * p.ostep, ox = p.ox0[phase] + pj * p.ostep;
+      const long obase = (((long)b * p.Ho + oy) * p.Wo + ox) * p.Co + n0;
+      const int buf = lt & 1;
+      mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), r);
+        if (valid) {
+          float v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-        if (p.bias) {
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+          if (p.bias) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
-        }
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
-          uint4 r0 = rp[0], r1 = rp[1];
-          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+            for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
+          }
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
+              v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
+            }
+          }
+          if (p.act == BG_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (p.act == BG_ACT_TANH) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
+          }
+          uint4 o0, o1;
+          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
-            v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
+            q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
           }
+          uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+          op[0] = o0;
+          op[1] = o1;
         }
-        if (p.act == BG_ACT_RELU) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-        } else if (p.act == BG_ACT_TANH) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
-        }
-        uint4 o0, o1;
-        __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-        __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
-        }
-        uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
-        op[0] = o0;
-        op[1] = o1;
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
     }
   }
   tc_fence_before();
@@ -277,19 +310,13 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   if ((rc = make_w_map(&P.bmap, w_kmajor, maxw + 1, g.Co, g.Ci, BN))) return rc;
   P.B = g.B; P.Ho = g.Ho; P.Wo = g.Wo; P.Co = g.Co;
   P.nphase = g.nphase; P.ostep = g.ostep;
-  P.bw = bw; P.bh = bh; P.bb = bb;
+  P.bw = bw; P.bh = bh; P.bb = bb; P.MT = 1;
   P.tw = (int)bg_cdiv(g.ph[0].Wp, bw); P.th = (int)bg_cdiv(g.ph[0].Hp, bh); P.tb = (int)bg_cdiv(g.B, bb);
   P.nkb = (int)bg_cdiv(g.Ci, 64);
   P.BN = BN; P.act = act;
   const int stage_bytes = 16384 + BN * 128;
-  // Short-K tiles (few taps x k-blocks) are dominated by pipeline fill + epilogue: keep the per-CTA
-  // ring small so that 2-3 CTAs are resident per SM and one CTA's epilogue overlaps another's MMAs.
-  int max_iters = 0;
-  for (int ph = 0; ph < g.nphase; ++ph) max_iters = max(max_iters, g.ph[ph].ntaps * (int)bg_cdiv(g.Ci, 64));
-  int stages = (stage_bytes <= 32 * 1024) ? 3 : 4;
-  if (max_iters >= 64 && stage_bytes <= 32 * 1024) stages = 6;
-  if (stages > max_iters) stages = max(2, max_iters);
-  if ((size_t)stages * stage_bytes + 1024 > 226 * 1024) stages = (225 * 1024) / stage_bytes;
+  int stages = (200 * 1024) / stage_bytes;       // one persistent CTA per SM: a deep ring that never drains
+  if (stages > 8) stages = 8;
   if (stages < 2) return BG_OK;
   P.stages = stages;
   for (int ph = 0; ph < g.nphase; ++ph) {
@@ -305,7 +332,8 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   }
   P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  dim3 grid((unsigned)(P.tw * P.th * P.tb * g.nphase), (unsigned)(g.Co / BN));
+  const long ntiles = (long)P.tw * P.th * P.tb * g.nphase * (g.Co / BN);
+  dim3 grid((unsigned)min(ntiles, (long)bg_num_sms()));
 #define TC_LAUNCH(COLS)                                                                                          \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
@@ -313,12 +341,14 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
       BG_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    tc_fwd_kernel<COLS><<<grid, 192, smem, st>>>(P);                                                             \
+    tc_fwd_kernel<COLS><<<grid, 320, smem, st>>>(P);                                                             \
   } while (0)
-  if (BN <= 32) TC_LAUNCH(32);
-  else if (BN <= 64) TC_LAUNCH(64);
-  else if (BN <= 128) TC_LAUNCH(128);
-  else TC_LAUNCH(256);
+  const int cols = 2 * BN;                       // double-buffered accumulator
+  if (cols <= 32) TC_LAUNCH(32);
+  else if (cols <= 64) TC_LAUNCH(64);
+  else if (cols <= 128) TC_LAUNCH(128);
+  else if (cols <= 256) TC_LAUNCH(256);
+  else TC_LAUNCH(512);
 #undef TC_LAUNCH
   BG_LAUNCH_CHECK();
   g_cnt_tc_fwd++;

@@ -144,37 +144,51 @@ extern "C" int bg_bn_finalize(const double* sums, double count, float* mean, flo
 }
 
 // y = act(x*inv + (beta - mean*inv)), inv = rsqrt(var+eps)*gamma   (tf.nn.batch_normalization form)
+// grid: x = 128-channel block, y = row chunk of one sample, z = sample; a thread keeps its 4 channels'
+// scale/shift in registers and streams rows (coalesced 16-byte accesses, no per-element index math).
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int gb_bstride, T* __restrict__ y, int act,
-                float eps, long HW, int C, long total4) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  const int C4 = C >> 2;
-  for (; i < total4; i += stride) {
-    const int c = (int)(i % C4) * 4;
-    const long b = i / ((long)C4 * HW);
-    f4 xv = bg_ld4(x, i * 4);
-    float xe[4] = {xv.x, xv.y, xv.z, xv.w}, o[4];
+                float eps, long HW, int C, int nchunk) {
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * BN_CPB + lane * 4;
+  if (c >= C) return;
+  const int b = blockIdx.z;
+  const long rpc = (HW + nchunk - 1) / nchunk;
+  const long r0 = (long)blockIdx.y * rpc, r1 = min(HW, r0 + rpc);
+  float inv[4], shift[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float inv = rsqrtf(var[c + e] + eps) * gamma[b * gb_bstride + c + e];
-      float v = xe[e] * inv + (beta[b * gb_bstride + c + e] - mean[c + e] * inv);
-      if (act == BG_ACT_RELU) v = fmaxf(v, 0.f);
-      o[e] = v;
-    }
-    bg_st4(y, i * 4, f4{o[0], o[1], o[2], o[3]});
+  for (int e = 0; e < 4; ++e) {
+    inv[e] = rsqrtf(var[c + e] + eps) * gamma[(long)b * gb_bstride + c + e];
+    shift[e] = beta[(long)b * gb_bstride + c + e] - mean[c + e] * inv[e];
   }
+  const long base = (long)b * HW * C + c;
+  for (long r = r0 + ty; r < r1; r += 8) {
+    f4 xv = bg_ld4(x, base + r * C);
+    float o[4] = {xv.x * inv[0] + shift[0], xv.y * inv[1] + shift[1], xv.z * inv[2] + shift[2], xv.w * inv[3] + shift[3]};
+    if (act == BG_ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+    }
+    bg_st4(y, base + r * C, f4{o[0], o[1], o[2], o[3]});
+  }
+}
+
+static inline int bn_apply_chunks(int B, long HW, int C) {
+  long want = bg_cdiv(16L * bg_num_sms(), (long)B * bg_cdiv(C, BN_CPB));
+  long mx = bg_cdiv(HW, 8);
+  long n = want < mx ? want : mx;
+  return (int)(n < 1 ? 1 : n);
 }
 
 extern "C" int bg_bn_apply(const void* x, const float* mean, const float* var, const float* gamma, const float* beta,
                            int gb_bstride, void* y, int act, float eps, int B, long HW, int C, int dtype, void* stream) {
   BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
-  const long total4 = (long)B * HW * C / 4;
-  const int blocks = (int)min(bg_cdiv(total4, 256), (long)bg_num_sms() * 16);
-  BG_DISPATCH_DTYPE(dtype, T, bn_apply_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, mean, var, gamma, beta, gb_bstride,
-                                                                                       (T*)y, act, eps, HW, C, total4));
+  const int nchunk = bn_apply_chunks(B, HW, C);
+  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
+  BG_DISPATCH_DTYPE(dtype, T, bn_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, mean, var, gamma, beta, gb_bstride,
+                                                                                     (T*)y, act, eps, HW, C, nchunk));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
@@ -217,33 +231,41 @@ extern "C" int bg_bn_bwd_sums(const float* dgamma, const float* dbeta, const flo
   return BG_OK;
 }
 
-// dx = rstd * (gamma*g - s1/count - xhat * s2/count)
+// dx = rstd * (gamma*g - s1/count - xhat * s2/count)      (same thread layout as bn_apply_kernel)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int gb_bstride, const double* __restrict__ s, double count, T* __restrict__ dx, int act, float eps,
-                    long HW, int C, long total4) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  const int C4 = C >> 2;
-  for (; i < total4; i += stride) {
-    const int c = (int)(i % C4) * 4;
-    const long b = i / ((long)C4 * HW);
-    f4 xv = bg_ld4(x, i * 4), dv = bg_ld4(dy, i * 4);
+                    long HW, int C, int nchunk) {
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * BN_CPB + lane * 4;
+  if (c >= C) return;
+  const int b = blockIdx.z;
+  const long rpc = (HW + nchunk - 1) / nchunk;
+  const long r0 = (long)blockIdx.y * rpc, r1 = min(HW, r0 + rpc);
+  float rs[4], gm[4], inv[4], shift[4], mu[4], m1[4], m2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    rs[e] = rsqrtf(var[c + e] + eps);
+    gm[e] = gamma[(long)b * gb_bstride + c + e];
+    mu[e] = mean[c + e];
+    inv[e] = rs[e] * gm[e];
+    shift[e] = beta[(long)b * gb_bstride + c + e] - mu[e] * inv[e];
+    m1[e] = (float)(s[c + e] / count);
+    m2[e] = (float)(s[C + c + e] / count);
+  }
+  const long base = (long)b * HW * C + c;
+  for (long r = r0 + ty; r < r1; r += 8) {
+    f4 xv = bg_ld4(x, base + r * C), dv = bg_ld4(dy, base + r * C);
     float xe[4] = {xv.x, xv.y, xv.z, xv.w}, de[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float rs = rsqrtf(var[c + e] + eps);
-      const float gm = gamma[b * gb_bstride + c + e];
-      const float inv = rs * gm;
-      const float xhat = (xe[e] - mean[c + e]) * rs;
       float g = de[e];
-      if (act == BG_ACT_RELU && !(xe[e] * inv + (beta[b * gb_bstride + c + e] - mean[c + e] * inv) > 0.f)) g = 0.f;
-      const float m1 = (float)(s[c + e] / count), m2 = (float)(s[C + c + e] / count);
-      o[e] = rs * (gm * g - m1 - xhat * m2);
+      if (act == BG_ACT_RELU && !(xe[e] * inv[e] + shift[e] > 0.f)) g = 0.f;
+      o[e] = rs[e] * (gm[e] * g - m1[e] - (xe[e] - mu[e]) * rs[e] * m2[e]);
     }
-    bg_st4(dx, i * 4, f4{o[0], o[1], o[2], o[3]});
+    bg_st4(dx, base + r * C, f4{o[0], o[1], o[2], o[3]});
   }
 }
 
@@ -251,11 +273,11 @@ extern "C" int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean,
                                const float* beta, int gb_bstride, const double* s, double count, void* dx, int act, float eps,
                                int B, long HW, int C, int dtype, void* stream) {
   BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
-  const long total4 = (long)B * HW * C / 4;
-  const int blocks = (int)min(bg_cdiv(total4, 256), (long)bg_num_sms() * 16);
-  BG_DISPATCH_DTYPE(dtype, T, bn_bwd_apply_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, mean, var, gamma,
-                                                                                           beta, gb_bstride, s, count, (T*)dx, act,
-                                                                                           eps, HW, C, total4));
+  const int nchunk = bn_apply_chunks(B, HW, C);
+  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
+  BG_DISPATCH_DTYPE(dtype, T, bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, mean, var, gamma,
+                                                                                         beta, gb_bstride, s, count, (T*)dx, act,
+                                                                                         eps, HW, C, nchunk));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
