@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-entry-point timing breakdown here")
+    ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the captured CUDA graph")
     ap.add_argument("--quick", action="store_true", help="warm-up + timed steps only (for ncu captures): no e2e / breakdown pass")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -204,12 +205,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None
+    if not args.no_graph and not cfg.da_policy:
+        from biggan_tensorflow_b200.graph import GraphedStep
+        try:
+            graphed = GraphedStep(tr, devt["real"], devt["labels"], devt["z_d"], devt["z_g"], devt["labels"])
+        except Exception as e:           # capture is an optimisation: the eager CUDA step is the same computation
+            print("[bench] CUDA graph capture failed, running eagerly: %r" % (e,), file=sys.stderr)
+            graphed = None
+    run = graphed if graphed is not None else tr.train_step
+
     def step_resident():
-        return tr.train_step(devt["real"], devt["labels"], devt["z_d"], devt["z_g"], devt["labels"])
+        return run(devt["real"], devt["labels"], devt["z_d"], devt["z_g"], devt["labels"])
 
     def step_e2e():
-        d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
-        dl, gl = tr.train_step(d["real"], d["labels"], d["z_d"], d["z_g"], d["labels"])
+        if graphed is not None:          # H2D straight into the graph's static input buffers
+            dl, gl = run(host["real"], host["labels"], host["z_d"], host["z_g"], host["labels"])
+        else:
+            d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+            dl, gl = run(d["real"], d["labels"], d["z_d"], d["z_g"], d["labels"])
         return float(dl.cpu()), float(gl.cpu())        # device->host read of the step's result
 
     def timed(fn, steps):
@@ -232,7 +246,7 @@ def main():
         sampler.start()
     l0 = _lib.launch_count
     ms_step, _ = timed(step_resident, args.steps)
-    launches = (_lib.launch_count - l0) // args.steps
+    launches = graphed.launches if graphed is not None else (_lib.launch_count - l0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
     if args.quick:
         if rank == 0:
@@ -243,7 +257,7 @@ def main():
 
     # per-entry-point breakdown of one more step (CUDA events around every C-ABI call on the launch stream)
     _lib.profile_begin()
-    step_resident()
+    tr.train_step(devt["real"], devt["labels"], devt["z_d"], devt["z_g"], devt["labels"])      # eager, so that events bracket each call
     prof = _lib.profile_end()
     if rank != 0:
         return
@@ -280,7 +294,7 @@ def main():
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e, "losses": list(losses)},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": launches, "cuda_graph": graphed is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -88,7 +88,9 @@ extern "C" int bg_logistic_cls_fwd_bwd(const void* logits, const float* labels, 
 // m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g^2 ; p -= lr_t * m / (sqrt(v) + eps) ; ema = d*ema + (1-d)*p
 __global__ void __launch_bounds__(256)
 adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                float* __restrict__ ema, long n, float lr_t, float b1, float b2, float eps, float d, float gscale) {
+                float* __restrict__ ema, long n, float lr_host, const float* __restrict__ lr_dev, float b1, float b2, float eps, float d,
+                float gscale) {
+  const float lr_t = lr_dev ? lr_dev[0] : lr_host;       // device scalar: the step size can change under CUDA-graph replay
   long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const long stride = (long)gridDim.x * blockDim.x * 4;
   for (; i < n; i += stride) {
@@ -127,13 +129,27 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
   }
 }
 
-extern "C" int bg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float lr_t, float beta1,
-                                float beta2, float eps, float ema_decay, float grad_scale, void* stream) {
+extern "C" int bg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float lr_t, const float* lr_t_dev,
+                                float beta1, float beta2, float eps, float ema_decay, float grad_scale, void* stream) {
   if (n <= 0) return BG_OK;
   long blocks = bg_cdiv(n, 1024);
   const long mx = (long)bg_num_sms() * 8;
   if (blocks > mx) blocks = mx;
-  adam_ema_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, lr_t, beta1, beta2, eps, ema_decay, grad_scale);
+  adam_ema_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, lr_t, lr_t_dev, beta1, beta2, eps, ema_decay, grad_scale);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// state = {t, lr_t}: t += 1; lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)  (tf.train.AdamOptimizer); keeping the step
+// counter on the device makes the whole training step replayable as one CUDA graph
+__global__ void adam_lr_kernel(float* state, float lr, float b1, float b2) {
+  const float t = state[0] + 1.f;
+  state[0] = t;
+  const double c1 = 1.0 - pow((double)b1, (double)t), c2 = 1.0 - pow((double)b2, (double)t);
+  state[1] = (float)((double)lr * sqrt(c2) / c1);
+}
+extern "C" int bg_adam_lr_step(float* state, float lr, float beta1, float beta2, void* stream) {
+  adam_lr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

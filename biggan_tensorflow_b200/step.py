@@ -90,7 +90,8 @@ class Trainer:
             ar = self.store.pack(net)
             n = ar["params"].numel()
             self.opt[net] = {"m": torch.zeros(n, device=dev), "v": torch.zeros(n, device=dev),
-                             "ema": ar["params"].clone() if net == "generator" else None}
+                             "ema": ar["params"].clone() if net == "generator" else None,
+                             "state": torch.zeros(2, device=dev)}          # [t, lr_t]
         if cfg.acgan:
             self.cls_weights = torch.ones(cfg.n_labels, device=dev)            # BigGAN.py:100
         self.store.begin_phase()
@@ -130,13 +131,14 @@ class Trainer:
             dist.all_reduce(ar["grads"], group=self.pg)          # NCCL over NVLink; sum == global-batch gradient
         return ar
 
-    def _adam(self, net, lr, t):
+    def _adam(self, net, lr):
+        """Adam(+EMA) over the network's flat arena; the step counter and lr_t live on the device (graph-replayable)."""
         cfg = self.cfg
         ar = self.store.arenas[net]
         o = self.opt[net]
-        lr_t = lr * math.sqrt(1.0 - cfg.beta2 ** t) / (1.0 - cfg.beta1 ** t)     # tf.train.AdamOptimizer
+        call("bg_adam_lr_step", o["state"], float(lr), float(cfg.beta1), float(cfg.beta2), stream())
         call("bg_adam_ema_step", ar["params"], ar["grads"], o["m"], o["v"], o["ema"], ar["params"].numel(),
-             float(lr_t), float(cfg.beta1), float(cfg.beta2), 1e-8, float(cfg.moving_decay), 1.0, stream())
+             0.0, o["state"][1:], float(cfg.beta1), float(cfg.beta2), 1e-8, float(cfg.moving_decay), 1.0, stream())
 
     def _as_input(self, img):
         t = Tensor(img)
@@ -169,8 +171,7 @@ class Trainer:
         backward([(d_loss, torch.ones(1, device=real.device))])
         self._finish_grads("discriminator")
         if apply:
-            self.t_d += 1
-            self._adam("discriminator", cfg.d_lr, self.t_d)
+            self._adam("discriminator", cfg.d_lr)
         return d_loss.data, {"fake": fake, "real_logits": real_logits, "fake_logits": fake_logits}
 
     def g_update(self, z, cls_z, apply=True):
@@ -189,8 +190,7 @@ class Trainer:
         backward([(g_loss, torch.ones(1, device=z.device))])
         self._finish_grads("generator")
         if apply:
-            self.t_g += 1
-            self._adam("generator", cfg.g_lr, self.t_g)
+            self._adam("generator", cfg.g_lr)
         return g_loss.data, {"fake": fake, "fake_logits": out["real"]}
 
     def train_step(self, real, labels, z_d, z_g, cls_z):

@@ -214,11 +214,14 @@ int bg_diffaug_bwd(const void* dy, void* dx, const float* rnd_f, const int* rnd_
 /* ---------------------------------------------------------------------------------------------
  * Optimizer -- tf.train.AdamOptimizer + contrib MovingAverageOptimizer (BigGAN.py:923-926).
  * One launch over a flat parameter arena: m,v,p(,ema) updated in place from g.
- * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is computed by the caller.  grad_scale multiplies g first.
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) is computed by the caller; lr_t_dev (device scalar, optional) overrides
+ * lr_t so that a captured CUDA graph can be replayed with a new step size.  grad_scale multiplies g first.
  * ------------------------------------------------------------------------------------------- */
 int bg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float lr_t,
-                     float beta1, float beta2, float eps, float ema_decay, float grad_scale,
-                     void* stream);
+                     const float* lr_t_dev, float beta1, float beta2, float eps, float ema_decay,
+                     float grad_scale, void* stream);
+/* state[0] = t (step count, as float) += 1; state[1] = lr*sqrt(1-beta2^t)/(1-beta1^t): device-side Adam schedule */
+int bg_adam_lr_step(float* state, float lr, float beta1, float beta2, void* stream);
 int bg_fill(void* p, float value, long n, int dtype, void* stream);
 
 #ifdef __cplusplus

@@ -369,7 +369,7 @@ def test_adam_ema_matches_tf_formula():
     for t in range(1, 4):
         g = rng.standard_normal(n).astype(np.float32)
         lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
-        call("bg_adam_ema_step", tp, torch.from_numpy(g).cuda(), tm, tv, te, n, float(lr_t), b1, b2, 1e-8, d, 1.0, stream())
+        call("bg_adam_ema_step", tp, torch.from_numpy(g).cuda(), tm, tv, te, n, float(lr_t), None, b1, b2, 1e-8, d, 1.0, stream())
         m64 = b1 * m64 + (1 - b1) * g
         v64 = b2 * v64 + (1 - b2) * g.astype(np.float64) ** 2
         p64 = p64 - lr_t * m64 / (np.sqrt(v64) + 1e-8)
