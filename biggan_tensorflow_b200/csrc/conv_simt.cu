@@ -20,7 +20,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gather_gemm_fwd_kernel(const __grid_constant__ BgGeom g, const T* __restrict__ in,
                        const T* __restrict__ w, const float* __restrict__ bias,
-                       const T* residual, T* out, int act, int tiles_per_phase) {
+                       const T* residual, T* out, int act, int tiles_per_phase, int kc, float* __restrict__ partial) {
+  // kc > 0: split-K (skinny GEMMs, e.g. fully_connected with M = batch rows): this CTA contracts over
+  // channels [blockIdx.z*kc, +kc) and writes an fp32 partial tile; splitk_fwd_reduce_kernel finishes.
   __shared__ float As[GF_BK][GF_BM + 4];
   __shared__ float Bs[GF_BK][GF_BN + 4];
   const int tid = threadIdx.x;
@@ -64,28 +66,29 @@ gather_gemm_fwd_kernel(const __grid_constant__ BgGeom g, const T* __restrict__ i
     ok = ok && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
     const long abase = (((long)ab * g.Hi + iy) * g.Wi + ix) * g.Ci;
     const T* wt = w + (long)tap.widx * g.wtap;
-    for (int k0 = 0; k0 < g.Ci; k0 += GF_BK) {
+    const int k_lo = kc ? blockIdx.z * kc : 0, k_hi = kc ? min(g.Ci, k_lo + kc) : g.Ci;
+    for (int k0 = k_lo; k0 < k_hi; k0 += GF_BK) {
       float ra[8], rb[4];
       if (vecA) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           int k = k0 + ka + h * 4;
           f4 v = {0.f, 0.f, 0.f, 0.f};
-          if (ok && k < g.Ci) v = bg_ld4(in, abase + k);
+          if (ok && k < k_hi) v = bg_ld4(in, abase + k);
           ra[h * 4 + 0] = v.x; ra[h * 4 + 1] = v.y; ra[h * 4 + 2] = v.z; ra[h * 4 + 3] = v.w;
         }
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           int k = k0 + ka + e;
-          ra[e] = (ok && k < g.Ci) ? bg_ld(in, abase + k) : 0.f;
+          ra[e] = (ok && k < k_hi) ? bg_ld(in, abase + k) : 0.f;
         }
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         int k = k0 + kb + (n_contig ? 0 : e);
         int n = n0 + nb + (n_contig ? e : 0);
-        rb[e] = (k < g.Ci && n < g.Co) ? bg_ld(wt, (long)k * g.wk + (long)n * g.wn) : 0.f;
+        rb[e] = (k < k_hi && n < g.Co) ? bg_ld(wt, (long)k * g.wk + (long)n * g.wn) : 0.f;
       }
       __syncthreads();
 #pragma unroll
@@ -111,6 +114,19 @@ gather_gemm_fwd_kernel(const __grid_constant__ BgGeom g, const T* __restrict__ i
     }
   }
   // epilogue
+  if (partial) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = mt * GF_BM + ty * 8 + i;
+      if (m >= Mph) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < g.Co) partial[((long)blockIdx.z * Mph + m) * g.Co + n] = acc[i][j];
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = mt * GF_BM + ty * 8 + i;
@@ -380,9 +396,36 @@ size_t bg_small_wgrad_ws(const BgGeom& g, long numel);
 int bg_small_wgrad(const BgGeom& g, const void* in, const void* og, float* dw, long numel, int dtype, void* ws, size_t ws_bytes,
                    cudaStream_t st, int* taken);
 
+// split-K factor for skinny single-tap GEMMs (fully_connected: M = batch rows): enough CTAs to fill the GPU
+static int fwd_ksplit(const BgGeom& g) {
+  if (g.nphase != 1 || g.ph[0].ntaps != 1 || g.ostep != 1 || g.ph[0].oy0 || g.ph[0].ox0) return 1;
+  const long M = (long)g.B * g.ph[0].Hp * g.ph[0].Wp;
+  if (M > 1024 || g.Ci < 256) return 1;
+  const long tiles = bg_cdiv(M, GF_BM) * bg_cdiv(g.Co, GF_BN);
+  long ks = bg_cdiv(2L * bg_num_sms(), tiles);
+  ks = min(ks, (long)g.Ci / 64);
+  ks = min(ks, 64L);
+  return (int)max(ks, 1L);
+}
+static size_t fwd_ksplit_bytes(const BgGeom& g) {
+  const int ks = fwd_ksplit(g);
+  return ks > 1 ? (size_t)ks * g.B * g.ph[0].Hp * g.ph[0].Wp * g.Co * sizeof(float) : 0;
+}
+
+__global__ void splitk_fwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, const float* residual,
+                                         float* out, long n, int Co, int nz, int act) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < nz; ++z) s += part[(long)z * n + i];
+    if (bias) s += bias[i % Co];
+    if (residual) s += residual[i];
+    out[i] = bg_apply_act(s, act);
+  }
+}
+
 template <typename T>
 static int launch_fwd_type(const BgGeom& g, const T* in, const T* w, const float* bias, const T* residual, T* out,
-                           int act, cudaStream_t st) {
+                           int act, cudaStream_t st, void* ws = nullptr, size_t ws_bytes = 0) {
   if (g.Co <= 4 || g.Ci <= 4) {      // RGB layers: memory-bound direct kernels (conv_small.cu)
     int taken = 0;
     int rc = bg_small_fwd(g, in, w, bias, residual, out, act, sizeof(T) == 4 ? BG_F32 : BG_BF16, st, &taken);
@@ -392,14 +435,30 @@ static int launch_fwd_type(const BgGeom& g, const T* in, const T* w, const float
   long maxM = 0;
   for (int p = 0; p < g.nphase; ++p) maxM = max(maxM, (long)g.B * g.ph[p].Hp * g.ph[p].Wp);
   const int tiles = (int)bg_cdiv(maxM, GF_BM);
+  const int ks = fwd_ksplit(g);
+  if (ks > 1 && sizeof(T) == 4 && ws && ws_bytes >= (size_t)ks * maxM * g.Co * sizeof(float)) {
+    const int kc = (int)(bg_cdiv(bg_cdiv(g.Ci, ks), 16) * 16);
+    const int nz = (int)bg_cdiv(g.Ci, kc);
+    dim3 grid(tiles, (unsigned)bg_cdiv(g.Co, GF_BN), nz);
+    gather_gemm_fwd_kernel<T><<<grid, 256, 0, st>>>(g, in, w, nullptr, nullptr, out, 0, tiles, kc, (float*)ws);
+    BG_LAUNCH_CHECK();
+    const long n = maxM * g.Co;
+    splitk_fwd_reduce_kernel<<<(unsigned)min(bg_cdiv(n, 256), (long)bg_num_sms() * 8), 256, 0, st>>>(
+        (const float*)ws, bias, (const float*)residual, (float*)out, n, g.Co, nz, act);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+  }
   dim3 grid(tiles * g.nphase, (unsigned)bg_cdiv(g.Co, GF_BN));
-  gather_gemm_fwd_kernel<T><<<grid, 256, 0, st>>>(g, in, w, bias, residual, out, act, tiles);
+  gather_gemm_fwd_kernel<T><<<grid, 256, 0, st>>>(g, in, w, bias, residual, out, act, tiles, 0, nullptr);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 
 extern "C" size_t bg_conv2d_fwd_workspace_bytes(const bg_conv_desc* d, int dtype) {
-  return (dtype == BG_BF16 && reflect_padded(d)) ? padded_bytes(d, 2) : 0;
+  if (dtype == BG_BF16 && reflect_padded(d)) return padded_bytes(d, 2);
+  BgGeom g;
+  if (dtype == BG_F32 && bg_build_geom(d, BG_OP_FWD, &g) == BG_OK) return fwd_ksplit_bytes(g);
+  return 0;
 }
 
 extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const void* w_t, const float* bias,
@@ -429,7 +488,7 @@ extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w
       }
     }
   }
-  BG_DISPATCH_DTYPE(dtype, T, return launch_fwd_type<T>(g, (const T*)x, (const T*)w, bias, (const T*)residual, (T*)y, act, st));
+  BG_DISPATCH_DTYPE(dtype, T, return launch_fwd_type<T>(g, (const T*)x, (const T*)w, bias, (const T*)residual, (T*)y, act, st, ws, ws_bytes));
 }
 
 static bool dgrad_padded(const bg_conv_desc* d) {
@@ -437,7 +496,11 @@ static bool dgrad_padded(const bg_conv_desc* d) {
 }
 
 extern "C" size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype) {
-  if (!dgrad_padded(d)) return 0;
+  if (!dgrad_padded(d)) {
+    BgGeom g;
+    if (dtype == BG_F32 && bg_build_geom(d, BG_OP_DGRAD, &g) == BG_OK) return fwd_ksplit_bytes(g);
+    return 0;
+  }
   size_t es = dtype == BG_F32 ? 4 : 2;
   return (size_t)d->B * (d->Hi + d->pad_t + d->pad_b) * (d->Wi + d->pad_l + d->pad_r) * d->Ci * es + 256;
 }
@@ -463,7 +526,8 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
     }
   }
   if (!done) {
-    BG_DISPATCH_DTYPE(dtype, T, rc = launch_fwd_type<T>(g, (const T*)dy, (const T*)w, nullptr, (const T*)gres, (T*)gout, BG_ACT_NONE, st));
+    BG_DISPATCH_DTYPE(dtype, T, rc = launch_fwd_type<T>(g, (const T*)dy, (const T*)w, nullptr, (const T*)gres, (T*)gout, BG_ACT_NONE, st,
+                                                        padded ? nullptr : ws, padded ? 0 : ws_bytes));
     if (rc) return rc;
   }
   if (padded) {

@@ -2,6 +2,11 @@
 // HBM-bound: W [K,C] fp32 is streamed once from HBM for both matvecs (the second use of each row
 // tile hits L1/L2), once more for the scale pass.  All reductions are fixed-order (deterministic,
 // so data-parallel replicas keep bit-identical u).
+//
+// Two front ends over the same device bodies: per-matrix entry points (bg_sn_power_iter / bg_sn_scale /
+// bg_sn_bwd) and GROUPED entry points (bg_sn_group_*) that process every weight matrix of a network in
+// 4 (forward) / 2 (backward) launches from a device-resident plan -- the per-step cost of ~60 small
+// matrices is otherwise launch latency, which does not shrink with data parallelism.
 #include "bg_common.cuh"
 
 #define SN_MAX_RT 64
@@ -13,12 +18,13 @@ static inline int sn_rows_per_block(int K) {
   return (int)rt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// device bodies (blk = block index within the matrix)
+// ---------------------------------------------------------------------------------------------
 // v[r] = W[r,:].u for the block's rows, then pcol[blk][c] = sum_r v[r] * W[r,c]
-__global__ void __launch_bounds__(256)
-sn_matvec_kernel(const float* __restrict__ W, const float* __restrict__ u, float* __restrict__ vraw,
-                 float* __restrict__ pcol, int K, int C, int RT) {
-  __shared__ float vs[SN_MAX_RT];
-  const int r0 = blockIdx.x * RT;
+__device__ __forceinline__ void sn_matvec_body(const float* __restrict__ W, const float* __restrict__ u, float* __restrict__ vraw,
+                                               float* __restrict__ pcol, int K, int C, int RT, int blk, float* vs) {
+  const int r0 = blk * RT;
   const int nr = min(RT, K - r0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool vec = (C % 4 == 0);
@@ -38,7 +44,7 @@ sn_matvec_kernel(const float* __restrict__ W, const float* __restrict__ u, float
     if (lane == 0) { vs[r] = s; vraw[r0 + r] = s; }
   }
   __syncthreads();
-  float* dst = pcol + (long)blockIdx.x * C;
+  float* dst = pcol + (long)blk * C;
   if (vec) {
     for (int c = threadIdx.x * 4; c < C; c += 1024) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -58,19 +64,17 @@ sn_matvec_kernel(const float* __restrict__ W, const float* __restrict__ u, float
   }
 }
 
-__global__ void sn_colreduce_kernel(const float* __restrict__ pcol, float* __restrict__ uraw, int nblk, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void sn_colreduce_body(const float* __restrict__ pcol, float* __restrict__ uraw, int nblk, int C, int blk) {
+  const int c = blk * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
   for (int b = 0; b < nblk; ++b) s += pcol[(long)b * C + c];
   uraw[c] = s;
 }
 
-// single block: normalise v, form u' = uraw * inv|v|, u_hat, sigma = u'.u_hat
-__global__ void __launch_bounds__(1024)
-sn_finalize_kernel(float* __restrict__ v, const float* __restrict__ uraw, float* __restrict__ u_out,
-                   float* __restrict__ sigma, int K, int C) {
-  __shared__ float sh[33];
+// one block: normalise v, form u' = uraw * inv|v|, u_hat, sigma = u'.u_hat
+__device__ __forceinline__ void sn_finalize_body(float* __restrict__ v, const float* __restrict__ uraw, float* __restrict__ u_out,
+                                                 float* __restrict__ sigma, int K, int C, float* sh) {
   float s = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) { float t = v[k]; s += t * t; }
   const float ssv = bg_block_sum(s, sh);
@@ -82,6 +86,74 @@ sn_finalize_kernel(float* __restrict__ v, const float* __restrict__ uraw, float*
   const float inv_u = rsqrtf(fmaxf(ssu, 1e-12f));
   for (int c = threadIdx.x; c < C; c += blockDim.x) u_out[c] = uraw[c] * inv_v * inv_u;
   if (threadIdx.x == 0) sigma[0] = ssu * inv_u;            // (v_hat W) . u_hat
+}
+
+// 32x32 tile (xt, yt) of tap z: out[(z*r_pad + r)*c_pad + c] and out_t[z][c][r]; 256 threads
+template <typename T>
+__device__ __forceinline__ void sn_scale_tile_body(const float* __restrict__ W, float sg, T* __restrict__ out, T* __restrict__ out_t,
+                                                   int rows, int C, int r_pad, int c_pad, int z, int yt, int xt, float (*tile)[33]) {
+  const long tapoff = (long)z * rows * C, tapoff_p = (long)z * r_pad * c_pad;
+  const int r0 = yt * 32, c0 = xt * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < rows && c < C) {
+      const float v = W[tapoff + (long)r * C + c] / sg;
+      tile[i][tx] = v;
+      bg_st(out, tapoff_p + (long)r * c_pad + c, v);
+    }
+  }
+  if (!out_t) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < C) bg_st(out_t, tapoff_p + (long)c * r_pad + r, tile[tx][i]);
+  }
+}
+
+__device__ __forceinline__ long sn_g_index(long i, int C, int rows, int r_pad, int g_ld) {
+  const long k = i / C;
+  return ((k / rows) * r_pad + (k % rows)) * g_ld + (i % C);
+}
+
+// part[blk] = sum over this block's strided slice of G.W   (nblk blocks of 256 threads)
+__device__ __forceinline__ void sn_dot_body(const float* __restrict__ G, const float* __restrict__ W, float* __restrict__ part, long n,
+                                            int C, int g_ld, int rows, int r_pad, int blk, int nblk, float* sh) {
+  float s = 0.f;
+  for (long i = (long)blk * blockDim.x + threadIdx.x; i < n; i += (long)nblk * blockDim.x)
+    s = fmaf(G[sn_g_index(i, C, rows, r_pad, g_ld)], W[i], s);
+  s = bg_block_sum(s, sh);
+  if (threadIdx.x == 0) part[blk] = s;
+}
+
+// dW = G/sigma - (<G,W>/sigma^2) v_hat[k] u_hat[c]
+__device__ __forceinline__ void sn_bwd_apply_body(const float* __restrict__ G, const float* __restrict__ part, int npart,
+                                                  const float* __restrict__ u_hat, const float* __restrict__ v_hat, float sg,
+                                                  float* __restrict__ dW, int K, int C, int g_ld, int rows, int r_pad, int blk, int nblk,
+                                                  float* sh) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < npart; i += blockDim.x) s += part[i];
+  const float dot = bg_block_sum(s, sh);       // identical in every block: fixed order
+  const float coef = dot / (sg * sg);
+  const long n = (long)K * C;
+  for (long i = (long)blk * blockDim.x + threadIdx.x; i < n; i += (long)nblk * blockDim.x) {
+    const int k = (int)(i / C), c = (int)(i - (long)k * C);
+    dW[i] = G[sn_g_index(i, C, rows, r_pad, g_ld)] / sg - coef * v_hat[k] * u_hat[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-matrix kernels / entry points
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sn_matvec_kernel(const float* W, const float* u, float* vraw, float* pcol, int K, int C, int RT) {
+  __shared__ float vs[SN_MAX_RT];
+  sn_matvec_body(W, u, vraw, pcol, K, C, RT, blockIdx.x, vs);
+}
+__global__ void sn_colreduce_kernel(const float* pcol, float* uraw, int nblk, int C) { sn_colreduce_body(pcol, uraw, nblk, C, blockIdx.x); }
+__global__ void __launch_bounds__(1024) sn_finalize_kernel(float* v, const float* uraw, float* u_out, float* sigma, int K, int C) {
+  __shared__ float sh[33];
+  sn_finalize_body(v, uraw, u_out, sigma, K, C, sh);
 }
 
 extern "C" size_t bg_sn_workspace_bytes(int K, int C) {
@@ -110,7 +182,7 @@ extern "C" int bg_sn_power_iter(const float* W, const float* u, float* u_out, fl
   return BG_OK;
 }
 
-// out = W / sigma (+ per-tap transposed copy out_t[t][c][r])
+// out = W / sigma, plain contiguous case
 template <typename T>
 __global__ void sn_scale_kernel(const float* __restrict__ W, const float* __restrict__ sigma, T* __restrict__ out, long n) {
   const float sg = sigma[0];
@@ -120,36 +192,19 @@ __global__ void sn_scale_kernel(const float* __restrict__ W, const float* __rest
     float4 w4 = *reinterpret_cast<const float4*>(W + i);
     bg_st4(out, i, f4{w4.x / sg, w4.y / sg, w4.z / sg, w4.w / sg});
   }
-  // tail (n % 4) handled by the first threads of block 0
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {      // tail (n % 4)
     long j = (n & ~3L) + threadIdx.x;
     bg_st(out, j, W[j] / sg);
   }
 }
 
-// generic writer: out[(t*r_pad + r)*c_pad + c] and out_t[t][c][r] (tap stride c_pad*r_pad, row stride r_pad);
-// destinations with r_pad > rows or c_pad > C are pre-zeroed by the caller (zero-padded channels)
+// generic writer (padding and/or per-tap transposed copy); destinations with r_pad > rows or c_pad > C are
+// pre-zeroed by the caller (zero-padded channels)
 template <typename T>
-__global__ void sn_scale_t_kernel(const float* __restrict__ W, const float* __restrict__ sigma, T* __restrict__ out,
-                                  T* __restrict__ out_t, int rows, int C, int r_pad, int c_pad) {
+__global__ void __launch_bounds__(256)
+sn_scale_t_kernel(const float* W, const float* sigma, T* out, T* out_t, int rows, int C, int r_pad, int c_pad) {
   __shared__ float tile[32][33];
-  const float sg = sigma[0];
-  const long tapoff = (long)blockIdx.z * rows * C, tapoff_p = (long)blockIdx.z * r_pad * c_pad;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    if (r < rows && c < C) {
-      const float v = W[tapoff + (long)r * C + c] / sg;
-      tile[i][threadIdx.x] = v;
-      bg_st(out, tapoff_p + (long)r * c_pad + c, v);
-    }
-  }
-  if (!out_t) return;
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < C) bg_st(out_t, tapoff_p + (long)c * r_pad + r, tile[threadIdx.x][i]);
-  }
+  sn_scale_tile_body<T>(W, sigma[0], out, out_t, rows, C, r_pad, c_pad, blockIdx.z, blockIdx.y, blockIdx.x, tile);
 }
 
 extern "C" int bg_sn_scale(const float* W, const float* sigma, void* out, void* out_t, int dtype, int taps, int rows,
@@ -161,45 +216,23 @@ extern "C" int bg_sn_scale(const float* W, const float* sigma, void* out, void* 
     const int blocks = (int)min(bg_cdiv(n, 1024), (long)bg_num_sms() * 8);
     BG_DISPATCH_DTYPE(dtype, T, sn_scale_kernel<T><<<blocks, 256, 0, st>>>(W, sigma, (T*)out, n));
   } else {
-    dim3 grid((unsigned)bg_cdiv(C, 32), (unsigned)bg_cdiv(rows, 32), taps), block(32, 8);
-    BG_DISPATCH_DTYPE(dtype, T, sn_scale_t_kernel<T><<<grid, block, 0, st>>>(W, sigma, (T*)out, (T*)out_t, rows, C, r_pad, c_pad));
+    dim3 grid((unsigned)bg_cdiv(C, 32), (unsigned)bg_cdiv(rows, 32), taps);
+    BG_DISPATCH_DTYPE(dtype, T, sn_scale_t_kernel<T><<<grid, 256, 0, st>>>(W, sigma, (T*)out, (T*)out_t, rows, C, r_pad, c_pad));
   }
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 
-// backward: dW = G/sigma - (<G,W>/sigma^2) v_hat[k] u_hat[c]
 __global__ void __launch_bounds__(256)
-sn_dot_partial_kernel(const float* __restrict__ G, const float* __restrict__ W, float* __restrict__ part, long n, int C, int g_ld, int rows, int r_pad) {
+sn_dot_partial_kernel(const float* G, const float* W, float* part, long n, int C, int g_ld, int rows, int r_pad) {
   __shared__ float sh[33];
-  float s = 0.f;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const long k = i / C;
-    const long gi = ((k / rows) * r_pad + (k % rows)) * g_ld + (i % C);
-    s = fmaf(G[gi], W[i], s);
-  }
-  s = bg_block_sum(s, sh);
-  if (threadIdx.x == 0) part[blockIdx.x] = s;
+  sn_dot_body(G, W, part, n, C, g_ld, rows, r_pad, blockIdx.x, gridDim.x, sh);
 }
-
 __global__ void __launch_bounds__(256)
-sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ part, int npart, const float* __restrict__ u_hat,
-                    const float* __restrict__ v_hat, const float* __restrict__ sigma, float* __restrict__ dW, int K, int C, int g_ld, int rows, int r_pad) {
+sn_bwd_apply_kernel(const float* G, const float* part, int npart, const float* u_hat, const float* v_hat, const float* sigma, float* dW,
+                    int K, int C, int g_ld, int rows, int r_pad) {
   __shared__ float sh[33];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < npart; i += blockDim.x) s += part[i];
-  const float dot = bg_block_sum(s, sh);       // identical in every block: fixed order
-  const float sg = sigma[0];
-  const float coef = dot / (sg * sg);
-  const long n = (long)K * C;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const int k = (int)(i / C), c = (int)(i - (long)k * C);
-    dW[i] = G[((long)(k / rows) * r_pad + (k % rows)) * g_ld + c] / sg - coef * v_hat[k] * u_hat[c];
-  }
+  sn_bwd_apply_body(G, part, npart, u_hat, v_hat, sigma[0], dW, K, C, g_ld, rows, r_pad, blockIdx.x, gridDim.x, sh);
 }
 
 extern "C" int bg_sn_bwd(const float* W, const float* dWn, int rows, int r_pad, int g_ld, const float* u_hat, const float* v_hat,
@@ -213,6 +246,172 @@ extern "C" int bg_sn_bwd(const float* W, const float* dWn, int rows, int r_pad, 
   BG_LAUNCH_CHECK();
   const int blocks = (int)min(bg_cdiv(n, 256), (long)bg_num_sms() * 8);
   sn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dWn, (const float*)ws, npart, u_hat, v_hat, sigma, dW, K, C, g_ld, rows, r_pad);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grouped front end: every matrix of a network per launch
+// ---------------------------------------------------------------------------------------------
+struct SnItemDev {
+  bg_sn_item it;
+  float* pcol; float* uraw; float* dotpart;
+  int RT, nblk, npart, napply;
+  int sx, sy;            // scale tiles per tap (x over C, y over rows)
+};
+struct SnMap { int item, local; };
+
+// plan layout (device): [SnItemDev x n][SnMap matvec][SnMap colred][SnMap scale][SnMap dot][SnMap apply][float workspace]
+// totals (host, int[8]): n, T_matvec, T_colred, T_scale, T_dot, T_apply, off_maps (bytes), 0
+struct SnPlanSizes { long t[5]; size_t off_maps, off_ws, total; };
+
+static void sn_item_sizes(const bg_sn_item& it, SnItemDev* d) {
+  d->it = it;
+  d->RT = sn_rows_per_block(it.K);
+  d->nblk = (int)bg_cdiv(it.K, d->RT);
+  const long n = (long)it.K * it.C;
+  d->npart = (int)min(bg_cdiv(n, 1024), 256L);
+  d->napply = (int)min(bg_cdiv(n, 256 * 8), 1024L);
+  if (d->napply < 1) d->napply = 1;
+  d->sx = (int)bg_cdiv(it.C, 32);
+  d->sy = (int)bg_cdiv(it.rows, 32);
+}
+
+static SnPlanSizes sn_plan_sizes(const bg_sn_item* items, int n) {
+  SnPlanSizes s;
+  memset(&s, 0, sizeof(s));
+  size_t wsf = 0;
+  for (int i = 0; i < n; ++i) {
+    SnItemDev d;
+    sn_item_sizes(items[i], &d);
+    s.t[0] += d.nblk;
+    s.t[1] += bg_cdiv(items[i].C, 256);
+    s.t[2] += (long)d.sx * d.sy * items[i].taps;
+    s.t[3] += d.npart;
+    s.t[4] += d.napply;
+    wsf += (size_t)(d.nblk + 1) * items[i].C + d.npart + 8;
+    wsf = (wsf + 3) / 4 * 4;
+  }
+  s.off_maps = (sizeof(SnItemDev) * n + 255) / 256 * 256;
+  s.off_ws = (s.off_maps + sizeof(SnMap) * (s.t[0] + s.t[1] + s.t[2] + s.t[3] + s.t[4]) + 255) / 256 * 256;
+  s.total = s.off_ws + wsf * sizeof(float) + 256;
+  return s;
+}
+
+extern "C" size_t bg_sn_group_plan_bytes(const bg_sn_item* items, int n) { return sn_plan_sizes(items, n).total; }
+
+// builds the plan on the host and copies it to plan_dev (synchronous; done once at build time)
+extern "C" int bg_sn_group_plan(const bg_sn_item* items, int n, void* plan_dev, size_t plan_bytes, int* totals) {
+  BG_REQUIRE(n > 0, BG_ERR_SHAPE, "sn_group: empty");
+  const SnPlanSizes sz = sn_plan_sizes(items, n);
+  BG_REQUIRE(plan_dev && plan_bytes >= sz.total, BG_ERR_WORKSPACE, "sn_group: plan buffer too small");
+  char* host = (char*)malloc(sz.off_ws);
+  BG_REQUIRE(host != nullptr, BG_ERR_CUDA, "sn_group: out of host memory");
+  memset(host, 0, sz.off_ws);
+  SnItemDev* its = (SnItemDev*)host;
+  SnMap* maps = (SnMap*)(host + sz.off_maps);
+  SnMap* m[5];
+  m[0] = maps;
+  for (int k = 1; k < 5; ++k) m[k] = m[k - 1] + sz.t[k - 1];
+  long cur[5] = {0, 0, 0, 0, 0};
+  float* ws = (float*)((char*)plan_dev + sz.off_ws);
+  size_t wsf = 0;
+  for (int i = 0; i < n; ++i) {
+    SnItemDev* d = &its[i];
+    sn_item_sizes(items[i], d);
+    if (!(items[i].K > 0 && items[i].C > 0 && items[i].taps > 0 && items[i].K == items[i].taps * items[i].rows &&
+          items[i].r_pad >= items[i].rows && items[i].c_pad >= items[i].C)) {
+      free(host);
+      bg_set_error("sn_group: bad item %d", i);
+      return BG_ERR_SHAPE;
+    }
+    d->pcol = ws + wsf;
+    d->uraw = d->pcol + (size_t)d->nblk * items[i].C;
+    d->dotpart = d->uraw + items[i].C;
+    wsf += (size_t)(d->nblk + 1) * items[i].C + d->npart + 8;
+    wsf = (wsf + 3) / 4 * 4;
+    const long cnt[5] = {d->nblk, bg_cdiv(items[i].C, 256), (long)d->sx * d->sy * items[i].taps, d->npart, d->napply};
+    for (int k = 0; k < 5; ++k)
+      for (long j = 0; j < cnt[k]; ++j) { m[k][cur[k]].item = i; m[k][cur[k]].local = (int)j; cur[k]++; }
+  }
+  cudaError_t e = cudaMemcpy(plan_dev, host, sz.off_ws, cudaMemcpyHostToDevice);
+  free(host);
+  BG_CHECK_CUDA(e);
+  totals[0] = n;
+  for (int k = 0; k < 5; ++k) totals[1 + k] = (int)sz.t[k];
+  totals[6] = (int)sz.off_maps;
+  totals[7] = 0;
+  return BG_OK;
+}
+
+__global__ void __launch_bounds__(256) sng_matvec_kernel(const SnItemDev* its, const SnMap* map) {
+  __shared__ float vs[SN_MAX_RT];
+  const SnMap mp = map[blockIdx.x];
+  const SnItemDev& d = its[mp.item];
+  sn_matvec_body(d.it.W, d.it.u, d.it.v, d.pcol, d.it.K, d.it.C, d.RT, mp.local, vs);
+}
+__global__ void __launch_bounds__(256) sng_colreduce_kernel(const SnItemDev* its, const SnMap* map) {
+  const SnMap mp = map[blockIdx.x];
+  const SnItemDev& d = its[mp.item];
+  sn_colreduce_body(d.pcol, d.uraw, d.nblk, d.it.C, mp.local);
+}
+__global__ void __launch_bounds__(1024) sng_finalize_kernel(const SnItemDev* its) {
+  __shared__ float sh[33];
+  const SnItemDev& d = its[blockIdx.x];
+  sn_finalize_body(d.it.v, d.uraw, d.it.u, d.it.sigma, d.it.K, d.it.C, sh);
+}
+__global__ void __launch_bounds__(256) sng_scale_kernel(const SnItemDev* its, const SnMap* map) {
+  __shared__ float tile[32][33];
+  const SnMap mp = map[blockIdx.x];
+  const SnItemDev& d = its[mp.item];
+  const int per_tap = d.sx * d.sy;
+  const int z = mp.local / per_tap, r = mp.local - z * per_tap;
+  const float sg = d.it.sigma[0];
+  if (d.it.dtype == BG_F32)
+    sn_scale_tile_body<float>(d.it.W, sg, (float*)d.it.out, (float*)d.it.out_t, d.it.rows, d.it.C, d.it.r_pad, d.it.c_pad, z, r / d.sx, r % d.sx, tile);
+  else
+    sn_scale_tile_body<bf16>(d.it.W, sg, (bf16*)d.it.out, (bf16*)d.it.out_t, d.it.rows, d.it.C, d.it.r_pad, d.it.c_pad, z, r / d.sx, r % d.sx, tile);
+}
+__global__ void __launch_bounds__(256) sng_dot_kernel(const SnItemDev* its, const SnMap* map) {
+  __shared__ float sh[33];
+  const SnMap mp = map[blockIdx.x];
+  const SnItemDev& d = its[mp.item];
+  sn_dot_body(d.it.dWn, d.it.W, d.dotpart, (long)d.it.K * d.it.C, d.it.C, d.it.g_ld, d.it.rows, d.it.r_pad, mp.local, d.npart, sh);
+}
+__global__ void __launch_bounds__(256) sng_apply_kernel(const SnItemDev* its, const SnMap* map) {
+  __shared__ float sh[33];
+  const SnMap mp = map[blockIdx.x];
+  const SnItemDev& d = its[mp.item];
+  sn_bwd_apply_body(d.it.dWn, d.dotpart, d.npart, d.it.u, d.it.v, d.it.sigma[0], d.it.dW, d.it.K, d.it.C, d.it.g_ld, d.it.rows, d.it.r_pad,
+                    mp.local, d.napply, sh);
+}
+
+extern "C" int bg_sn_group_forward(const void* plan_dev, const int* totals, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const SnItemDev* its = (const SnItemDev*)plan_dev;
+  const SnMap* m0 = (const SnMap*)((const char*)plan_dev + totals[6]);
+  const SnMap* m1 = m0 + totals[1];
+  const SnMap* m2 = m1 + totals[2];
+  sng_matvec_kernel<<<totals[1], 256, 0, st>>>(its, m0);
+  BG_LAUNCH_CHECK();
+  sng_colreduce_kernel<<<totals[2], 256, 0, st>>>(its, m1);
+  BG_LAUNCH_CHECK();
+  sng_finalize_kernel<<<totals[0], 1024, 0, st>>>(its);
+  BG_LAUNCH_CHECK();
+  sng_scale_kernel<<<totals[3], 256, 0, st>>>(its, m2);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
+extern "C" int bg_sn_group_backward(const void* plan_dev, const int* totals, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const SnItemDev* its = (const SnItemDev*)plan_dev;
+  const SnMap* m0 = (const SnMap*)((const char*)plan_dev + totals[6]);
+  const SnMap* m3 = m0 + totals[1] + totals[2] + totals[3];
+  const SnMap* m4 = m3 + totals[4];
+  sng_dot_kernel<<<totals[4], 256, 0, st>>>(its, m3);
+  BG_LAUNCH_CHECK();
+  sng_apply_kernel<<<totals[5], 256, 0, st>>>(its, m4);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

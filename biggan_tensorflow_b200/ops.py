@@ -147,6 +147,10 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_
     hit = store.sn_cache.get(key)
     if hit is not None:
         return hit
+    reg = getattr(store, "sn_registry", None)
+    if reg is not None and key not in reg:       # the Trainer is enumerating the network's spectral norms
+        reg[key] = {"w": w, "u": u, "taps": _taps, "rows": rows, "r_pad": r_pad, "c_pad": c_pad, "out_dtype": out_dtype,
+                    "want_t": bool(_want_t), "key": key}
     base = store.sn_cache.get(("pi", u.name))
     if base is None:
         v_hat = empty([K], F32)

@@ -80,9 +80,11 @@ class Trainer:
         z = torch.zeros(2, 1, 1, cfg.z_dim, device=dev)
         cls = torch.zeros(2, max(cfg.n_labels, 1), device=dev)
         self.store.begin_phase()
+        self.store.sn_registry = {}                  # enumerate every spectral_norm call of both networks
         with no_grad():
             fake = generator(cfg, z, cls)
             discriminator(cfg, fake)
+        registry, self.store.sn_registry = self.store.sn_registry, None
         snap = {k: v.data.clone() for k, v in self.store.vars.items() if not v.trainable}
         for k, d in snap.items():       # undo the dry run's side effects on u / BN running stats
             self.store.vars[k].data.copy_(torch.from_numpy(self._initial(k, d.shape)).to(dev))
@@ -92,6 +94,9 @@ class Trainer:
             self.opt[net] = {"m": torch.zeros(n, device=dev), "v": torch.zeros(n, device=dev),
                              "ema": ar["params"].clone() if net == "generator" else None,
                              "state": torch.zeros(2, device=dev)}          # [t, lr_t]
+        from .sn_group import SnGroup
+        self.sn_groups = {net: SnGroup([e for e in registry.values() if net in e["u"].name])
+                          for net in ("generator", "discriminator")}
         if cfg.acgan:
             self.cls_weights = torch.ones(cfg.n_labels, device=dev)            # BigGAN.py:100
         self.store.begin_phase()
@@ -120,8 +125,11 @@ class Trainer:
             v.grad_owned = True
         self.store.begin_phase()
         clear_tape()
+        for grp in self.sn_groups.values():          # every forward of a network advances its u once per phase
+            grp.forward(self.store)
 
     def _finish_grads(self, net):
+        self.sn_groups[net].backward()
         ar = self.store.arenas[net]
         for v in ar["vars"]:
             if not v.grad_set:

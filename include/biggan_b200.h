@@ -59,6 +59,21 @@ int bg_sn_bwd(const float* W, const float* dWn, int rows, int r_pad, int g_ld, c
               const float* v_hat, const float* sigma, float* dW, int K, int C, void* ws, size_t ws_bytes,
               void* stream);
 
+/* Grouped spectral norm: every weight matrix of a network in 4 launches (forward) / 2 launches (backward)
+ * driven by a device-resident plan built once.  All pointers in bg_sn_item are device pointers that must stay
+ * valid (persistent buffers): W master weights, u (updated in place), v (K floats), sigma (1 float), out / out_t
+ * normalised weights (layouts of bg_sn_scale; out_t may be NULL), dWn gradient w.r.t. the normalised weights
+ * ([taps][r_pad][g_ld] fp32), dW destination of the weight gradient ([K, C] fp32). */
+typedef struct {
+  const float* W; float* u; float* v; float* sigma; void* out; void* out_t; const float* dWn; float* dW;
+  int K, C, taps, rows, r_pad, c_pad, dtype, g_ld;
+} bg_sn_item;
+size_t bg_sn_group_plan_bytes(const bg_sn_item* items, int n);
+/* host-side planning + synchronous upload into plan_dev; totals[8] (host ints) is passed to the launches */
+int bg_sn_group_plan(const bg_sn_item* items, int n, void* plan_dev, size_t plan_bytes, int* totals);
+int bg_sn_group_forward(const void* plan_dev, const int* totals, void* stream);
+int bg_sn_group_backward(const void* plan_dev, const int* totals, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Convolution family -- ops.py:49-113 (conv), ops.py:116-139 (deconv), ops.py:148-175
  * (fully_connected == 1x1 conv on a 1x1 map).
