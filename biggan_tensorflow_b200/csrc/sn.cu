@@ -120,8 +120,16 @@ __device__ __forceinline__ long sn_g_index(long i, int C, int rows, int r_pad, i
 __device__ __forceinline__ void sn_dot_body(const float* __restrict__ G, const float* __restrict__ W, float* __restrict__ part, long n,
                                             int C, int g_ld, int rows, int r_pad, int blk, int nblk, float* sh) {
   float s = 0.f;
-  for (long i = (long)blk * blockDim.x + threadIdx.x; i < n; i += (long)nblk * blockDim.x)
-    s = fmaf(G[sn_g_index(i, C, rows, r_pad, g_ld)], W[i], s);
+  if (g_ld == C && r_pad == rows && (n & 3) == 0) {        // unpadded gradient layout: 16-byte streaming
+    const long n4 = n >> 2;
+    for (long i = (long)blk * blockDim.x + threadIdx.x; i < n4; i += (long)nblk * blockDim.x) {
+      const float4 g = *reinterpret_cast<const float4*>(G + 4 * i), w = *reinterpret_cast<const float4*>(W + 4 * i);
+      s += g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+    }
+  } else {
+    for (long i = (long)blk * blockDim.x + threadIdx.x; i < n; i += (long)nblk * blockDim.x)
+      s = fmaf(G[sn_g_index(i, C, rows, r_pad, g_ld)], W[i], s);
+  }
   s = bg_block_sum(s, sh);
   if (threadIdx.x == 0) part[blk] = s;
 }
@@ -136,6 +144,17 @@ __device__ __forceinline__ void sn_bwd_apply_body(const float* __restrict__ G, c
   const float dot = bg_block_sum(s, sh);       // identical in every block: fixed order
   const float coef = dot / (sg * sg);
   const long n = (long)K * C;
+  if (g_ld == C && r_pad == rows && (C & 3) == 0) {
+    const long n4 = n >> 2;
+    const int C4 = C >> 2;
+    for (long i = (long)blk * blockDim.x + threadIdx.x; i < n4; i += (long)nblk * blockDim.x) {
+      const int k = (int)(i / C4), c = (int)(i - (long)k * C4) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(G + 4 * i), u4 = *reinterpret_cast<const float4*>(u_hat + c);
+      const float cv = coef * v_hat[k];
+      *reinterpret_cast<float4*>(dW + 4 * i) = make_float4(g.x / sg - cv * u4.x, g.y / sg - cv * u4.y, g.z / sg - cv * u4.z, g.w / sg - cv * u4.w);
+    }
+    return;
+  }
   for (long i = (long)blk * blockDim.x + threadIdx.x; i < n; i += (long)nblk * blockDim.x) {
     const int k = (int)(i / C), c = (int)(i - (long)k * C);
     dW[i] = G[sn_g_index(i, C, rows, r_pad, g_ld)] / sg - coef * v_hat[k] * u_hat[c];
@@ -270,8 +289,8 @@ static void sn_item_sizes(const bg_sn_item& it, SnItemDev* d) {
   d->RT = sn_rows_per_block(it.K);
   d->nblk = (int)bg_cdiv(it.K, d->RT);
   const long n = (long)it.K * it.C;
-  d->npart = (int)min(bg_cdiv(n, 1024), 256L);
-  d->napply = (int)min(bg_cdiv(n, 256 * 8), 1024L);
+  d->npart = (int)min(bg_cdiv(n, 4096), 512L);
+  d->napply = (int)min(bg_cdiv(n, 256 * 16), 2048L);
   if (d->napply < 1) d->napply = 1;
   d->sx = (int)bg_cdiv(it.C, 32);
   d->sy = (int)bg_cdiv(it.rows, 32);
