@@ -239,6 +239,22 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)      # max over ranks, device-timed
         return float(ms.cpu()) / steps, out
 
+    def finish():
+        """All ranks: drain, drop the captured graph, tear NCCL down, and leave without running interpreter
+        teardown (a captured graph holding NCCL work can otherwise stall process exit)."""
+        nonlocal graphed
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            try:
+                dist.barrier()
+                graphed = None
+                dist.destroy_process_group()
+            except Exception:
+                pass
+            os._exit(0)
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(local)
@@ -251,7 +267,7 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "value": B / (ms_step * 1e-3), "gpu_launches": launches}))
-        return
+        return finish()
     step_e2e()
     ms_e2e, losses = timed(step_e2e, max(2, args.steps // 2))
 
@@ -260,7 +276,7 @@ def main():
     tr.train_step(devt["real"], devt["labels"], devt["z_d"], devt["z_g"], devt["labels"])      # eager, so that events bracket each call
     prof = _lib.profile_end()
     if rank != 0:
-        return
+        return finish()
     peaks = load_peaks()
     tot_ms = sum(d["ms"] for d in prof.values())
     conv = {k: d for k, d in prof.items() if k.startswith("conv_") and "[fc]" not in k}
@@ -296,8 +312,7 @@ def main():
                     "ms_per_step": ms_e2e, "losses": list(losses)},
             "gpu_launches": launches, "cuda_graph": graphed is not None, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

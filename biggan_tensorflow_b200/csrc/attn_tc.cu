@@ -19,56 +19,54 @@ struct AttnFwdParams {
   float* lse;
 };
 
-__device__ __forceinline__ void tma_load_3d_g(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
-  tma_load_3d(dst, tmap, bar, c0, c1, c2);
-}
-
-__global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+// 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax / epilogue.  Two softmax warps
+// share each TMEM lane quarter (one query row per lane) and split the 128 key columns of a block in halves;
+// row max / row sums are combined through shared memory once per pass.  112 KB of shared memory and 256
+// TMEM columns per CTA, so two CTAs are resident per SM and one CTA's softmax overlaps the other's MMAs.
+__global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full, p_empty, o_full;
+  __shared__ __align__(8) uint64_t q_full, k_full, k_empty, v_full, v_empty, s_full, s_empty, p_full, p_empty, o_full;
   __shared__ uint32_t tmem_slot;
+  __shared__ float xch[2][2][128];          // [quantity][half][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t vstage = (uint32_t)p.nvblk * 16384u;
-  const uint32_t Qs = base, Ks = base + 16384u, Vs = Ks + 2u * 16384u, Ps = Vs + 2u * vstage;
+  const uint32_t vbytes = (uint32_t)p.nvblk * 16384u;
+  const uint32_t Qs = base, Ks = base + 16384u, Vs = Ks + 16384u, Ps = Vs + vbytes;
   const int b = blockIdx.y, q0 = blockIdx.x * 128;
   const int T = 2 * p.nkb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap);
     mbar_init(smem_u32(&q_full), 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&k_full[i]), 1); mbar_init(smem_u32(&k_empty[i]), 1);
-      mbar_init(smem_u32(&v_full[i]), 1); mbar_init(smem_u32(&v_empty[i]), 1);
-      mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 4);
-    }
-    mbar_init(smem_u32(&p_full), 4); mbar_init(smem_u32(&p_empty), 1); mbar_init(smem_u32(&o_full), 1);
+    mbar_init(smem_u32(&k_full), 1); mbar_init(smem_u32(&k_empty), 1);
+    mbar_init(smem_u32(&v_full), 1); mbar_init(smem_u32(&v_empty), 1);
+    mbar_init(smem_u32(&s_full), 1); mbar_init(smem_u32(&s_empty), 8);
+    mbar_init(smem_u32(&p_full), 8); mbar_init(smem_u32(&p_empty), 1); mbar_init(smem_u32(&o_full), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+  if (warp == 1) tmem_alloc<256>(smem_u32(&tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tS[2] = {tmem, tmem + 128u};
-  const uint32_t tO = tmem + 256u;
+  const uint32_t tS = tmem, tO = tmem + 128u;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(smem_u32(&q_full), 16384u);
       tma_load_3d(Qs, &p.qmap, smem_u32(&q_full), 0, q0, b);
       for (int it = 0; it < T; ++it) {
-        const int j = it % p.nkb, s = it & 1;
-        mbar_wait(smem_u32(&k_empty[s]), (uint32_t)(((it >> 1) & 1) ^ 1));
-        mbar_expect_tx(smem_u32(&k_full[s]), 16384u);
-        tma_load_3d(Ks + (uint32_t)s * 16384u, &p.kmap, smem_u32(&k_full[s]), 0, j * AT_KB, b);
+        const int j = it % p.nkb;
+        mbar_wait(smem_u32(&k_empty), (uint32_t)((it & 1) ^ 1));
+        mbar_expect_tx(smem_u32(&k_full), 16384u);
+        tma_load_3d(Ks, &p.kmap, smem_u32(&k_full), 0, j * AT_KB, b);
         if (it >= p.nkb) {
-          const int jj = it - p.nkb, vs = jj & 1;
-          mbar_wait(smem_u32(&v_empty[vs]), (uint32_t)(((jj >> 1) & 1) ^ 1));
-          mbar_expect_tx(smem_u32(&v_full[vs]), vstage);
+          const int jj = it - p.nkb;
+          mbar_wait(smem_u32(&v_empty), (uint32_t)((jj & 1) ^ 1));
+          mbar_expect_tx(smem_u32(&v_full), vbytes);
           for (int c = 0; c < p.nvblk; ++c)
-            tma_load_3d(Vs + (uint32_t)vs * vstage + (uint32_t)c * 16384u, &p.vmap, smem_u32(&v_full[vs]), c * 64, j * AT_KB, b);
+            tma_load_3d(Vs + (uint32_t)c * 16384u, &p.vmap, smem_u32(&v_full), c * 64, j * AT_KB, b);
         }
       }
     }
@@ -80,49 +78,53 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
       mbar_wait(smem_u32(&q_full), 0);
       for (int it = 0; it <= T; ++it) {
         if (it < T) {
-          const int s = it & 1;
-          mbar_wait(smem_u32(&k_full[s]), (uint32_t)((it >> 1) & 1));
-          mbar_wait(smem_u32(&s_empty[s]), (uint32_t)(((it >> 1) & 1) ^ 1));
+          mbar_wait(smem_u32(&k_full), (uint32_t)(it & 1));
+          mbar_wait(smem_u32(&s_empty), (uint32_t)((it & 1) ^ 1));
           tc_fence_after();
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tS[s], umma_desc_kmajor_sw128(Qs + k * 32), umma_desc_kmajor_sw128(Ks + (uint32_t)s * 16384u + k * 32), idesc_s,
-                      k ? 1u : 0u);
-          umma_commit(smem_u32(&s_full[s]));
-          umma_commit(smem_u32(&k_empty[s]));
+            umma_bf16(tS, umma_desc_kmajor_sw128(Qs + k * 32), umma_desc_kmajor_sw128(Ks + k * 32), idesc_s, k ? 1u : 0u);
+          umma_commit(smem_u32(&s_full));
+          umma_commit(smem_u32(&k_empty));
         }
         const int pv = it - 1 - p.nkb;            // the P V product of the previous (pass-2) iteration
         if (pv >= 0) {
-          const int vs = pv & 1;
-          mbar_wait(smem_u32(&v_full[vs]), (uint32_t)((pv >> 1) & 1));
+          mbar_wait(smem_u32(&v_full), (uint32_t)(pv & 1));
           mbar_wait(smem_u32(&p_full), (uint32_t)(pv & 1));
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < AT_KB / 16; ++k) {
             const uint64_t ad = umma_desc_kmajor_sw128(Ps + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
-            const uint64_t bd = umma_desc_mnmajor_sw128(Vs + (uint32_t)vs * vstage + (uint32_t)k * 2048u, 16384u, 1024u);
+            const uint64_t bd = umma_desc_mnmajor_sw128(Vs + (uint32_t)k * 2048u, 16384u, 1024u);
             umma_bf16(tO, ad, bd, idesc_o, (pv | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&p_empty));
-          umma_commit(smem_u32(&v_empty[vs]));
+          umma_commit(smem_u32(&v_empty));
         }
       }
       umma_commit(smem_u32(&o_full));
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                       // TMEM lane quarter
+    const int half = (warp - 2) >> 2;             // which 64 of the 128 key columns of a block
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
     float m = -INFINITY, sum = 0.f, sum_true = 0.f;
     for (int it = 0; it < T; ++it) {
-      const int j = it % p.nkb, s = it & 1;
+      const int j = it % p.nkb;
       const bool pass2 = it >= p.nkb;
-      mbar_wait(smem_u32(&s_full[s]), (uint32_t)((it >> 1) & 1));
+      if (it == p.nkb) {                          // pass 1 done: combine the two halves' row maxima
+        xch[0][half][row] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(xch[0][0][row], xch[0][1][row]);
+      }
+      mbar_wait(smem_u32(&s_full), (uint32_t)(it & 1));
       tc_fence_after();
       if (pass2) mbar_wait(smem_u32(&p_empty), (uint32_t)(((it - p.nkb) & 1) ^ 1));
-      for (int c0 = 0; c0 < AT_KB; c0 += 16) {
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = half * 64 + cc;
         uint32_t r[16];
-        tmem_ld_x16(tS[s] + lane_base + (uint32_t)c0, r);
+        tmem_ld_x16(tS + lane_base + (uint32_t)c0, r);
         float v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -154,15 +156,23 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
       if (pass2) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(smem_u32(&s_empty[s]));
+        mbar_arrive(smem_u32(&s_empty));
         if (pass2) mbar_arrive(smem_u32(&p_full));
       }
     }
+    // combine the halves' row sums
+    xch[0][half][row] = sum;
+    xch[1][half][row] = sum_true;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum = xch[0][0][row] + xch[0][1][row];
+    sum_true = xch[1][0][row] + xch[1][1][row];
     mbar_wait(smem_u32(&o_full), 0);
     tc_fence_after();
     const int qi = q0 + row;
     const float inv = 1.f / sum;
-    for (int c0 = 0; c0 < p.dv; c0 += 16) {
+    const int csplit = ((p.dv / 16 + 1) / 2) * 16;
+    const int cbeg = half ? csplit : 0, cend = half ? p.dv : csplit;
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
       uint32_t r[16];
       tmem_ld_x16(tO + lane_base + (uint32_t)c0, r);
       if (qi < p.Nq) {
@@ -178,11 +188,11 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
         op[0] = o0; op[1] = o1;
       }
     }
-    if (qi < p.Nq) p.lse[(long)b * p.Nq + qi] = m + logf(sum_true);
+    if (half == 0 && qi < p.Nq) p.lse[(long)b * p.Nq + qi] = m + logf(sum_true);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -218,7 +228,7 @@ extern "C" int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o
                             void* stream) {
   BG_REQUIRE(bg_has_tensor_core_path(), BG_ERR_UNSUPPORTED, "attn2: tensor-core path unavailable on this device");
   BG_REQUIRE(dq % 16 == 0 && dq >= 16 && dq <= 64, BG_ERR_UNSUPPORTED, "attn2: dq=%d must be 16..64, multiple of 16", dq);
-  BG_REQUIRE(dv % 16 == 0 && dv >= 16 && dv <= 256, BG_ERR_UNSUPPORTED, "attn2: dv=%d must be 16..256, multiple of 16", dv);
+  BG_REQUIRE(dv % 16 == 0 && dv >= 16 && dv <= 128, BG_ERR_UNSUPPORTED, "attn2: dv=%d must be 16..128, multiple of 16", dv);
   BG_REQUIRE(B > 0 && Nq > 0 && Nk > 0 && B <= 65535, BG_ERR_SHAPE, "attn2: bad shape");
   static AttnFwdParams P;
   memset(&P, 0, sizeof(P));
@@ -230,14 +240,15 @@ extern "C" int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o
   P.nkb = (int)bg_cdiv(Nk, AT_KB);
   P.nvblk = (dv + 63) / 64;
   P.o = (bf16*)o; P.lse = lse;
-  const size_t smem = 16384 + 2 * 16384 + 2 * (size_t)P.nvblk * 16384 + 32768 + 1024;
+  const size_t smem = 16384 + 16384 + (size_t)P.nvblk * 16384 + 32768 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   dim3 grid((unsigned)bg_cdiv(Nq, 128), (unsigned)B);
-  attn_fwd_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(P);
+  attn_fwd_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(P);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
