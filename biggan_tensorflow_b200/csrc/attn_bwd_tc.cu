@@ -55,7 +55,7 @@ __device__ __forceinline__ void issue_s_dp(uint32_t tS, uint32_t tdP, uint32_t Q
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 1) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdParams p) {
+__global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_full, qd_full[2], qd_empty[2], s_full, s_empty, pds_full, pds_empty, acc_full;
   __shared__ uint32_t tmem_slot;
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkdv_kernel(const __grid_cons
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.domap);
     mbar_init(smem_u32(&kv_full), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&qd_full[i]), 1); mbar_init(smem_u32(&qd_empty[i]), 1); }
-    mbar_init(smem_u32(&s_full), 1); mbar_init(smem_u32(&s_empty), 4);
-    mbar_init(smem_u32(&pds_full), 4); mbar_init(smem_u32(&pds_empty), 1); mbar_init(smem_u32(&acc_full), 1);
+    mbar_init(smem_u32(&s_full), 1); mbar_init(smem_u32(&s_empty), 8);
+    mbar_init(smem_u32(&pds_full), 8); mbar_init(smem_u32(&pds_empty), 1); mbar_init(smem_u32(&acc_full), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkdv_kernel(const __grid_cons
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;          // two warps per TMEM lane quarter split the 128 key columns
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkdv_kernel(const __grid_cons
       mbar_wait(smem_u32(&s_full), (uint32_t)(i & 1));
       tc_fence_after();
       mbar_wait(smem_u32(&pds_empty), (uint32_t)((i & 1) ^ 1));
-      for (int c0 = 0; c0 < AB_T; c0 += 16) {
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = half * 64 + cc;
         uint32_t rs[16], rp[16], pk[8], dk[8];
         tmem_ld_x16(tS + lane_base + (uint32_t)c0, rs);
         tmem_ld_x16(tdP + lane_base + (uint32_t)c0, rp);
@@ -170,12 +172,13 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkdv_kernel(const __grid_cons
     mbar_wait(smem_u32(&acc_full), 0);
     tc_fence_after();
     const int key = j * AB_T + row;          // accumulator rows are keys
-    for (int c0 = 0; c0 < p.dv; c0 += 16) {
+    const int vsplit = ((p.dv / 16 + 1) / 2) * 16, ksplit = ((p.dq / 16 + 1) / 2) * 16;
+    for (int c0 = half ? vsplit : 0; c0 < (half ? p.dv : vsplit); c0 += 16) {
       uint32_t r[16];
       tmem_ld_x16(tdV + lane_base + (uint32_t)c0, r);
       if (key < p.Nk) store_acc_bf16(p.dv_out + ((long)b * p.Nk + key) * p.dv + c0, r);
     }
-    for (int c0 = 0; c0 < p.dq; c0 += 16) {
+    for (int c0 = half ? ksplit : 0; c0 < (half ? p.dq : ksplit); c0 += 16) {
       uint32_t r[16];
       tmem_ld_x16(tdK + lane_base + (uint32_t)c0, r);
       if (key < p.Nk) store_acc_bf16(p.dk_out + ((long)b * p.Nk + key) * p.dq + c0, r);
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkdv_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdParams p) {
+__global__ void __launch_bounds__(320, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t qd_full, kv_full[2], kv_empty[2], s_full, s_empty, ds_full, ds_empty, acc_full;
   __shared__ uint32_t tmem_slot;
@@ -201,8 +204,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_kernel(const __grid_consta
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.domap);
     mbar_init(smem_u32(&qd_full), 1);
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
-    mbar_init(smem_u32(&s_full), 1); mbar_init(smem_u32(&s_empty), 4);
-    mbar_init(smem_u32(&ds_full), 4); mbar_init(smem_u32(&ds_empty), 1); mbar_init(smem_u32(&acc_full), 1);
+    mbar_init(smem_u32(&s_full), 1); mbar_init(smem_u32(&s_empty), 8);
+    mbar_init(smem_u32(&ds_full), 8); mbar_init(smem_u32(&ds_empty), 1); mbar_init(smem_u32(&acc_full), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_kernel(const __grid_consta
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
@@ -269,7 +273,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_kernel(const __grid_consta
       mbar_wait(smem_u32(&s_full), (uint32_t)(j & 1));
       tc_fence_after();
       mbar_wait(smem_u32(&ds_empty), (uint32_t)((j & 1) ^ 1));
-      for (int c0 = 0; c0 < AB_T; c0 += 16) {
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = half * 64 + cc;
         uint32_t rs[16], rp[16], dk[8];
         tmem_ld_x16(tS + lane_base + (uint32_t)c0, rs);
         tmem_ld_x16(tdP + lane_base + (uint32_t)c0, rp);
@@ -294,7 +299,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_kernel(const __grid_consta
     }
     mbar_wait(smem_u32(&acc_full), 0);
     tc_fence_after();
-    for (int c0 = 0; c0 < p.dq; c0 += 16) {
+    const int qsplit = ((p.dq / 16 + 1) / 2) * 16;
+    for (int c0 = half ? qsplit : 0; c0 < (half ? p.dq : qsplit); c0 += 16) {
       uint32_t r[16];
       tmem_ld_x16(tdQ + lane_base + (uint32_t)c0, r);
       if (qv) store_acc_bf16(p.dq_out + ((long)b * p.Nq + qi) * p.dq + c0, r);
@@ -346,9 +352,9 @@ extern "C" int bg_attn2_bwd(const void* q, const void* k, const void* v, const v
   const size_t vb = (size_t)P.nvblk * 16384;
   const size_t smem_kv = 16384 + vb + 2 * 16384 + 2 * vb + 32768 + 32768 + 1024;
   const size_t smem_q = 16384 + vb + 2 * 16384 + 2 * vb + 32768 + 1024;
-  attn_bwd_dkdv_kernel<<<dim3((unsigned)P.nkb, (unsigned)B), 192, smem_kv, st>>>(P);
+  attn_bwd_dkdv_kernel<<<dim3((unsigned)P.nkb, (unsigned)B), 320, smem_kv, st>>>(P);
   BG_LAUNCH_CHECK();
-  attn_bwd_dq_kernel<<<dim3((unsigned)P.nqt, (unsigned)B), 192, smem_q, st>>>(P);
+  attn_bwd_dq_kernel<<<dim3((unsigned)P.nqt, (unsigned)B), 320, smem_q, st>>>(P);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

@@ -41,7 +41,9 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
       }
     }
     const long base = (long)b * HW * C + c;
-    for (long r = r0 + ty; r < r1; r += 8) {
+#pragma unroll 4
+  #pragma unroll 4
+  for (long r = r0 + ty; r < r1; r += 8) {
       f4 xv = bg_ld4(x, base + r * C);
       float xe[4] = {xv.x, xv.y, xv.z, xv.w};
       if (MODE == 0) {
@@ -164,6 +166,7 @@ bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const f
     shift[e] = beta[(long)b * gb_bstride + c + e] - mean[c + e] * inv[e];
   }
   const long base = (long)b * HW * C + c;
+#pragma unroll 4
   for (long r = r0 + ty; r < r1; r += 8) {
     f4 xv = bg_ld4(x, base + r * C);
     float o[4] = {xv.x * inv[0] + shift[0], xv.y * inv[1] + shift[1], xv.z * inv[2] + shift[2], xv.w * inv[3] + shift[3]};
@@ -256,6 +259,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
     m2[e] = (float)(s[C + c + e] / count);
   }
   const long base = (long)b * HW * C + c;
+#pragma unroll 4
   for (long r = r0 + ty; r < r1; r += 8) {
     f4 xv = bg_ld4(x, base + r * C), dv = bg_ld4(dy, base + r * C);
     float xe[4] = {xv.x, xv.y, xv.z, xv.w}, de[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
