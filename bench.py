@@ -116,6 +116,8 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):       # torchrun pins these to 1; the CPU arm uses every host core
+        os.environ[var] = str(threads)
     batch = args.cpu_batch
     steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
     t0 = time.perf_counter()
@@ -247,12 +249,8 @@ def main():
         sys.stdout.flush()
         sys.stderr.flush()
         if world > 1:
-            try:
-                dist.barrier()
-                graphed = None
-                dist.destroy_process_group()
-            except Exception:
-                pass
+            # every collective of this rank has completed (synchronize above).  Leave without NCCL / CUDA-graph
+            # teardown: destroying a communicator that a live captured graph references can stall process exit.
             os._exit(0)
 
     for _ in range(max(args.warmup, 3)):
