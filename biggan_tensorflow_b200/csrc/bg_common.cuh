@@ -118,6 +118,29 @@ __device__ __forceinline__ double bg_block_sum_d(double v, double* sh /* >= 33 d
   return sh[32];
 }
 
+// 16-byte vector access: 4 floats or 8 bf16 per thread (n % VEC == 0 and 16-byte aligned base required)
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void ld(const float* p, long i, float* v) { float4 t = *reinterpret_cast<const float4*>(p + i); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void st(float* p, long i, const float* v) { *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void ld(const bf16* p, long i, float* v) {
+    uint4 t = *reinterpret_cast<const uint4*>(p + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] = __low2float(h[e]); v[2 * e + 1] = __high2float(h[e]); }
+  }
+  static __device__ __forceinline__ void st(bf16* p, long i, const float* v) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p + i) = t;
+  }
+};
 // dispatch on activation storage dtype
 #define BG_DISPATCH_DTYPE(dtype, T, ...)                                        \
   do {                                                                          \

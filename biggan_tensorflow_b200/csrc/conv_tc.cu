@@ -370,6 +370,7 @@ struct TcWgParams {
   int Ci, Co, BN, nblkB;        // M total, N total, N tile, 64-channel blocks per B tile
   int ntile_n, nsplit, nboxes, stages;
   int ntaps;
+  int TPC;                      // taps per CTA: they share every Og (B operand) tile, one TMEM accumulator each
   TcTap taps[TC_MAX_TAPS];
   float* part;
   long zstride, wtap, wk;
@@ -385,9 +386,12 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = 16384u + (uint32_t)p.nblkB * 8192u;
+  const int tap0 = blockIdx.y * p.TPC;
+  const int nt = min(p.TPC, p.ntaps - tap0);          // taps handled by this CTA
+  const uint32_t b_off = (uint32_t)nt * 16384u;       // stage layout: [A tap 0][A tap 1]...[B]
+  const uint32_t stage_bytes = b_off + (uint32_t)p.nblkB * 8192u;
+  const uint32_t stage_stride = (uint32_t)p.TPC * 16384u + (uint32_t)p.nblkB * 8192u;
   const int m0 = (blockIdx.x / p.ntile_n) * 128, n0 = (blockIdx.x % p.ntile_n) * p.BN;
-  const TcTap tap = p.taps[blockIdx.y];
   const int box_beg = (int)(((long)blockIdx.z * p.nboxes) / p.nsplit);
   const int box_end = (int)(((long)(blockIdx.z + 1) * p.nboxes) / p.nsplit);
   const int total = box_end - box_beg;
@@ -417,11 +421,14 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
         mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, stage_bytes);
-        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-        tma_load_4d(sa, &p.amap[tap.map], fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
-        tma_load_4d(sa + 8192u, &p.amap[tap.map], fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
+        const uint32_t sa = smem_base + (uint32_t)s * stage_stride;
+        for (int t2 = 0; t2 < nt; ++t2) {
+          const TcTap tap = p.taps[tap0 + t2];
+          tma_load_4d(sa + (uint32_t)t2 * 16384u, &p.amap[tap.map], fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
+          tma_load_4d(sa + (uint32_t)t2 * 16384u + 8192u, &p.amap[tap.map], fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
+        }
         for (int nb = 0; nb < p.nblkB; ++nb)
-          tma_load_4d(sa + 16384u + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
+          tma_load_4d(sa + b_off + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
       }
     }
   } else if (warp == 1) {
@@ -432,12 +439,13 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
         const uint32_t par = (uint32_t)((it / p.stages) & 1);
         mbar_wait(smem_u32(&full_bar[s]), par);
         tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t sa = smem_base + (uint32_t)s * stage_stride;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {     // 16 pixels (2 swizzle atoms of 8 rows) per MMA
-          const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, 8192, 1024);
-          const uint64_t bd = umma_desc_mnmajor_sw128(sa + 16384u + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          const uint64_t bd = umma_desc_mnmajor_sw128(sa + b_off + k * 2048, 8192, 1024);
+          for (int t2 = 0; t2 < nt; ++t2)
+            umma_bf16(tmem_base + (uint32_t)(t2 * p.BN), umma_desc_mnmajor_sw128(sa + (uint32_t)t2 * 16384u + k * 2048, 8192, 1024), bd,
+                      idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[s]));
       }
@@ -446,24 +454,26 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
   } else {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
-    float* dst = p.part + (long)blockIdx.z * p.zstride + (long)tap.widx * p.wtap + (long)m * p.wk + n0;
     if (total > 0) {
       mbar_wait(smem_u32(&accum_bar), 0);
       tc_fence_after();
     }
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t r[16];
-      if (total > 0) tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      else {
+    for (int t2 = 0; t2 < nt; ++t2) {
+      float* dst = p.part + (long)blockIdx.z * p.zstride + (long)p.taps[tap0 + t2].widx * p.wtap + (long)m * p.wk + n0;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        if (total > 0) tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t2 * p.BN + c0), r);
+        else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = 0u;
-      }
-      if (m < p.Ci) {
-        float4* o = reinterpret_cast<float4*>(dst + c0);
+          for (int e = 0; e < 16; ++e) r[e] = 0u;
+        }
+        if (m < p.Ci) {
+          float4* o = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
-                             __uint_as_float(r[4 * e + 3]));
+          for (int e = 0; e < 4; ++e)
+            o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                               __uint_as_float(r[4 * e + 3]));
+        }
       }
     }
   }
@@ -486,7 +496,7 @@ static int wg_nsplit(int tiles, int nboxes) {
   return (int)ns;
 }
 
-struct WgPlan { int ok, BN, bw, bh, bb, tw, th, tb, nboxes, tiles, nsplit; };
+struct WgPlan { int ok, BN, bw, bh, bb, tw, th, tb, nboxes, tiles, nsplit, TPC; };
 
 static WgPlan wg_plan(const BgGeom& g) {
   WgPlan pl;
@@ -501,7 +511,18 @@ static WgPlan wg_plan(const BgGeom& g) {
   choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 64, &pl.bw, &pl.bh, &pl.bb);
   pl.tw = (int)bg_cdiv(g.ph[0].Wp, pl.bw); pl.th = (int)bg_cdiv(g.ph[0].Hp, pl.bh); pl.tb = (int)bg_cdiv(g.B, pl.bb);
   pl.nboxes = pl.tw * pl.th * pl.tb;
-  pl.tiles = (int)(bg_cdiv(g.Ci, 128) * (g.Co / pl.BN) * g.ph[0].ntaps);
+  // taps per CTA: share the Og tile across taps while accumulators (TPC*BN <= 512 columns) and two pipeline stages fit
+  {
+    const int nt = g.ph[0].ntaps, nblk = (pl.BN + 63) / 64;
+    int best = 1;
+    for (int t = 2; t <= 4; ++t) {
+      if (t * pl.BN > 512 || t > nt) continue;
+      if (2 * (t * 16384 + nblk * 8192) > 200 * 1024) continue;
+      if (bg_cdiv(nt, t) * t - nt <= (best > 1 ? bg_cdiv(nt, best) * best - nt : 99)) best = t;   // least idle accumulator slots, prefer larger
+    }
+    pl.TPC = best;
+  }
+  pl.tiles = (int)(bg_cdiv(g.Ci, 128) * (g.Co / pl.BN) * bg_cdiv(g.ph[0].ntaps, pl.TPC));
   pl.nsplit = wg_nsplit(pl.tiles, pl.nboxes);
   pl.ok = 1;
   return pl;
@@ -557,8 +578,11 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
   P.bw = pl.bw; P.bh = pl.bh; P.bb = pl.bb; P.tw = pl.tw; P.th = pl.th; P.tb = pl.tb;
   P.Ci = g.Ci; P.Co = g.Co; P.BN = pl.BN; P.nblkB = (pl.BN + 63) / 64;
   P.ntile_n = g.Co / pl.BN; P.nsplit = pl.nsplit; P.nboxes = pl.nboxes;
-  const int stage_bytes = 16384 + P.nblkB * 8192;
-  int stages = (stage_bytes <= 32 * 1024) ? 3 : 4;     // 2 CTAs per SM for the small tiles
+  P.TPC = pl.TPC;
+  const int stage_bytes = pl.TPC * 16384 + P.nblkB * 8192;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
   P.stages = stages;
   P.ntaps = g.ph[0].ntaps;
   for (int t = 0; t < P.ntaps; ++t) {
@@ -572,7 +596,7 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
   P.part = pl.nsplit > 1 ? (float*)wsp : dw;
   P.zstride = numel; P.wtap = g.wtap; P.wk = g.wk;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  dim3 grid((unsigned)(bg_cdiv(g.Ci, 128) * P.ntile_n), (unsigned)P.ntaps, (unsigned)pl.nsplit);
+  dim3 grid((unsigned)(bg_cdiv(g.Ci, 128) * P.ntile_n), (unsigned)bg_cdiv(P.ntaps, pl.TPC), (unsigned)pl.nsplit);
 #define TC_LAUNCH_WG(COLS)                                                                                       \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
@@ -582,10 +606,12 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
     }                                                                                                            \
     tc_wgrad_kernel<COLS><<<grid, 192, smem, st>>>(P);                                                           \
   } while (0)
-  if (pl.BN <= 32) TC_LAUNCH_WG(32);
-  else if (pl.BN <= 64) TC_LAUNCH_WG(64);
-  else if (pl.BN <= 128) TC_LAUNCH_WG(128);
-  else TC_LAUNCH_WG(256);
+  const int wcols = pl.TPC * pl.BN;
+  if (wcols <= 32) TC_LAUNCH_WG(32);
+  else if (wcols <= 64) TC_LAUNCH_WG(64);
+  else if (wcols <= 128) TC_LAUNCH_WG(128);
+  else if (wcols <= 256) TC_LAUNCH_WG(256);
+  else TC_LAUNCH_WG(512);
 #undef TC_LAUNCH_WG
   BG_LAUNCH_CHECK();
   if (pl.nsplit > 1) {

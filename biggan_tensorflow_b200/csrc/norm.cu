@@ -79,14 +79,22 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
   }
 }
 
-// sums over (sample, chunk) partials -> double [2C]
-__global__ void bn_stats_final_kernel(const float* __restrict__ part, double* __restrict__ sums, int nrow, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// sums over (sample, chunk) partials -> double [2C].  Block = 32 channels x 32 row groups (fixed-order tree).
+__global__ void __launch_bounds__(1024) bn_stats_final_kernel(const float* __restrict__ part, double* __restrict__ sums, int nrow, int C) {
+  __shared__ double sa[32][33], sq[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   double a = 0.0, q = 0.0;
-  for (int i = 0; i < nrow; ++i) { a += (double)part[((long)i * 2) * C + c]; q += (double)part[((long)i * 2 + 1) * C + c]; }
-  sums[c] = a;
-  sums[C + c] = q;
+  if (c < C)
+    for (int i = ty; i < nrow; i += 32) { a += (double)part[((long)i * 2) * C + c]; q += (double)part[((long)i * 2 + 1) * C + c]; }
+  sa[ty][tx] = a; sq[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double ta = 0.0, tq = 0.0;
+    for (int i = 0; i < 32; ++i) { ta += sa[i][tx]; tq += sq[i][tx]; }
+    sums[c] = ta;
+    sums[C + c] = tq;
+  }
 }
 
 // per-sample: dbeta[b,c], dgamma[b,c] = sum over chunks
@@ -118,7 +126,7 @@ extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, i
   BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0,
                                                                         0.f, (float*)ws, HW, C, nchunk));
   BG_LAUNCH_CHECK();
-  bn_stats_final_kernel<<<(unsigned)bg_cdiv(C, 128), 128, 0, st>>>((const float*)ws, sums, B * nchunk, C);
+  bn_stats_final_kernel<<<(unsigned)bg_cdiv(C, 32), 1024, 0, st>>>((const float*)ws, sums, B * nchunk, C);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
@@ -213,23 +221,32 @@ extern "C" int bg_bn_bwd_reduce(const void* dy, const void* x, const float* mean
   return BG_OK;
 }
 
-__global__ void bn_bwd_sums_kernel(const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                   const float* __restrict__ gamma, int gb_bstride, double* __restrict__ s, int B, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024)
+bn_bwd_sums_kernel(const float* __restrict__ dgamma, const float* __restrict__ dbeta, const float* __restrict__ gamma, int gb_bstride,
+                   double* __restrict__ s, int B, int C) {
+  __shared__ double sa[32][33], sq[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   double a = 0.0, q = 0.0;
-  for (int b = 0; b < B; ++b) {
-    const double gm = (double)gamma[(long)b * gb_bstride + c];
-    a += gm * (double)dbeta[(long)b * C + c];
-    q += gm * (double)dgamma[(long)b * C + c];
+  if (c < C)
+    for (int b = ty; b < B; b += 32) {
+      const double gm = (double)gamma[(long)b * gb_bstride + c];
+      a += gm * (double)dbeta[(long)b * C + c];
+      q += gm * (double)dgamma[(long)b * C + c];
+    }
+  sa[ty][tx] = a; sq[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double ta = 0.0, tq = 0.0;
+    for (int i = 0; i < 32; ++i) { ta += sa[i][tx]; tq += sq[i][tx]; }
+    s[c] = ta;
+    s[C + c] = tq;
   }
-  s[c] = a;
-  s[C + c] = q;
 }
 
 extern "C" int bg_bn_bwd_sums(const float* dgamma, const float* dbeta, const float* gamma, int gb_bstride, double* s, int B,
                               int C, void* stream) {
-  bn_bwd_sums_kernel<<<(unsigned)bg_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(dgamma, dbeta, gamma, gb_bstride, s, B, C);
+  bn_bwd_sums_kernel<<<(unsigned)bg_cdiv(C, 32), 1024, 0, (cudaStream_t)stream>>>(dgamma, dbeta, gamma, gb_bstride, s, B, C);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
