@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
   const uint32_t Ks = base, Vs = Ks + 16384u, Qs = Vs + vbytes, dOs = Qs + 2u * 16384u, Ps = dOs + 2u * vbytes, dSs = Ps + 32768u;
   const int b = blockIdx.y, j = blockIdx.x;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.domap);
     mbar_init(smem_u32(&kv_full), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&qd_full[i]), 1); mbar_init(smem_u32(&qd_empty[i]), 1); }
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
   const uint32_t tS = tmem, tdP = tmem + 128u, tdV = tmem + 256u, tdK = tmem + 384u;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(smem_u32(&kv_full), 16384u + vbytes);
       tma_load_3d(Ks, &p.kmap, smem_u32(&kv_full), 0, j * AB_T, b);
       for (int c = 0; c < p.nvblk; ++c) tma_load_3d(Vs + (uint32_t)c * 16384u, &p.vmap, smem_u32(&kv_full), c * 64, j * AB_T, b);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc_dv = umma_idesc_bf16(128, p.dv, 1, 1);
       const uint32_t idesc_dk = umma_idesc_bf16(128, p.dq, 1, 1);
       mbar_wait(smem_u32(&kv_full), 0);
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dq_kernel(const __grid_consta
   const uint32_t Qs = base, dOs = Qs + 16384u, Ks = dOs + vbytes, Vs = Ks + 2u * 16384u, dSs = Vs + 2u * vbytes;
   const int b = blockIdx.y, i = blockIdx.x;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.domap);
     mbar_init(smem_u32(&qd_full), 1);
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dq_kernel(const __grid_consta
   const uint32_t tS = tmem, tdP = tmem + 128u, tdQ = tmem + 256u;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(smem_u32(&qd_full), 16384u + vbytes);
       tma_load_3d(Qs, &p.qmap, smem_u32(&qd_full), 0, i * AB_T, b);
       for (int c = 0; c < p.nvblk; ++c) tma_load_3d(dOs + (uint32_t)c * 16384u, &p.domap, smem_u32(&qd_full), c * 64, i * AB_T, b);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dq_kernel(const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc_dq = umma_idesc_bf16(128, p.dq, 0, 1);
       mbar_wait(smem_u32(&qd_full), 0);
       for (int j = 0; j <= p.nkb; ++j) {

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
   const int b = blockIdx.y, q0 = blockIdx.x * 128;
   const int T = 2 * p.nkb;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap);
     mbar_init(smem_u32(&q_full), 1);
     mbar_init(smem_u32(&k_full), 1); mbar_init(smem_u32(&k_empty), 1);
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
   const uint32_t tS = tmem, tO = tmem + 128u;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(smem_u32(&q_full), 16384u);
       tma_load_3d(Qs, &p.qmap, smem_u32(&q_full), 0, q0, b);
       for (int it = 0; it < T; ++it) {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, AT_KB, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, p.dv, 0, 1);
       const int ksteps = p.dq / 16;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
       tc_fence_before();
       if (pass2) fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_arrive(smem_u32(&s_empty));
         if (pass2) mbar_arrive(smem_u32(&p_full));
       }

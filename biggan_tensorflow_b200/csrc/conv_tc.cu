@@ -8,6 +8,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issue,
 // warps 2-5 = epilogue (tcgen05.ld -> bias / residual / act -> bf16 -> global).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "bg_common.cuh"
 
@@ -18,6 +19,9 @@
 // ------------------------------------------------------------------------------------------------
 #define TC_MAX_TAPS 16
 struct TcTap { int map, dy, dx, widx; };
+#define TC_MAX_GROUPS 8
+#define TC_HALO_ABYTES 17408   // activation box region of a halo stage: up to 136 pixel rows of 128 B, 1024-aligned
+struct TcGroup { int dy, dx0, ntap; int widx[3]; int dxo[3]; };
 struct TcFwdParams {
   CUtensorMap amap[4];
   CUtensorMap bmap;
@@ -27,12 +31,113 @@ struct TcFwdParams {
   int MT;                    // 128-pixel sub-tiles per CTA sharing every weight tile (B operand)
   int tw, th, tb;            // tiles per phase
   int nkb, BN, act, stages;
+  int dry;                   // tuning: skip the MMAs (measures the bare TMA ingest rate of the tile stream)
+  int ktail;                 // 16-channel MMA steps holding data in the last 64-channel k-block (the rest is OOB zero fill)
   int oy0[4], ox0[4], Hp[4], Wp[4], ntaps[4];
   TcTap taps[4][TC_MAX_TAPS];
   const float* bias;
   const bf16* residual;
   bf16* out;
+  // halo mode (tc_fwd_halo_kernel): taps that differ only in dx share ONE activation box widened by their dx span
+  int ngroups, halo_w;       // tap groups; box width in pixels (128 + span)
+  int halo_bo;               // encode the row phase in the descriptor's matrix-base-offset field
+  TcGroup groups[TC_MAX_GROUPS];
 };
+
+// Epilogue warps (8): drain the double-buffered TMEM accumulator of every tile this CTA owns:
+// tcgen05.ld -> bias / residual / activation -> bf16 -> global.  Shared by the plain and the halo kernel.
+__device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                int warp, int lane, int ntiles, int ntn, int tiles_pp) {
+    const int ew = warp - 2;                      // 0..7
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                     // which half of the BN columns
+    const int csplit = ((p.BN / 16 + 1) / 2) * 16;
+    const int cbeg = half ? csplit : 0, cend = half ? p.BN : csplit;
+    const int row = q * 32 + lane;
+    const int w = row % p.bw, h = (row / p.bw) % p.bh, bl = row / (p.bw * p.bh);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int nt = tile % ntn; int t = tile / ntn;
+      const int phase = t / tiles_pp; t -= phase * tiles_pp;
+      const int j0 = (t % p.tw) * p.bw; t /= p.tw;
+      const int i0 = (t % p.th) * p.bh; t /= p.th;
+      const int b0 = t * p.bb;
+      const int n0 = nt * p.BN;
+      const int pi = i0 + h, pj = j0 + w, b = b0 + bl;
+      const bool valid = (b < p.B) && (pi < p.Hp[phase]) && (pj < p.Wp[phase]);
+      const int oy = p.oy0[phase] + pi * p.ostep, ox = p.ox0[phase] + pj * p.ostep;
+      const long obase = (((long)b * p.Ho + oy) * p.Wo + ox) * p.Co + n0;
+      const int buf = lt & 1;
+      // residual (fused accumulate / skip connection) is read in groups of 4 x 16 channels, one group ahead of its use; the
+      // first group is in flight while this warp still waits for the accumulator, so the global-load latency is off the
+      // per-tile critical path
+      const bool use_res = (p.residual != nullptr) && valid;
+      uint4 rb[2][4][2];
+      auto load_group = [&](int g, int cg) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (use_res && cg + j * 16 < cend) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg + j * 16);
+            rb[g][j][0] = __ldg(rp);
+            rb[g][j][1] = __ldg(rp + 1);
+          }
+      };
+      load_group(0, cbeg);
+      mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+      int gsel = 0;
+      for (int cg = cbeg; cg < cend; cg += 64, gsel ^= 1) {
+        if (gsel == 0) load_group(1, cg + 64); else load_group(0, cg + 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = cg + j * 16;
+          if (c0 >= cend) break;
+          uint32_t r[16];
+          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), r);
+          if (valid) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+            if (p.bias) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
+            }
+            if (p.residual) {
+              const uint4 r0 = gsel == 0 ? rb[0][j][0] : rb[1][j][0], r1 = gsel == 0 ? rb[0][j][1] : rb[1][j][1];
+              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
+                v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
+              }
+            }
+            if (p.act == BG_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+            } else if (p.act == BG_ACT_TANH) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
+            }
+            uint4 o0, o1;
+            __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+            __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+              q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+            op[0] = o0;
+            op[1] = o1;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+    }
+}
 
 // Persistent: one CTA per SM walks the tile list (n-tile fastest, so concurrently running CTAs share the
 // activation tile in L2).  The TMA ring never drains between tiles, and the accumulator is double-buffered
@@ -53,7 +158,7 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
   const int ntn = p.Co / p.BN;
   const int ntiles = tiles_pp * p.nphase * ntn;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     for (int m = 0; m < 4; ++m) tma_prefetch_desc(&p.amap[m]);
     tma_prefetch_desc(&p.bmap);
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
@@ -67,7 +172,7 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nt = tile % ntn; int t = tile / ntn;
@@ -93,7 +198,7 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
@@ -103,92 +208,136 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
         mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
+        int kb = 0;
         for (int li = 0; li < total; ++li, ++it) {
           const int s = it % p.stages;
           const uint32_t par = (uint32_t)((it / p.stages) & 1);
           mbar_wait(smem_u32(&full_bar[s]), par);
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const int nk = (kb == p.nkb - 1) ? p.ktail : 4;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_desc_kmajor_sw128(sa + k * 32);
-            const uint64_t bd = umma_desc_kmajor_sw128(sa + 16384u + k * 32);
-            umma_bf16(tacc, ad, bd, idesc, (li | k) != 0 ? 1u : 0u);
+            if (k < nk && !p.dry) {
+              const uint64_t ad = umma_desc_kmajor_sw128(sa + k * 32);
+              const uint64_t bd = umma_desc_kmajor_sw128(sa + 16384u + k * 32);
+              umma_bf16(tacc, ad, bd, idesc, (li | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&empty_bar[s]));
+          if (++kb == p.nkb) kb = 0;
         }
         umma_commit(smem_u32(&tfull_bar[buf]));
       }
     }
   } else {
-    const int ew = warp - 2;                      // 0..7
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                     // which half of the BN columns
-    const int csplit = ((p.BN / 16 + 1) / 2) * 16;
-    const int cbeg = half ? csplit : 0, cend = half ? p.BN : csplit;
-    const int row = q * 32 + lane;
-    const int w = row % p.bw, h = (row / p.bw) % p.bh, bl = row / (p.bw * p.bh);
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-      const int nt = tile % ntn; int t = tile / ntn;
-      const int phase = t / tiles_pp; t -= phase * tiles_pp;
-      const int j0 = (t % p.tw) * p.bw; t /= p.tw;
-      const int i0 = (t % p.th) * p.bh; t /= p.th;
-      const int b0 = t * p.bb;
-      const int n0 = nt * p.BN;
-      const int pi = i0 + h, pj = j0 + w, b = b0 + bl;
-      const bool valid = (b < p.B) && (pi < p.Hp[phase]) && (pj < p.Wp[phase]);
-      const int oy = p.oy0[phase] + pi * p.ostep, ox = p.ox0[phase] + pj * p.ostep;
-      const long obase = (((long)b * p.Ho + oy) * p.Wo + ox) * p.Co + n0;
-      const int buf = lt & 1;
-      mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
-      tc_fence_after();
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), r);
-        if (valid) {
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-          if (p.bias) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
+    tc_fwd_epilogue(p, tmem_base, tfull_bar, tempty_bar, warp, lane, ntiles, ntn, tiles_pp);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// Halo variant for stride-1 layers whose tile is one 128-pixel image-row segment: the taps (dy, dx0..dx0+2) of a
+// group read the SAME activation rows shifted by one pixel, i.e. by one 128-byte row of the K-major SWIZZLE_128B tile.
+// One TMA box of 128+span pixels feeds all of them: tap j's A descriptor starts dxo[j] rows into the box (matrix base
+// offset = dxo[j], the row phase of the swizzle pattern), so a 3x3 conv loads each activation row 3x instead of 9x.
+// These layers are bound by the L2->SM ingest of the activation stream, not by the tensor pipe.
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(320, 1) tc_fwd_halo_kernel(const __grid_constant__ TcFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t wbytes = (uint32_t)p.BN * 128u;                       // one weight tile
+  const uint32_t stage_bytes = TC_HALO_ABYTES + 3u * wbytes;
+  const uint32_t abox_bytes = (uint32_t)p.halo_w * 128u;
+  const int tiles_pp = p.tw * p.th * p.tb;
+  const int ntn = p.Co / p.BN;
+  const int ntiles = tiles_pp * ntn;
+
+  if (warp == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&p.amap[0]);
+    tma_prefetch_desc(&p.bmap);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = tile % ntn; int t = tile / ntn;
+        const int j0 = (t % p.tw) * p.bw; t /= p.tw;
+        const int i0 = (t % p.th) * p.bh; t /= p.th;
+        const int b0 = t * p.bb;
+        const int n0 = nt * p.BN;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const TcGroup& grp = p.groups[g];
+          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t par = (uint32_t)((it / p.stages) & 1);
+            mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            mbar_expect_tx(fb, abox_bytes + (uint32_t)grp.ntap * wbytes);
+            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+            tma_load_4d(sa, &p.amap[0], fb, kb * 64, j0 + grp.dx0, i0 + grp.dy, b0);
+            for (int j = 0; j < grp.ntap; ++j)
+              tma_load_3d(sa + TC_HALO_ABYTES + (uint32_t)j * wbytes, &p.bmap, fb, kb * 64, n0, grp.widx[j]);
           }
-          if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
-            uint4 r0 = rp[0], r1 = rp[1];
-            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
-              v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
-            }
-          }
-          if (p.act == BG_ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-          } else if (p.act == BG_ACT_TANH) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
-          }
-          uint4 o0, o1;
-          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-            q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
-          }
-          uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
-          op[0] = o0;
-          op[1] = o1;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
     }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
+        uint32_t first = 0u;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const TcGroup& grp = p.groups[g];
+          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t par = (uint32_t)((it / p.stages) & 1);
+            mbar_wait(smem_u32(&full_bar[s]), par);
+            tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+            const int nk = (kb == p.nkb - 1) ? p.ktail : 4;
+            for (int j = 0; j < grp.ntap; ++j) {
+              const uint32_t a0 = sa + (uint32_t)grp.dxo[j] * 128u;
+              const uint64_t abase_off = p.halo_bo ? ((uint64_t)(grp.dxo[j] & 7) << 49) : 0ull;   // matrix base offset: row phase of the swizzle
+              const uint32_t b0s = sa + TC_HALO_ABYTES + (uint32_t)j * wbytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < nk) {
+                  umma_bf16(tacc, umma_desc_kmajor_sw128(a0 + k * 32) | abase_off, umma_desc_kmajor_sw128(b0s + k * 32), idesc, first);
+                  first = 1u;
+                }
+              }
+            }
+            umma_commit(smem_u32(&empty_bar[s]));
+          }
+        }
+        umma_commit(smem_u32(&tfull_bar[buf]));
+      }
+    }
+  } else {
+    tc_fwd_epilogue(p, tmem_base, tfull_bar, tempty_bar, warp, lane, ntiles, ntn, tiles_pp);
   }
   tc_fence_before();
   __syncthreads();
@@ -240,8 +389,10 @@ static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, i
   cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
   cuuint32_t es[4] = {1, 1, 1, 1};
   const char* ptr = (const char*)base + ((long)pa * W + pb) * C * 2;
+  static int promo = -1;                          // tuning knob: L2 promotion of the activation maps (default 256 B)
+  if (promo < 0) { const char* e = getenv("BG_TC_PROMO"); promo = e ? atoi(e) : 3; if (promo < 0 || promo > 3) promo = 3; }
   CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { bg_set_error("cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d B=%d s=%d)", (int)r, C, Ws, Hs, B, s); return BG_ERR_CUDA; }
   return BG_OK;
 }
@@ -298,6 +449,13 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   if (BN == 0) return BG_OK;
   int bw = 128, bh = 1, bb = 1;
   choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 128, &bw, &bh, &bb);
+  {
+    const char* e = getenv("BG_TC_BOX");          // tuning knob: "bw,bh,bb" (product 128)
+    int a = 0, b = 0, c = 0;
+    if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a * b * c == 128) { bw = a; bh = b; bb = c; }
+    const char* dry = getenv("BG_TC_DRY");
+    P.dry = (dry && dry[0] == '1') ? 1 : 0;
+  }
   const int s = g.istep;
   int rc;
   for (int pa = 0; pa < s; ++pa)
@@ -313,10 +471,16 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   P.bw = bw; P.bh = bh; P.bb = bb; P.MT = 1;
   P.tw = (int)bg_cdiv(g.ph[0].Wp, bw); P.th = (int)bg_cdiv(g.ph[0].Hp, bh); P.tb = (int)bg_cdiv(g.B, bb);
   P.nkb = (int)bg_cdiv(g.Ci, 64);
+  P.ktail = (int)bg_cdiv(g.Ci - (P.nkb - 1) * 64, 16);
   P.BN = BN; P.act = act;
   const int stage_bytes = 16384 + BN * 128;
   int stages = (200 * 1024) / stage_bytes;       // one persistent CTA per SM: a deep ring that never drains
   if (stages > 8) stages = 8;
+  {
+    static int st_env = -1;                       // tuning knob (tools/layer_bench.py)
+    if (st_env < 0) { const char* e = getenv("BG_TC_FWD_STAGES"); st_env = e ? atoi(e) : 0; }
+    if (st_env >= 2 && st_env < stages) stages = st_env;
+  }
   if (stages < 2) return BG_OK;
   P.stages = stages;
   for (int ph = 0; ph < g.nphase; ++ph) {
@@ -331,9 +495,66 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     }
   }
   P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
   const long ntiles = (long)P.tw * P.th * P.tb * g.nphase * (g.Co / BN);
   dim3 grid((unsigned)min(ntiles, (long)bg_num_sms()));
+  // halo mode: stride-1 layer tiled in full 128-pixel row segments -> taps differing only in dx share one activation box
+  {
+    const char* he = getenv("BG_TC_HALO");        // tuning / A-B knob, read per call
+    const int halo_env = he ? atoi(he) : 1;
+    const char* hb = getenv("BG_TC_HALO_BO");
+    P.halo_bo = hb ? atoi(hb) : 0;             // measured: the UMMA swizzle is a function of the absolute smem address, the field must stay 0
+    const int hstage = TC_HALO_ABYTES + 3 * BN * 128;
+    int hstages = (200 * 1024) / hstage;
+    if (hstages > 8) hstages = 8;
+    if (halo_env && g.nphase == 1 && s == 1 && bw == 128 && bh == 1 && bb == 1 && hstages >= 3) {
+      TcTap srt[TC_MAX_TAPS];
+      const int nt = g.ph[0].ntaps;
+      for (int t = 0; t < nt; ++t) srt[t] = P.taps[0][t];
+      for (int a = 1; a < nt; ++a)                        // insertion sort by (dy, dx)
+        for (int b = a; b > 0 && (srt[b].dy < srt[b - 1].dy || (srt[b].dy == srt[b - 1].dy && srt[b].dx < srt[b - 1].dx)); --b) {
+          TcTap tmp = srt[b]; srt[b] = srt[b - 1]; srt[b - 1] = tmp;
+        }
+      int ng = 0, span = 0, shared = 0;
+      bool ok = true;
+      for (int t = 0; t < nt && ok;) {
+        if (ng == TC_MAX_GROUPS) { ok = false; break; }
+        TcGroup& gr = P.groups[ng];
+        gr.dy = srt[t].dy; gr.dx0 = srt[t].dx; gr.ntap = 0;
+        while (t < nt && gr.ntap < 3 && srt[t].dy == gr.dy && srt[t].dx == gr.dx0 + gr.ntap) {
+          gr.widx[gr.ntap] = srt[t].widx; gr.dxo[gr.ntap] = gr.ntap; gr.ntap++; t++;
+        }
+        span = max(span, gr.ntap - 1);
+        shared += gr.ntap - 1;
+        ng++;
+      }
+      if (ok && shared > 0) {
+        P.ngroups = ng; P.halo_w = 128 + span; P.stages = hstages;
+        if ((rc = make_act_map(&P.amap[0], in, g.B, in_H, in_W, g.Ci, 1, 0, 0, P.halo_w, 1, 1))) return rc;
+        const size_t hsmem = (size_t)hstages * hstage + 1024;
+#define TC_LAUNCH_H(COLS)                                                                                        \
+  do {                                                                                                           \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      BG_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_halo_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    tc_fwd_halo_kernel<COLS><<<grid, 320, hsmem, st>>>(P);                                                       \
+  } while (0)
+        const int hcols = 2 * BN;
+        if (hcols <= 32) TC_LAUNCH_H(32);
+        else if (hcols <= 64) TC_LAUNCH_H(64);
+        else if (hcols <= 128) TC_LAUNCH_H(128);
+        else if (hcols <= 256) TC_LAUNCH_H(256);
+        else TC_LAUNCH_H(512);
+#undef TC_LAUNCH_H
+        BG_LAUNCH_CHECK();
+        g_cnt_tc_fwd++;
+        *taken = 1;
+        return BG_OK;
+      }
+    }
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
 #define TC_LAUNCH(COLS)                                                                                          \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
@@ -370,7 +591,6 @@ struct TcWgParams {
   int Ci, Co, BN, nblkB;        // M total, N total, N tile, 64-channel blocks per B tile
   int ntile_n, nsplit, nboxes, stages;
   int ntaps;
-  int TPC;                      // taps per CTA: they share every Og (B operand) tile, one TMEM accumulator each
   TcTap taps[TC_MAX_TAPS];
   float* part;
   long zstride, wtap, wk;
@@ -386,17 +606,14 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int tap0 = blockIdx.y * p.TPC;
-  const int nt = min(p.TPC, p.ntaps - tap0);          // taps handled by this CTA
-  const uint32_t b_off = (uint32_t)nt * 16384u;       // stage layout: [A tap 0][A tap 1]...[B]
-  const uint32_t stage_bytes = b_off + (uint32_t)p.nblkB * 8192u;
-  const uint32_t stage_stride = (uint32_t)p.TPC * 16384u + (uint32_t)p.nblkB * 8192u;
+  const uint32_t stage_bytes = 16384u + (uint32_t)p.nblkB * 8192u;
   const int m0 = (blockIdx.x / p.ntile_n) * 128, n0 = (blockIdx.x % p.ntile_n) * p.BN;
+  const TcTap tap = p.taps[blockIdx.y];
   const int box_beg = (int)(((long)blockIdx.z * p.nboxes) / p.nsplit);
   const int box_end = (int)(((long)(blockIdx.z + 1) * p.nboxes) / p.nsplit);
   const int total = box_end - box_beg;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one_sync()) {
     for (int m = 0; m < 4; ++m) tma_prefetch_desc(&p.amap[m]);
     tma_prefetch_desc(&p.bmap);
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
@@ -410,7 +627,7 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int it = 0; it < total; ++it) {
         int t = box_beg + it;
         const int j0 = (t % p.tw) * p.bw; t /= p.tw;
@@ -421,31 +638,27 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
         mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, stage_bytes);
-        const uint32_t sa = smem_base + (uint32_t)s * stage_stride;
-        for (int t2 = 0; t2 < nt; ++t2) {
-          const TcTap tap = p.taps[tap0 + t2];
-          tma_load_4d(sa + (uint32_t)t2 * 16384u, &p.amap[tap.map], fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
-          tma_load_4d(sa + (uint32_t)t2 * 16384u + 8192u, &p.amap[tap.map], fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
-        }
+        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+        tma_load_4d(sa, &p.amap[tap.map], fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
+        tma_load_4d(sa + 8192u, &p.amap[tap.map], fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
         for (int nb = 0; nb < p.nblkB; ++nb)
-          tma_load_4d(sa + b_off + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
+          tma_load_4d(sa + 16384u + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);
       for (int it = 0; it < total; ++it) {
         const int s = it % p.stages;
         const uint32_t par = (uint32_t)((it / p.stages) & 1);
         mbar_wait(smem_u32(&full_bar[s]), par);
         tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)s * stage_stride;
+        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {     // 16 pixels (2 swizzle atoms of 8 rows) per MMA
-          const uint64_t bd = umma_desc_mnmajor_sw128(sa + b_off + k * 2048, 8192, 1024);
-          for (int t2 = 0; t2 < nt; ++t2)
-            umma_bf16(tmem_base + (uint32_t)(t2 * p.BN), umma_desc_mnmajor_sw128(sa + (uint32_t)t2 * 16384u + k * 2048, 8192, 1024), bd,
-                      idesc, (it | k) != 0 ? 1u : 0u);
+          const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, 8192, 1024);
+          const uint64_t bd = umma_desc_mnmajor_sw128(sa + 16384u + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[s]));
       }
@@ -454,26 +667,24 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
   } else {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
+    float* dst = p.part + (long)blockIdx.z * p.zstride + (long)tap.widx * p.wtap + (long)m * p.wk + n0;
     if (total > 0) {
       mbar_wait(smem_u32(&accum_bar), 0);
       tc_fence_after();
     }
-    for (int t2 = 0; t2 < nt; ++t2) {
-      float* dst = p.part + (long)blockIdx.z * p.zstride + (long)p.taps[tap0 + t2].widx * p.wtap + (long)m * p.wk + n0;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t r[16];
-        if (total > 0) tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t2 * p.BN + c0), r);
-        else {
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t r[16];
+      if (total > 0) tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] = 0u;
-        }
-        if (m < p.Ci) {
-          float4* o = reinterpret_cast<float4*>(dst + c0);
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+      }
+      if (m < p.Ci) {
+        float4* o = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
-                               __uint_as_float(r[4 * e + 3]));
-        }
+        for (int e = 0; e < 4; ++e)
+          o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                             __uint_as_float(r[4 * e + 3]));
       }
     }
   }
@@ -488,15 +699,29 @@ extern "C" int bg_debug_counters(int* tc_fwd, int* tc_wgrad) {
   return BG_OK;
 }
 
-static int wg_nsplit(int tiles, int nboxes) {
-  long ns = bg_cdiv(2L * bg_num_sms(), tiles);
-  if (ns > nboxes / 4) ns = nboxes / 4;      // keep >= 4 boxes (256 pixels) per CTA
-  if (ns > 64) ns = 64;
-  if (ns < 1) ns = 1;
-  return (int)ns;
+// split-K factor: the grid is tiles*ns CTAs on `slots` = SMs x resident CTAs.  Minimise a microsecond model of
+//   waves x (boxes per CTA x t_box + t_fixed) + t_reduce
+// t_box: one 64-pixel stage at this CTA's share of the L2->SM bandwidth (~80 B/ns per SM); t_fixed: prologue, pipeline
+// fill and the fp32 accumulator drain at the SM's share of HBM write bandwidth; t_reduce: the split-K reduction pass
+// (absent for ns == 1).  297 CTAs on 296 slots cost two waves; splitting a 1536x1536 layer costs more than it buys.
+static int wg_nsplit(int tiles, int nboxes, int ctas_per_sm, int BN, long numel) {
+  const long slots = (long)bg_num_sms() * ctas_per_sm;
+  long mx = nboxes / 4;
+  if (mx > 64) mx = 64;
+  if (mx < 1) mx = 1;
+  const double t_box = (16384.0 + ((BN + 63) / 64) * 8192.0) / (80e3 / ctas_per_sm);       // us
+  const double t_fixed = 2.0 + 128.0 * BN * 4.0 / (43e3 / ctas_per_sm);                      // us
+  long best = 1;
+  double best_cost = 1e30;
+  for (long ns = 1; ns <= mx; ++ns) {
+    double cost = (double)bg_cdiv((long)tiles * ns, slots) * ((double)bg_cdiv(nboxes, ns) * t_box + t_fixed);
+    if (ns > 1) cost += 3.0 + (double)(ns + 1) * numel * 4.0 / 5e6;
+    if (cost < best_cost * 0.999) { best_cost = cost; best = ns; }
+  }
+  return (int)best;
 }
 
-struct WgPlan { int ok, BN, bw, bh, bb, tw, th, tb, nboxes, tiles, nsplit, TPC; };
+struct WgPlan { int ok, BN, bw, bh, bb, tw, th, tb, nboxes, tiles, nsplit; };
 
 static WgPlan wg_plan(const BgGeom& g) {
   WgPlan pl;
@@ -511,19 +736,9 @@ static WgPlan wg_plan(const BgGeom& g) {
   choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 64, &pl.bw, &pl.bh, &pl.bb);
   pl.tw = (int)bg_cdiv(g.ph[0].Wp, pl.bw); pl.th = (int)bg_cdiv(g.ph[0].Hp, pl.bh); pl.tb = (int)bg_cdiv(g.B, pl.bb);
   pl.nboxes = pl.tw * pl.th * pl.tb;
-  // taps per CTA: share the Og tile across taps while accumulators (TPC*BN <= 512 columns) and two pipeline stages fit
-  {
-    const int nt = g.ph[0].ntaps, nblk = (pl.BN + 63) / 64;
-    int best = 1;
-    for (int t = 2; t <= 4; ++t) {
-      if (t * pl.BN > 512 || t > nt) continue;
-      if (2 * (t * 16384 + nblk * 8192) > 200 * 1024) continue;
-      if (bg_cdiv(nt, t) * t - nt <= (best > 1 ? bg_cdiv(nt, best) * best - nt : 99)) best = t;   // least idle accumulator slots, prefer larger
-    }
-    pl.TPC = best;
-  }
-  pl.tiles = (int)(bg_cdiv(g.Ci, 128) * (g.Co / pl.BN) * bg_cdiv(g.ph[0].ntaps, pl.TPC));
-  pl.nsplit = wg_nsplit(pl.tiles, pl.nboxes);
+  pl.tiles = (int)(bg_cdiv(g.Ci, 128) * (g.Co / pl.BN) * g.ph[0].ntaps);
+  pl.nsplit = wg_nsplit(pl.tiles, pl.nboxes, (16384 + ((pl.BN + 63) / 64) * 8192 <= 32 * 1024) ? 2 : 1, pl.BN,
+                        (long)g.ph[0].ntaps * g.Ci * g.Co);
   pl.ok = 1;
   return pl;
 }
@@ -578,11 +793,8 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
   P.bw = pl.bw; P.bh = pl.bh; P.bb = pl.bb; P.tw = pl.tw; P.th = pl.th; P.tb = pl.tb;
   P.Ci = g.Ci; P.Co = g.Co; P.BN = pl.BN; P.nblkB = (pl.BN + 63) / 64;
   P.ntile_n = g.Co / pl.BN; P.nsplit = pl.nsplit; P.nboxes = pl.nboxes;
-  P.TPC = pl.TPC;
-  const int stage_bytes = pl.TPC * 16384 + P.nblkB * 8192;
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > 4) stages = 4;
-  if (stages < 2) stages = 2;
+  const int stage_bytes = 16384 + P.nblkB * 8192;
+  int stages = (stage_bytes <= 32 * 1024) ? 3 : 4;     // 2 CTAs per SM for the small tiles
   P.stages = stages;
   P.ntaps = g.ph[0].ntaps;
   for (int t = 0; t < P.ntaps; ++t) {
@@ -596,7 +808,7 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
   P.part = pl.nsplit > 1 ? (float*)wsp : dw;
   P.zstride = numel; P.wtap = g.wtap; P.wk = g.wk;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  dim3 grid((unsigned)(bg_cdiv(g.Ci, 128) * P.ntile_n), (unsigned)bg_cdiv(P.ntaps, pl.TPC), (unsigned)pl.nsplit);
+  dim3 grid((unsigned)(bg_cdiv(g.Ci, 128) * P.ntile_n), (unsigned)P.ntaps, (unsigned)pl.nsplit);
 #define TC_LAUNCH_WG(COLS)                                                                                       \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
@@ -606,12 +818,10 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
     }                                                                                                            \
     tc_wgrad_kernel<COLS><<<grid, 192, smem, st>>>(P);                                                           \
   } while (0)
-  const int wcols = pl.TPC * pl.BN;
-  if (wcols <= 32) TC_LAUNCH_WG(32);
-  else if (wcols <= 64) TC_LAUNCH_WG(64);
-  else if (wcols <= 128) TC_LAUNCH_WG(128);
-  else if (wcols <= 256) TC_LAUNCH_WG(256);
-  else TC_LAUNCH_WG(512);
+  if (pl.BN <= 32) TC_LAUNCH_WG(32);
+  else if (pl.BN <= 64) TC_LAUNCH_WG(64);
+  else if (pl.BN <= 128) TC_LAUNCH_WG(128);
+  else TC_LAUNCH_WG(256);
 #undef TC_LAUNCH_WG
   BG_LAUNCH_CHECK();
   if (pl.nsplit > 1) {

@@ -8,7 +8,7 @@
 
 static inline int bn_nchunk(int B, long rows, int C) {
   // chunks of one sample's HW rows; B * nchunk * channel-blocks ~ 8 CTAs per SM
-  long want = bg_cdiv(8L * bg_num_sms(), (long)B * bg_cdiv(C, BN_CPB));
+  long want = bg_cdiv(8L * bg_num_sms(), (long)B);
   long mx = bg_cdiv(rows, 32);
   long n = want < mx ? want : mx;
   if (n < 1) n = 1;
@@ -16,66 +16,82 @@ static inline int bn_nchunk(int B, long rows, int C) {
   return (int)n;
 }
 
+// Thread layout of the streaming kernels: a pixel row of C channels is covered by TPR = C / V threads holding one
+// 16-byte vector each (V = 8 bf16 / 4 fp32), R = blockDim / TPRB consecutive rows per block iteration, so a warp
+// always reads/writes full contiguous lines whatever C is.  Channel blocks (gridDim.x) only when TPR > 256.
+struct BnLayout { int V, TPR, nxb, TPRB, R, threads; };
+static BnLayout bn_layout(int C, int dtype) {
+  BnLayout L;
+  L.V = dtype == BG_F32 ? 4 : 8;
+  L.TPR = C / L.V;
+  L.nxb = (int)bg_cdiv(L.TPR, 256);
+  while (L.TPR % L.nxb) ++L.nxb;
+  L.TPRB = L.TPR / L.nxb;
+  L.R = 256 / L.TPRB;
+  if (L.R < 1) L.R = 1;
+  L.threads = L.TPRB * L.R;
+  return L;
+}
+static inline bool bn_vec_ok(int C, int dtype) { return C % (dtype == BG_F32 ? 4 : 8) == 0; }
+
 // MODE 0: q1 = x, q2 = x^2.   MODE 1: g = dy * act'(y); q1 = g, q2 = g * xhat
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                  const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 int gb_bstride, int act, float eps, float* __restrict__ part, long HW, int C, int nchunk) {
-  // grid: x = channel block, y = chunk (over HW of one sample), z = sample
-  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * BN_CPB + lane * 4;
+                 int gb_bstride, int act, float eps, float* __restrict__ part, long HW, int C, int nchunk, int TPRB, int R) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float bn_sh[];                    // [2][R][TPRB*V]
+  const int r_in = threadIdx.x / TPRB, cv = threadIdx.x - r_in * TPRB;
+  const int c = (blockIdx.x * TPRB + cv) * V;         // first channel of this thread
   const int b = blockIdx.z;
   const long rpc = (HW + nchunk - 1) / nchunk;
   const long r0 = (long)blockIdx.y * rpc, r1 = min(HW, r0 + rpc);
-  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c < C) {
-    float inv[4], shift[4], mu[4], rs[4];
-    if (MODE == 1) {
+  float s1[V], s2[V];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        rs[e] = rsqrtf(var[c + e] + eps);
-        mu[e] = mean[c + e];
-        inv[e] = rs[e] * gamma[(long)b * gb_bstride + c + e];
-        shift[e] = beta[(long)b * gb_bstride + c + e] - mu[e] * inv[e];
-      }
+  for (int e = 0; e < V; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+  float inv[V], shift[V], mu[V], rs[V];
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      rs[e] = rsqrtf(var[c + e] + eps);
+      mu[e] = mean[c + e];
+      inv[e] = rs[e] * gamma[(long)b * gb_bstride + c + e];
+      shift[e] = beta[(long)b * gb_bstride + c + e] - mu[e] * inv[e];
     }
-    const long base = (long)b * HW * C + c;
-#pragma unroll 4
-  #pragma unroll 4
-  for (long r = r0 + ty; r < r1; r += 8) {
-      f4 xv = bg_ld4(x, base + r * C);
-      float xe[4] = {xv.x, xv.y, xv.z, xv.w};
-      if (MODE == 0) {
+  }
+  const long base = (long)b * HW * C + c;
+#pragma unroll 2
+  for (long r = r0 + r_in; r < r1; r += R) {
+    float xe[V];
+    Vec<T>::ld(x, base + r * C, xe);
+    if (MODE == 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { s1[e] += xe[e]; s2[e] = fmaf(xe[e], xe[e], s2[e]); }
-      } else {
-        f4 dv = bg_ld4(dy, base + r * C);
-        float de[4] = {dv.x, dv.y, dv.z, dv.w};
+      for (int e = 0; e < V; ++e) { s1[e] += xe[e]; s2[e] = fmaf(xe[e], xe[e], s2[e]); }
+    } else {
+      float de[V];
+      Vec<T>::ld(dy, base + r * C, de);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float g = de[e];
-          if (act == BG_ACT_RELU && !(xe[e] * inv[e] + shift[e] > 0.f)) g = 0.f;
-          s1[e] += g;
-          s2[e] = fmaf(g, (xe[e] - mu[e]) * rs[e], s2[e]);
-        }
+      for (int e = 0; e < V; ++e) {
+        float g = de[e];
+        if (act == BG_ACT_RELU && !(xe[e] * inv[e] + shift[e] > 0.f)) g = 0.f;
+        s1[e] += g;
+        s2[e] = fmaf(g, (xe[e] - mu[e]) * rs[e], s2[e]);
       }
     }
   }
-  __shared__ float sh[8][2][BN_CPB + 4];
+  const int CB = TPRB * V;                            // channels of this block
+  float* sh1 = bn_sh;
+  float* sh2 = bn_sh + R * CB;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) { sh[ty][0][lane * 4 + e] = s1[e]; sh[ty][1][lane * 4 + e] = s2[e]; }
+  for (int e = 0; e < V; ++e) { sh1[r_in * CB + cv * V + e] = s1[e]; sh2[r_in * CB + cv * V + e] = s2[e]; }
   __syncthreads();
-  if (threadIdx.x < BN_CPB) {
-    const int cc = blockIdx.x * BN_CPB + threadIdx.x;
-    if (cc < C) {
-      float a = 0.f, q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { a += sh[i][0][threadIdx.x]; q += sh[i][1][threadIdx.x]; }
-      float* dst = part + (((long)b * nchunk + blockIdx.y) * 2) * C;
-      dst[cc] = a;
-      dst[C + cc] = q;
-    }
+  for (int i = threadIdx.x; i < CB; i += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int r = 0; r < R; ++r) { a += sh1[r * CB + i]; q += sh2[r * CB + i]; }
+    float* dst = part + (((long)b * nchunk + blockIdx.y) * 2) * C + blockIdx.x * CB;
+    dst[i] = a;
+    dst[C + i] = q;
   }
 }
 
@@ -121,10 +137,13 @@ extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, i
   BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
   BG_REQUIRE(ws && ws_bytes >= bg_bn_workspace_bytes(B, HW, C), BG_ERR_WORKSPACE, "bn workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  BG_REQUIRE(bn_vec_ok(C, dtype), BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of %d", C, dtype == BG_F32 ? 4 : 8);
   const int nchunk = bn_nchunk(B, HW, C);
-  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
-  BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0,
-                                                                        0.f, (float*)ws, HW, C, nchunk));
+  const BnLayout L = bn_layout(C, dtype);
+  dim3 grid(L.nxb, nchunk, B);
+  const size_t shb = (size_t)2 * L.R * L.TPRB * L.V * sizeof(float);
+  BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 0><<<grid, L.threads, shb, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0,
+                                                                                0.f, (float*)ws, HW, C, nchunk, L.TPRB, L.R));
   BG_LAUNCH_CHECK();
   bn_stats_final_kernel<<<(unsigned)bg_cdiv(C, 32), 1024, 0, st>>>((const float*)ws, sums, B * nchunk, C);
   BG_LAUNCH_CHECK();
@@ -160,46 +179,48 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int gb_bstride, T* __restrict__ y, int act,
-                float eps, long HW, int C, int nchunk) {
-  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * BN_CPB + lane * 4;
-  if (c >= C) return;
+                float eps, long HW, int C, int nchunk, int TPRB, int R) {
+  constexpr int V = Vec<T>::N;
+  const int r_in = threadIdx.x / TPRB, cv = threadIdx.x - r_in * TPRB;
+  const int c = (blockIdx.x * TPRB + cv) * V;
   const int b = blockIdx.z;
   const long rpc = (HW + nchunk - 1) / nchunk;
   const long r0 = (long)blockIdx.y * rpc, r1 = min(HW, r0 + rpc);
-  float inv[4], shift[4];
+  float inv[V], shift[V];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < V; ++e) {
     inv[e] = rsqrtf(var[c + e] + eps) * gamma[(long)b * gb_bstride + c + e];
     shift[e] = beta[(long)b * gb_bstride + c + e] - mean[c + e] * inv[e];
   }
   const long base = (long)b * HW * C + c;
-#pragma unroll 4
-  for (long r = r0 + ty; r < r1; r += 8) {
-    f4 xv = bg_ld4(x, base + r * C);
-    float o[4] = {xv.x * inv[0] + shift[0], xv.y * inv[1] + shift[1], xv.z * inv[2] + shift[2], xv.w * inv[3] + shift[3]};
-    if (act == BG_ACT_RELU) {
+#pragma unroll 2
+  for (long r = r0 + r_in; r < r1; r += R) {
+    float v[V];
+    Vec<T>::ld(x, base + r * C, v);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+    for (int e = 0; e < V; ++e) {
+      v[e] = v[e] * inv[e] + shift[e];
+      if (act == BG_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
     }
-    bg_st4(y, base + r * C, f4{o[0], o[1], o[2], o[3]});
+    Vec<T>::st(y, base + r * C, v);
   }
 }
 
 static inline int bn_apply_chunks(int B, long HW, int C) {
-  long want = bg_cdiv(16L * bg_num_sms(), (long)B * bg_cdiv(C, BN_CPB));
-  long mx = bg_cdiv(HW, 8);
+  long want = bg_cdiv(16L * bg_num_sms(), (long)B);
+  long mx = bg_cdiv(HW, 32);
   long n = want < mx ? want : mx;
   return (int)(n < 1 ? 1 : n);
 }
 
 extern "C" int bg_bn_apply(const void* x, const float* mean, const float* var, const float* gamma, const float* beta,
                            int gb_bstride, void* y, int act, float eps, int B, long HW, int C, int dtype, void* stream) {
-  BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
+  BG_REQUIRE(bn_vec_ok(C, dtype), BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of %d", C, dtype == BG_F32 ? 4 : 8);
   const int nchunk = bn_apply_chunks(B, HW, C);
-  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
-  BG_DISPATCH_DTYPE(dtype, T, bn_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, mean, var, gamma, beta, gb_bstride,
-                                                                                     (T*)y, act, eps, HW, C, nchunk));
+  const BnLayout L = bn_layout(C, dtype);
+  dim3 grid(L.nxb, nchunk, B);
+  BG_DISPATCH_DTYPE(dtype, T, bn_apply_kernel<T><<<grid, L.threads, 0, (cudaStream_t)stream>>>((const T*)x, mean, var, gamma, beta, gb_bstride,
+                                                                                           (T*)y, act, eps, HW, C, nchunk, L.TPRB, L.R));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
@@ -210,10 +231,13 @@ extern "C" int bg_bn_bwd_reduce(const void* dy, const void* x, const float* mean
   BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
   BG_REQUIRE(ws && ws_bytes >= bg_bn_workspace_bytes(B, HW, C), BG_ERR_WORKSPACE, "bn workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  BG_REQUIRE(bn_vec_ok(C, dtype), BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of %d", C, dtype == BG_F32 ? 4 : 8);
   const int nchunk = bn_nchunk(B, HW, C);
-  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
-  BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, mean, var, gamma, beta, gb_bstride,
-                                                                        act, eps, (float*)ws, HW, C, nchunk));
+  const BnLayout L = bn_layout(C, dtype);
+  dim3 grid(L.nxb, nchunk, B);
+  const size_t shb = (size_t)2 * L.R * L.TPRB * L.V * sizeof(float);
+  BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 1><<<grid, L.threads, shb, st>>>((const T*)x, (const T*)dy, mean, var, gamma, beta, gb_bstride,
+                                                                                act, eps, (float*)ws, HW, C, nchunk, L.TPRB, L.R));
   BG_LAUNCH_CHECK();
   dim3 g2((unsigned)bg_cdiv(C, 128), B);
   bn_bwd_final_kernel<<<g2, 128, 0, st>>>((const float*)ws, dgamma, dbeta, nchunk, C);
@@ -257,16 +281,16 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int gb_bstride, const double* __restrict__ s, double count, T* __restrict__ dx, int act, float eps,
-                    long HW, int C, int nchunk) {
-  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * BN_CPB + lane * 4;
-  if (c >= C) return;
+                    long HW, int C, int nchunk, int TPRB, int R) {
+  constexpr int V = Vec<T>::N;
+  const int r_in = threadIdx.x / TPRB, cv = threadIdx.x - r_in * TPRB;
+  const int c = (blockIdx.x * TPRB + cv) * V;
   const int b = blockIdx.z;
   const long rpc = (HW + nchunk - 1) / nchunk;
   const long r0 = (long)blockIdx.y * rpc, r1 = min(HW, r0 + rpc);
-  float rs[4], gm[4], inv[4], shift[4], mu[4], m1[4], m2[4];
+  float rs[V], gm[V], inv[V], shift[V], mu[V], m1[V], m2[V];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < V; ++e) {
     rs[e] = rsqrtf(var[c + e] + eps);
     gm[e] = gamma[(long)b * gb_bstride + c + e];
     mu[e] = mean[c + e];
@@ -276,29 +300,30 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
     m2[e] = (float)(s[C + c + e] / count);
   }
   const long base = (long)b * HW * C + c;
-#pragma unroll 4
-  for (long r = r0 + ty; r < r1; r += 8) {
-    f4 xv = bg_ld4(x, base + r * C), dv = bg_ld4(dy, base + r * C);
-    float xe[4] = {xv.x, xv.y, xv.z, xv.w}, de[4] = {dv.x, dv.y, dv.z, dv.w}, o[4];
+  for (long r = r0 + r_in; r < r1; r += R) {
+    float xe[V], de[V];
+    Vec<T>::ld(x, base + r * C, xe);
+    Vec<T>::ld(dy, base + r * C, de);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < V; ++e) {
       float g = de[e];
       if (act == BG_ACT_RELU && !(xe[e] * inv[e] + shift[e] > 0.f)) g = 0.f;
-      o[e] = rs[e] * (gm[e] * g - m1[e] - (xe[e] - mu[e]) * rs[e] * m2[e]);
+      de[e] = rs[e] * (gm[e] * g - m1[e] - (xe[e] - mu[e]) * rs[e] * m2[e]);
     }
-    bg_st4(dx, base + r * C, f4{o[0], o[1], o[2], o[3]});
+    Vec<T>::st(dx, base + r * C, de);
   }
 }
 
 extern "C" int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* var, const float* gamma,
                                const float* beta, int gb_bstride, const double* s, double count, void* dx, int act, float eps,
                                int B, long HW, int C, int dtype, void* stream) {
-  BG_REQUIRE(C % 4 == 0, BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of 4", C);
+  BG_REQUIRE(bn_vec_ok(C, dtype), BG_ERR_UNSUPPORTED, "bn: C=%d must be a multiple of %d", C, dtype == BG_F32 ? 4 : 8);
   const int nchunk = bn_apply_chunks(B, HW, C);
-  dim3 grid((unsigned)bg_cdiv(C, BN_CPB), nchunk, B);
-  BG_DISPATCH_DTYPE(dtype, T, bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, mean, var, gamma,
-                                                                                         beta, gb_bstride, s, count, (T*)dx, act,
-                                                                                         eps, HW, C, nchunk));
+  const BnLayout L = bn_layout(C, dtype);
+  dim3 grid(L.nxb, nchunk, B);
+  BG_DISPATCH_DTYPE(dtype, T, bn_bwd_apply_kernel<T><<<grid, L.threads, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)x, mean, var, gamma,
+                                                                                               beta, gb_bstride, s, count, (T*)dx, act,
+                                                                                               eps, HW, C, nchunk, L.TPRB, L.R));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

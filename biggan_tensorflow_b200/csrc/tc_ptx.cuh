@@ -8,6 +8,22 @@
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp.  Role bodies (TMA producer, MMA issuer) MUST be guarded with this and not with
+// `lane == 0`: ptxas recognises elect.sync and keeps descriptors / coordinates on the uniform datapath, whereas a
+// lane-id test makes every UTCHMMA / UTMALDG a "waterfall" loop (ELECT + R2UR + BRA.U.ANY) costing ~150 cycles per issue
+// (measured with tools/micro/mma_bench.cu: 152 cycles per tcgen05.mma for any N).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }

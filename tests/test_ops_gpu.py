@@ -127,6 +127,9 @@ CONV_CASES = [
     (8, 4, 256, 512, 3, 1, 1, False, "reflect"),    # 4x4 map, N tiles of 256
     (2, 16, 192, 24, 1, 1, 0, True, "reflect"),     # attention 1x1, N=24 (not a multiple of 16 -> SIMT)
     (2, 16, 192, 96, 1, 1, 0, True, "reflect"),
+    (1, 128, 96, 16, 3, 1, 1, False, "reflect"),    # 128-pixel rows: halo kernel (taps of one dy share an activation box)
+    (1, 128, 96, 96, 3, 1, 1, True, "zero"),        # halo kernel, zero padding through TMA OOB fill, 2 k-blocks
+    (1, 256, 16, 32, 3, 1, 1, False, "reflect"),    # two 128-pixel tiles per image row
 ]
 
 
