@@ -171,9 +171,12 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // Both issue loops are single dependent instruction streams: stage index / parity / shared-memory addresses advance
+  // incrementally (no runtime divisions), descriptor words by plain adds.
   if (warp == 0) {
     if (elect_one_sync()) {
-      int it = 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t s = 0, par = 1, sa = smem_base;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nt = tile % ntn; int t = tile / ntn;
         const int phase = t / tiles_pp; t -= phase * tiles_pp;
@@ -184,15 +187,15 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
         const int ntaps = p.ntaps[phase];
         for (int tp = 0; tp < ntaps; ++tp) {
           const TcTap tap = p.taps[phase][tp];
-          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t par = (uint32_t)((it / p.stages) & 1);
-            mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
-            const uint32_t fb = smem_u32(&full_bar[s]);
+          const CUtensorMap* am = &p.amap[tap.map];
+          const int cx = j0 + tap.dx, cy = i0 + tap.dy;
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(empty0 + s * 8u, par);
+            const uint32_t fb = full0 + s * 8u;
             mbar_expect_tx(fb, stage_bytes);
-            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-            tma_load_4d(sa, &p.amap[tap.map], fb, kb * 64, j0 + tap.dx, i0 + tap.dy, b0);
+            tma_load_4d(sa, am, fb, kb * 64, cx, cy, b0);
             tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
+            if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
           }
         }
       }
@@ -200,7 +203,11 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
   } else if (warp == 1) {
     if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
-      int it = 0, lt = 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base, 16), stage_q = stage_bytes >> 4;
+      const uint32_t dry = (uint32_t)p.dry;
+      uint32_t s = 0, par = 0, a_lo = a_lo0;
+      int lt = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
         const int phase = (tile / ntn) / tiles_pp;
         const int total = p.ntaps[phase] * p.nkb;
@@ -209,23 +216,22 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
         int kb = 0;
-        for (int li = 0; li < total; ++li, ++it) {
-          const int s = it % p.stages;
-          const uint32_t par = (uint32_t)((it / p.stages) & 1);
-          mbar_wait(smem_u32(&full_bar[s]), par);
+        uint32_t acc = 0u;
+        for (int li = 0; li < total; ++li) {
+          mbar_wait(full0 + s * 8u, par);
           tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
           const int nk = (kb == p.nkb - 1) ? p.ktail : 4;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < nk && !p.dry) {
-              const uint64_t ad = umma_desc_kmajor_sw128(sa + k * 32);
-              const uint64_t bd = umma_desc_kmajor_sw128(sa + 16384u + k * 32);
-              umma_bf16(tacc, ad, bd, idesc, (li | k) != 0 ? 1u : 0u);
-            }
+          if (!dry) {
+            const uint32_t b_lo = a_lo + 1024u;          // weight tile: 16 KB behind the activation tile
+            umma_bf16_w(tacc, a_lo, UMMA_DESC_HI_KMAJOR_SW128, b_lo, UMMA_DESC_HI_KMAJOR_SW128, idesc, acc);
+            acc = 1u;
+            if (nk > 1) umma_bf16_w(tacc, a_lo + 2u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 2u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+            if (nk > 2) umma_bf16_w(tacc, a_lo + 4u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 4u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+            if (nk > 3) umma_bf16_w(tacc, a_lo + 6u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 6u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
           }
-          umma_commit(smem_u32(&empty_bar[s]));
+          umma_commit(empty0 + s * 8u);
           if (++kb == p.nkb) kb = 0;
+          if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; a_lo = a_lo0; } else a_lo += stage_q;
         }
         umma_commit(smem_u32(&tfull_bar[buf]));
       }
@@ -276,7 +282,8 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_halo_kernel(const __grid_consta
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      int it = 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t s = 0, par = 1, sa = smem_base;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nt = tile % ntn; int t = tile / ntn;
         const int j0 = (t % p.tw) * p.bw; t /= p.tw;
@@ -285,16 +292,19 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_halo_kernel(const __grid_consta
         const int n0 = nt * p.BN;
         for (int g = 0; g < p.ngroups; ++g) {
           const TcGroup& grp = p.groups[g];
-          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t par = (uint32_t)((it / p.stages) & 1);
-            mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
-            const uint32_t fb = smem_u32(&full_bar[s]);
-            mbar_expect_tx(fb, abox_bytes + (uint32_t)grp.ntap * wbytes);
-            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-            tma_load_4d(sa, &p.amap[0], fb, kb * 64, j0 + grp.dx0, i0 + grp.dy, b0);
-            for (int j = 0; j < grp.ntap; ++j)
-              tma_load_3d(sa + TC_HALO_ABYTES + (uint32_t)j * wbytes, &p.bmap, fb, kb * 64, n0, grp.widx[j]);
+          const int ntap = grp.ntap, cx = j0 + grp.dx0, cy = i0 + grp.dy;
+          const int w0 = grp.widx[0], w1 = grp.widx[1], w2 = grp.widx[2];
+          const uint32_t tx = abox_bytes + (uint32_t)ntap * wbytes;
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(empty0 + s * 8u, par);
+            const uint32_t fb = full0 + s * 8u;
+            mbar_expect_tx(fb, tx);
+            tma_load_4d(sa, &p.amap[0], fb, kb * 64, cx, cy, b0);
+            const uint32_t sb = sa + TC_HALO_ABYTES;
+            tma_load_3d(sb, &p.bmap, fb, kb * 64, n0, w0);
+            if (ntap > 1) tma_load_3d(sb + wbytes, &p.bmap, fb, kb * 64, n0, w1);
+            if (ntap > 2) tma_load_3d(sb + 2u * wbytes, &p.bmap, fb, kb * 64, n0, w2);
+            if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
           }
         }
       }
@@ -302,35 +312,37 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_halo_kernel(const __grid_consta
   } else if (warp == 1) {
     if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
-      int it = 0, lt = 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base, 16), stage_q = stage_bytes >> 4, w_q = wbytes >> 4;
+      const uint32_t dry = (uint32_t)p.dry;
+      uint32_t s = 0, par = 0, a_lo = a_lo0;
+      int lt = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
-        uint32_t first = 0u;
+        uint32_t acc = 0u;
         for (int g = 0; g < p.ngroups; ++g) {
-          const TcGroup& grp = p.groups[g];
-          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t par = (uint32_t)((it / p.stages) & 1);
-            mbar_wait(smem_u32(&full_bar[s]), par);
+          const int ntap = p.groups[g].ntap;
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(full0 + s * 8u, par);
             tc_fence_after();
-            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
             const int nk = (kb == p.nkb - 1) ? p.ktail : 4;
-            for (int j = 0; j < grp.ntap; ++j) {
-              const uint32_t a0 = sa + (uint32_t)grp.dxo[j] * 128u;
-              const uint64_t abase_off = p.halo_bo ? ((uint64_t)(grp.dxo[j] & 7) << 49) : 0ull;   // matrix base offset: row phase of the swizzle
-              const uint32_t b0s = sa + TC_HALO_ABYTES + (uint32_t)j * wbytes;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < nk) {
-                  umma_bf16(tacc, umma_desc_kmajor_sw128(a0 + k * 32) | abase_off, umma_desc_kmajor_sw128(b0s + k * 32), idesc, first);
-                  first = 1u;
-                }
+            if (!dry) {
+              // tap j reads the activation box j pixel rows (j * 128 B = 8 descriptor units) further in; the UMMA swizzle
+              // is a function of the absolute shared-memory address, so no matrix-base-offset is needed (checked on B200)
+              uint32_t aj = a_lo, bj = a_lo + (TC_HALO_ABYTES >> 4);
+              for (int j = 0; j < ntap; ++j, aj += 8u, bj += w_q) {
+                umma_bf16_w(tacc, aj, UMMA_DESC_HI_KMAJOR_SW128, bj, UMMA_DESC_HI_KMAJOR_SW128, idesc, acc);
+                acc = 1u;
+                if (nk > 1) umma_bf16_w(tacc, aj + 2u, UMMA_DESC_HI_KMAJOR_SW128, bj + 2u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+                if (nk > 2) umma_bf16_w(tacc, aj + 4u, UMMA_DESC_HI_KMAJOR_SW128, bj + 4u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+                if (nk > 3) umma_bf16_w(tacc, aj + 6u, UMMA_DESC_HI_KMAJOR_SW128, bj + 6u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
               }
             }
-            umma_commit(smem_u32(&empty_bar[s]));
+            umma_commit(empty0 + s * 8u);
+            if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; a_lo = a_lo0; } else a_lo += stage_q;
           }
         }
         umma_commit(smem_u32(&tfull_bar[buf]));
@@ -628,39 +640,48 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 
   if (warp == 0) {
     if (elect_one_sync()) {
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const CUtensorMap* am = &p.amap[tap.map];
+      // box coordinates advance incrementally (the issue thread is a single dependent instruction stream)
+      int t = box_beg;
+      int j0 = (t % p.tw) * p.bw; t /= p.tw;
+      int i0 = (t % p.th) * p.bh; t /= p.th;
+      int b0 = t * p.bb;
+      const int jend = p.tw * p.bw, iend = p.th * p.bh;
+      uint32_t s = 0, par = 1, sa = smem_base;
       for (int it = 0; it < total; ++it) {
-        int t = box_beg + it;
-        const int j0 = (t % p.tw) * p.bw; t /= p.tw;
-        const int i0 = (t % p.th) * p.bh; t /= p.th;
-        const int b0 = t * p.bb;
-        const int s = it % p.stages;
-        const uint32_t par = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(smem_u32(&empty_bar[s]), par ^ 1u);
-        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_wait(empty0 + s * 8u, par);
+        const uint32_t fb = full0 + s * 8u;
         mbar_expect_tx(fb, stage_bytes);
-        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-        tma_load_4d(sa, &p.amap[tap.map], fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
-        tma_load_4d(sa + 8192u, &p.amap[tap.map], fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
+        tma_load_4d(sa, am, fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
+        tma_load_4d(sa + 8192u, am, fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
         for (int nb = 0; nb < p.nblkB; ++nb)
           tma_load_4d(sa + 16384u + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
+        j0 += p.bw;
+        if (j0 >= jend) { j0 = 0; i0 += p.bh; if (i0 >= iend) { i0 = 0; b0 += p.bb; } }
+        if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
       }
     }
   } else if (warp == 1) {
     if (elect_one_sync()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      // MN-major SWIZZLE_128B operands: LBO = 8192 (next 64-channel block), SBO = 1024 (next 8 pixels); one MMA covers
+      // 16 pixels = 2048 B = 128 descriptor units
+      const uint32_t a_lo0 = umma_desc_lo(smem_base, 8192), stage_q = stage_bytes >> 4;
+      const uint32_t hi = umma_desc_hi_mnmajor_sw128(1024);
+      uint32_t s = 0, par = 0, a_lo = a_lo0, acc = 0u;
       for (int it = 0; it < total; ++it) {
-        const int s = it % p.stages;
-        const uint32_t par = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(smem_u32(&full_bar[s]), par);
+        mbar_wait(full0 + s * 8u, par);
         tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {     // 16 pixels (2 swizzle atoms of 8 rows) per MMA
-          const uint64_t ad = umma_desc_mnmajor_sw128(sa + k * 2048, 8192, 1024);
-          const uint64_t bd = umma_desc_mnmajor_sw128(sa + 16384u + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&empty_bar[s]));
+        const uint32_t b_lo = a_lo + 1024u;
+        umma_bf16_w(tmem_base, a_lo, hi, b_lo, hi, idesc, acc);
+        acc = 1u;
+        umma_bf16_w(tmem_base, a_lo + 128u, hi, b_lo + 128u, hi, idesc, 1u);
+        umma_bf16_w(tmem_base, a_lo + 256u, hi, b_lo + 256u, hi, idesc, 1u);
+        umma_bf16_w(tmem_base, a_lo + 384u, hi, b_lo + 384u, hi, idesc, 1u);
+        umma_commit(empty0 + s * 8u);
+        if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; a_lo = a_lo0; } else a_lo += stage_q;
       }
       umma_commit(smem_u32(&accum_bar));
     }

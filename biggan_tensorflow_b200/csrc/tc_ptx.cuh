@@ -82,6 +82,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Lean issue path: the issuing thread is a single dependent instruction stream (~4-5 cycles per instruction), so the
+// per-MMA bookkeeping must be a couple of 32-bit adds.  Descriptors are kept as a constant high word plus a low word
+// (start address >> 4 | LBO field) that advances by plain additions (no carry out of the 14-bit address field for any
+// address below 256 KB).
+#define UMMA_DESC_HI_KMAJOR_SW128 (64u | (1u << 14) | (2u << 29))          // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi_mnmajor_sw128(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 32 lanes x 16 consecutive fp32 columns: thread i gets row (lane base + i)
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
   asm volatile(

@@ -6,11 +6,6 @@
 #include <cuda_runtime.h>
 #include "tc_ptx.cuh"
 
-__device__ __forceinline__ uint32_t elect_one_sync() {
-  uint32_t pred = 0;
-  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.b32 %0, 1, 0, P1;\n}" : "=r"(pred));
-  return pred;
-}
 template <int mode>
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int nacc, int mnmajor, long long* out) {
   extern __shared__ uint8_t smem_raw[];
