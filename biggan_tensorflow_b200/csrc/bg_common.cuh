@@ -118,6 +118,12 @@ __device__ __forceinline__ double bg_block_sum_d(double v, double* sh /* >= 33 d
   return sh[32];
 }
 
+__device__ __forceinline__ float bg_apply_act(float v, int act) {
+  if (act == BG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == BG_ACT_TANH) return tanhf(v);
+  return v;
+}
+
 // 16-byte vector access: 4 floats or 8 bf16 per thread (n % VEC == 0 and 16-byte aligned base required)
 template <typename T> struct Vec;
 template <> struct Vec<float> {

@@ -7,12 +7,6 @@
 #define GF_BN 64
 #define GF_BK 16
 
-__device__ __forceinline__ float bg_apply_act(float v, int act) {
-  if (act == BG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == BG_ACT_TANH) return tanhf(v);
-  return v;
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward-type: out[b, oy, ox, n] = act( sum_t sum_k in[b, iy_t, ix_t, k] * w[t, k, n] + bias + res )
 // ------------------------------------------------------------------------------------------------
@@ -454,6 +448,13 @@ static int launch_fwd_type(const BgGeom& g, const T* in, const T* w, const float
   return BG_OK;
 }
 
+// fc.cu
+int bg_fc_fwd(const float* x, const float* w, const float* bias, float* y, int M, int K, int N, int act, cudaStream_t st);
+int bg_fc_wgrad(const float* x, const float* dy, float* dw, int M, int K, int N, cudaStream_t st);
+static inline bool fc_shape(const bg_conv_desc* d) {
+  return !d->transposed && d->Hi == 1 && d->Wi == 1 && d->Ho == 1 && d->Wo == 1 && d->kh == 1 && d->kw == 1;
+}
+
 extern "C" size_t bg_conv2d_fwd_workspace_bytes(const bg_conv_desc* d, int dtype) {
   if (dtype == BG_BF16 && reflect_padded(d)) return padded_bytes(d, 2);
   BgGeom g;
@@ -488,6 +489,9 @@ extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w
       }
     }
   }
+  // fully_connected: dedicated skinny-GEMM kernel (fc.cu) when its grid fills the GPU and the (serial) contraction is short
+  if (dtype == BG_F32 && fc_shape(d) && !residual && d->Co >= 64 && d->Ci <= 512 && bg_cdiv(d->Co, 128) * bg_cdiv(d->B, 16) >= 48)
+    return bg_fc_fwd((const float*)x, (const float*)w, bias, (float*)y, d->B, d->Ci, d->Co, act, st);
   BG_DISPATCH_DTYPE(dtype, T, return launch_fwd_type<T>(g, (const T*)x, (const T*)w, bias, (const T*)residual, (T*)y, act, st, ws, ws_bytes));
 }
 
@@ -588,6 +592,8 @@ extern "C" int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x, const void*
     if (taken) return BG_OK;
   }
   const long numel = wgrad_numel(d);
+  if (dtype == BG_F32 && fc_shape(d) && d->Co >= 64 && d->B <= 512 && bg_cdiv(d->Co, 128) * bg_cdiv(d->Ci, 16) >= 48)
+    return bg_fc_wgrad((const float*)x, (const float*)dy, dw, d->B, d->Ci, d->Co, st);
   if (g.Co <= 4 || g.Ci <= 4) {
     int taken = 0;
     rc = bg_small_wgrad(g, in, og, dw, numel, dtype, ws, ws_bytes, st, &taken);

@@ -608,7 +608,9 @@ struct TcWgParams {
   long zstride, wtap, wk;
 };
 
-template <int TMEM_COLS>
+// TPC taps per CTA: they share every Og (B operand) stage -- the shared tile is loaded once instead of once per tap, which
+// is what bounds the C <= 192 layers (L2 -> SM ingest) -- and each tap owns BN accumulator columns of TMEM.
+template <int TMEM_COLS, int TPC>
 __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant__ TcWgParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
@@ -618,9 +620,11 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = 16384u + (uint32_t)p.nblkB * 8192u;
+  constexpr uint32_t B_OFF = (uint32_t)TPC * 16384u;                  // stage layout: [A tap 0][A tap 1]...[B]
+  const uint32_t stage_bytes = B_OFF + (uint32_t)p.nblkB * 8192u;
   const int m0 = (blockIdx.x / p.ntile_n) * 128, n0 = (blockIdx.x % p.ntile_n) * p.BN;
-  const TcTap tap = p.taps[blockIdx.y];
+  const int tap0 = blockIdx.y * TPC;
+  const int nt = min(TPC, p.ntaps - tap0);                             // taps handled by this CTA
   const int box_beg = (int)(((long)blockIdx.z * p.nboxes) / p.nsplit);
   const int box_end = (int)(((long)(blockIdx.z + 1) * p.nboxes) / p.nsplit);
   const int total = box_end - box_beg;
@@ -641,7 +645,14 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
   if (warp == 0) {
     if (elect_one_sync()) {
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-      const CUtensorMap* am = &p.amap[tap.map];
+      const CUtensorMap* am[TPC];
+      int tdx[TPC], tdy[TPC];
+#pragma unroll
+      for (int t2 = 0; t2 < TPC; ++t2) {
+        const TcTap tp = p.taps[min(tap0 + t2, p.ntaps - 1)];
+        am[t2] = &p.amap[tp.map]; tdx[t2] = tp.dx; tdy[t2] = tp.dy;
+      }
+      const uint32_t tx = (uint32_t)nt * 16384u + (uint32_t)p.nblkB * 8192u;
       // box coordinates advance incrementally (the issue thread is a single dependent instruction stream)
       int t = box_beg;
       int j0 = (t % p.tw) * p.bw; t /= p.tw;
@@ -652,11 +663,15 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
       for (int it = 0; it < total; ++it) {
         mbar_wait(empty0 + s * 8u, par);
         const uint32_t fb = full0 + s * 8u;
-        mbar_expect_tx(fb, stage_bytes);
-        tma_load_4d(sa, am, fb, m0, j0 + tap.dx, i0 + tap.dy, b0);
-        tma_load_4d(sa + 8192u, am, fb, m0 + 64, j0 + tap.dx, i0 + tap.dy, b0);
+        mbar_expect_tx(fb, tx);
+#pragma unroll
+        for (int t2 = 0; t2 < TPC; ++t2)
+          if (t2 < nt) {
+            tma_load_4d(sa + (uint32_t)t2 * 16384u, am[t2], fb, m0, j0 + tdx[t2], i0 + tdy[t2], b0);
+            tma_load_4d(sa + (uint32_t)t2 * 16384u + 8192u, am[t2], fb, m0 + 64, j0 + tdx[t2], i0 + tdy[t2], b0);
+          }
         for (int nb = 0; nb < p.nblkB; ++nb)
-          tma_load_4d(sa + 16384u + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
+          tma_load_4d(sa + B_OFF + (uint32_t)nb * 8192u, &p.bmap, fb, n0 + nb * 64, j0, i0, b0);
         j0 += p.bw;
         if (j0 >= jend) { j0 = 0; i0 += p.bh; if (i0 >= iend) { i0 = 0; b0 += p.bb; } }
         if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
@@ -670,16 +685,21 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
       // 16 pixels = 2048 B = 128 descriptor units
       const uint32_t a_lo0 = umma_desc_lo(smem_base, 8192), stage_q = stage_bytes >> 4;
       const uint32_t hi = umma_desc_hi_mnmajor_sw128(1024);
+      const uint32_t bn = (uint32_t)p.BN;
       uint32_t s = 0, par = 0, a_lo = a_lo0, acc = 0u;
       for (int it = 0; it < total; ++it) {
         mbar_wait(full0 + s * 8u, par);
         tc_fence_after();
-        const uint32_t b_lo = a_lo + 1024u;
-        umma_bf16_w(tmem_base, a_lo, hi, b_lo, hi, idesc, acc);
+        const uint32_t b_lo = a_lo + (B_OFF >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int t2 = 0; t2 < TPC; ++t2)
+            if (t2 < nt)
+              umma_bf16_w(tmem_base + (uint32_t)t2 * bn, a_lo + (uint32_t)t2 * 1024u + (uint32_t)k * 128u, hi, b_lo + (uint32_t)k * 128u, hi,
+                          idesc, k == 0 ? acc : 1u);
+        }
         acc = 1u;
-        umma_bf16_w(tmem_base, a_lo + 128u, hi, b_lo + 128u, hi, idesc, 1u);
-        umma_bf16_w(tmem_base, a_lo + 256u, hi, b_lo + 256u, hi, idesc, 1u);
-        umma_bf16_w(tmem_base, a_lo + 384u, hi, b_lo + 384u, hi, idesc, 1u);
         umma_commit(empty0 + s * 8u);
         if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; a_lo = a_lo0; } else a_lo += stage_q;
       }
@@ -688,24 +708,28 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
   } else {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
-    float* dst = p.part + (long)blockIdx.z * p.zstride + (long)tap.widx * p.wtap + (long)m * p.wk + n0;
     if (total > 0) {
       mbar_wait(smem_u32(&accum_bar), 0);
       tc_fence_after();
     }
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t r[16];
-      if (total > 0) tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = 0u;
-      }
-      if (m < p.Ci) {
-        float4* o = reinterpret_cast<float4*>(dst + c0);
+    for (int t2 = 0; t2 < TPC; ++t2) {
+      if (t2 >= nt) break;
+      float* dst = p.part + (long)blockIdx.z * p.zstride + (long)p.taps[tap0 + t2].widx * p.wtap + (long)m * p.wk + n0;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        if (total > 0) tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t2 * p.BN + c0), r);
+        else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
-                             __uint_as_float(r[4 * e + 3]));
+          for (int e = 0; e < 16; ++e) r[e] = 0u;
+        }
+        if (m < p.Ci) {
+          float4* o = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                               __uint_as_float(r[4 * e + 3]));
+        }
       }
     }
   }
@@ -725,13 +749,13 @@ extern "C" int bg_debug_counters(int* tc_fwd, int* tc_wgrad) {
 // t_box: one 64-pixel stage at this CTA's share of the L2->SM bandwidth (~80 B/ns per SM); t_fixed: prologue, pipeline
 // fill and the fp32 accumulator drain at the SM's share of HBM write bandwidth; t_reduce: the split-K reduction pass
 // (absent for ns == 1).  297 CTAs on 296 slots cost two waves; splitting a 1536x1536 layer costs more than it buys.
-static int wg_nsplit(int tiles, int nboxes, int ctas_per_sm, int BN, long numel) {
+static int wg_nsplit(int tiles, int nboxes, int ctas_per_sm, int BN, int TPC, long numel) {
   const long slots = (long)bg_num_sms() * ctas_per_sm;
   long mx = nboxes / 4;
   if (mx > 64) mx = 64;
   if (mx < 1) mx = 1;
-  const double t_box = (16384.0 + ((BN + 63) / 64) * 8192.0) / (80e3 / ctas_per_sm);       // us
-  const double t_fixed = 2.0 + 128.0 * BN * 4.0 / (43e3 / ctas_per_sm);                      // us
+  const double t_box = (TPC * 16384.0 + ((BN + 63) / 64) * 8192.0) / (80e3 / ctas_per_sm);       // us
+  const double t_fixed = 2.0 + TPC * 128.0 * BN * 4.0 / (43e3 / ctas_per_sm);                      // us
   long best = 1;
   double best_cost = 1e30;
   for (long ns = 1; ns <= mx; ++ns) {
@@ -742,7 +766,7 @@ static int wg_nsplit(int tiles, int nboxes, int ctas_per_sm, int BN, long numel)
   return (int)best;
 }
 
-struct WgPlan { int ok, BN, bw, bh, bb, tw, th, tb, nboxes, tiles, nsplit; };
+struct WgPlan { int ok, BN, bw, bh, bb, tw, th, tb, nboxes, tiles, nsplit, TPC, stages; };
 
 static WgPlan wg_plan(const BgGeom& g) {
   WgPlan pl;
@@ -757,8 +781,33 @@ static WgPlan wg_plan(const BgGeom& g) {
   choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 64, &pl.bw, &pl.bh, &pl.bb);
   pl.tw = (int)bg_cdiv(g.ph[0].Wp, pl.bw); pl.th = (int)bg_cdiv(g.ph[0].Hp, pl.bh); pl.tb = (int)bg_cdiv(g.B, pl.bb);
   pl.nboxes = pl.tw * pl.th * pl.tb;
-  pl.tiles = (int)(bg_cdiv(g.Ci, 128) * (g.Co / pl.BN) * g.ph[0].ntaps);
-  pl.nsplit = wg_nsplit(pl.tiles, pl.nboxes, (16384 + ((pl.BN + 63) / 64) * 8192 <= 32 * 1024) ? 2 : 1, pl.BN,
+  // taps per CTA (TPC): sharing the Og stage pays when the layer is ingest-bound, i.e. when one stage's MMAs
+  // (4 x max(64, BN/2) cycles per tap) take less time than loading it (~48 B/clk/SM); needs TPC*BN <= 512 TMEM columns
+  // and at least two stages of shared memory
+  {
+    const int nt = g.ph[0].ntaps, nblk = (pl.BN + 63) / 64;
+    static int tpc_env = -1;
+    if (tpc_env < 0) { const char* e = getenv("BG_WGRAD_TPC"); tpc_env = e ? atoi(e) : 4; }
+    int best = 1;
+    for (int t = 2; t <= tpc_env && t <= 4; ++t) {
+      if (t * pl.BN > 512 || t > nt) continue;
+      if (2 * (t * 16384 + nblk * 8192) > 200 * 1024) continue;
+      const double mma_cyc = 4.0 * (pl.BN / 2 > 64 ? pl.BN / 2 : 64), load_cyc = (16384.0 + nblk * 8192.0) / 48.0;
+      if (mma_cyc >= load_cyc) continue;                       // tensor-pipe bound already
+      const int idle_t = (int)bg_cdiv(nt, t) * t - nt, idle_b = (int)bg_cdiv(nt, best) * best - nt;
+      if (best == 1 || idle_t <= idle_b) best = t;             // least idle accumulator slots, prefer larger
+    }
+    pl.TPC = best;
+  }
+  {
+    const int stage_bytes = pl.TPC * 16384 + ((pl.BN + 63) / 64) * 8192;
+    int stages = (stage_bytes <= 32 * 1024) ? 3 : 4;            // 2 CTAs per SM for the small tiles
+    if ((size_t)stages * stage_bytes > 200 * 1024) stages = (200 * 1024) / stage_bytes;
+    if (stages < 2) stages = 2;
+    pl.stages = stages;
+  }
+  pl.tiles = (int)(bg_cdiv(g.Ci, 128) * (g.Co / pl.BN) * bg_cdiv(g.ph[0].ntaps, pl.TPC));
+  pl.nsplit = wg_nsplit(pl.tiles, pl.nboxes, (pl.stages * (pl.TPC * 16384 + ((pl.BN + 63) / 64) * 8192) <= 100 * 1024) ? 2 : 1, pl.BN, pl.TPC,
                         (long)g.ph[0].ntaps * g.Ci * g.Co);
   pl.ok = 1;
   return pl;
@@ -814,8 +863,8 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
   P.bw = pl.bw; P.bh = pl.bh; P.bb = pl.bb; P.tw = pl.tw; P.th = pl.th; P.tb = pl.tb;
   P.Ci = g.Ci; P.Co = g.Co; P.BN = pl.BN; P.nblkB = (pl.BN + 63) / 64;
   P.ntile_n = g.Co / pl.BN; P.nsplit = pl.nsplit; P.nboxes = pl.nboxes;
-  const int stage_bytes = 16384 + P.nblkB * 8192;
-  int stages = (stage_bytes <= 32 * 1024) ? 3 : 4;     // 2 CTAs per SM for the small tiles
+  const int stage_bytes = pl.TPC * 16384 + P.nblkB * 8192;
+  const int stages = pl.stages;
   P.stages = stages;
   P.ntaps = g.ph[0].ntaps;
   for (int t = 0; t < P.ntaps; ++t) {
@@ -829,20 +878,30 @@ int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, con
   P.part = pl.nsplit > 1 ? (float*)wsp : dw;
   P.zstride = numel; P.wtap = g.wtap; P.wk = g.wk;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  dim3 grid((unsigned)(bg_cdiv(g.Ci, 128) * P.ntile_n), (unsigned)P.ntaps, (unsigned)pl.nsplit);
-#define TC_LAUNCH_WG(COLS)                                                                                       \
+  dim3 grid((unsigned)(bg_cdiv(g.Ci, 128) * P.ntile_n), (unsigned)bg_cdiv(P.ntaps, pl.TPC), (unsigned)pl.nsplit);
+#define TC_LAUNCH_WG(COLS, T)                                                                                    \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
     if (!attr_set) {                                                                                             \
-      BG_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+      BG_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<COLS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    tc_wgrad_kernel<COLS><<<grid, 192, smem, st>>>(P);                                                           \
+    tc_wgrad_kernel<COLS, T><<<grid, 192, smem, st>>>(P);                                                        \
   } while (0)
-  if (pl.BN <= 32) TC_LAUNCH_WG(32);
-  else if (pl.BN <= 64) TC_LAUNCH_WG(64);
-  else if (pl.BN <= 128) TC_LAUNCH_WG(128);
-  else TC_LAUNCH_WG(256);
+#define TC_LAUNCH_WG_T(T)                                                                                        \
+  do {                                                                                                           \
+    const int wcols = T * pl.BN;                                                                                 \
+    if (wcols <= 32) TC_LAUNCH_WG(32, T);                                                                        \
+    else if (wcols <= 64) TC_LAUNCH_WG(64, T);                                                                   \
+    else if (wcols <= 128) TC_LAUNCH_WG(128, T);                                                                 \
+    else if (wcols <= 256) TC_LAUNCH_WG(256, T);                                                                 \
+    else TC_LAUNCH_WG(512, T);                                                                                   \
+  } while (0)
+  if (pl.TPC == 1) TC_LAUNCH_WG_T(1);
+  else if (pl.TPC == 2) TC_LAUNCH_WG_T(2);
+  else if (pl.TPC == 3) TC_LAUNCH_WG_T(3);
+  else TC_LAUNCH_WG_T(4);
+#undef TC_LAUNCH_WG_T
 #undef TC_LAUNCH_WG
   BG_LAUNCH_CHECK();
   if (pl.nsplit > 1) {

@@ -165,15 +165,17 @@ def test_deconv(case, dtype):
 
 
 @pytest.mark.parametrize("sn", [True, False])
-def test_fully_connected(sn):
-    """ops.py:148-175 (SN path and tf.layers.dense path)."""
+@pytest.mark.parametrize("B,K,units", [(6, 52, 40), (6, 52, 200), (256, 148, 1536), (250, 300, 900), (3, 148, 96)])
+def test_fully_connected(B, K, units, sn):
+    """ops.py:148-175 (SN path and tf.layers.dense path); the two large cases take the dedicated skinny-GEMM kernel
+    (fc.cu): ragged row / column blocks, contraction longer than one shared-memory chunk."""
     from biggan_tensorflow_b200 import ops
     po, ro = _opt()
     po["conv"]["sn"] = sn
     ro["conv"]["sn"] = sn
-    x = np.random.default_rng(2).standard_normal((6, 1, 1, 52)).astype(np.float32)
-    run_case(lambda xs: ops.fully_connected(xs["x"], 40, po, scope="fc"),
-             lambda rs, xs: R.fully_connected(rs, xs["x"], 40, ro, scope="fc"),
+    x = np.random.default_rng(2).standard_normal((B, 1, 1, K)).astype(np.float32)
+    run_case(lambda xs: ops.fully_connected(xs["x"], units, po, scope="fc"),
+             lambda rs, xs: R.fully_connected(rs, xs["x"], units, ro, scope="fc"),
              {"x": x}, torch.float32)
 
 
