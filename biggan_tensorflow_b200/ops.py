@@ -204,9 +204,20 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
                requires_grad=x.requires_grad or wn.requires_grad or (bias is not None and bias.requires_grad)
                or (residual is not None and residual.requires_grad))
     w_t = wn.aux.get("w_t") if wn.aux else None
-    nbf = query("bg_conv2d_fwd_workspace_bytes", desc, dt)
+    # bf16 mode, reflect padding: pad ONCE into a tensor that lives until the backward pass; forward and weight gradient
+    # then run as plain (pad-free) convs on it instead of each re-padding x into transient workspace
+    xin, desc_f = x.data, desc
+    if (x.dtype == BF16 and not desc.transposed and desc.pad_mode == _lib.PAD_REFLECT
+            and (desc.pad_t | desc.pad_l | desc.pad_b | desc.pad_r)):
+        Hp, Wp = desc.Hi + desc.pad_t + desc.pad_b, desc.Wi + desc.pad_l + desc.pad_r
+        xin = empty([desc.B, Hp, Wp, desc.Ci], x.dtype)
+        call("bg_reflect_pad", x.data, xin, desc.B, desc.Hi, desc.Wi, desc.Ci, desc.pad_t, desc.pad_l, desc.pad_b, desc.pad_r, dt,
+             stream(), tag="reflect_pad")
+        desc_f = ConvDesc(desc.B, Hp, Wp, desc.Ci, desc.Ho, desc.Wo, desc.Co, desc.kh, desc.kw, desc.stride, 0, 0, 0, 0,
+                          _lib.PAD_ZERO, 0)
+    nbf = query("bg_conv2d_fwd_workspace_bytes", desc_f, dt)
     wsf = workspace(nbf) if nbf else None
-    call("bg_conv2d_fwd", desc, x.data, wn.data, w_t, bias.data if bias is not None else None,
+    call("bg_conv2d_fwd", desc_f, xin, wn.data, w_t, bias.data if bias is not None else None,
          residual.data if residual is not None else None, y.data, act, dt, wsf, wsf.numel() if nbf else 0, fs, stream(),
          flops=_conv_flops(desc), tag="conv_fwd" + _conv_tag(desc))
     if recording(x, wn, bias, residual):
@@ -226,9 +237,9 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
                 accumulate_grad(residual, dy, own=False)
             if wn.requires_grad:
                 dst, fin = grad_target(wn, dtype=F32)          # weight gradients are fp32 in every mode
-                nb = query("bg_conv2d_wgrad_workspace_bytes", desc, dt)
+                nb = query("bg_conv2d_wgrad_workspace_bytes", desc_f, dt)
                 ws = workspace(nb)
-                call("bg_conv2d_wgrad", desc, x.data, dy, dst, dt, ws, ws.numel(), fs, stream(),
+                call("bg_conv2d_wgrad", desc_f, xin, dy, dst, dt, ws, ws.numel(), fs, stream(),
                      flops=_conv_flops(desc), tag="conv_wgrad" + _conv_tag(desc))
                 if fin:
                     fin()
@@ -427,18 +438,24 @@ def hw_flatten(x):
 
 
 def fully_connected(x, units, opt, use_bias=True, lrmul=1.0, scope='fully_0'):
-    """ops.py:148-175.  Always fp32 (M = batch rows only)."""
+    """ops.py:148-175.  fp32 in parity mode.  In bf16 tensor-core mode the spectrally normalised projections whose shapes
+    fit the tcgen05 kernels (in-features % 8 == 0, units % 16 == 0: the conditional-BatchNorm gamma/beta projections
+    [1040 -> C] and dense2) run as 1x1 convs over the batch rows, bf16 operands / fp32 accumulate, result cast back to
+    fp32; everything else (z -> dense1, the logits) stays fp32."""
     with variable_scope(scope):
         x = flatten(x)
-        x = cast(x, F32)
         Bn, channels = x.shape
         desc = ConvDesc(Bn, 1, 1, channels, 1, 1, units, 1, 1, 1, 0, 0, 0, 0, _lib.PAD_ZERO, 0)
         bias = None
-        if opt.get("conv", {}).get("sn", True):
+        sn = opt.get("conv", {}).get("sn", True)
+        tc = (sn and _state["compute_dtype"] == BF16 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1
+              and channels % 8 == 0 and channels >= 16 and units % 16 == 0)
+        x = cast(x, BF16 if tc else F32)
+        if sn:
             w = get_variable_with_custom_lr("kernel", shape=[channels, units], regularizer=None, lrmul=lrmul)
             if use_bias:
                 bias = get_variable("bias", [units], initializer=constant_initializer(0.0))
-            wn = spectral_norm(w, _out_dtype=F32)
+            wn = _sn_weight(w, 1, True, BF16) if tc else spectral_norm(w, _out_dtype=F32)
         else:
             with variable_scope("dense"):                                      # tf.layers.dense (:167-173)
                 wn = get_variable("kernel", shape=[channels, units], initializer=weight_init)
@@ -446,7 +463,7 @@ def fully_connected(x, units, opt, use_bias=True, lrmul=1.0, scope='fully_0'):
                     bias = get_variable("bias", [units], initializer=constant_initializer(0.0))
         x4 = reshape(x, [Bn, 1, 1, channels])
         y = _conv_op(x4, wn, bias, desc)
-        return reshape(y, [Bn, units])
+        return cast(reshape(y, [Bn, units]), F32)
 
 
 ##################################################################################

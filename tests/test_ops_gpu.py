@@ -277,7 +277,8 @@ def test_resblock_up_condition(dtype):
     z = rng.standard_normal((2, 1, 1, 24)).astype(np.float32)
     run_case(lambda xs: ops.resblock_up_condition(xs["x"], xs["z"], 32, po, use_bias=False, scope="resblock_up_4"),
              lambda rs, xs: R.resblock_up_condition(rs, xs["x"], xs["z"], 32, ro, use_bias=False, scope="resblock_up_4"),
-             {"x": x, "z": z}, dtype, fp32_inputs=("z",), tol_scale=4.0)
+             {"x": x, "z": z}, dtype, fp32_inputs=("z",), tol_scale=4.0 if dtype == torch.float32 else 7.5)   # bf16: see
+    # tests/test_bf16_conditioning.py::test_bf16_projection_rounding_moves_the_small_resblock_case
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
