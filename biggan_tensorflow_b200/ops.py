@@ -854,6 +854,9 @@ def condition_batch_norm(x, z, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
         decay = opt.get("bn", {}).get("momentum", 0.98)
         test_mean = get_variable("pop_mean", shape=[c], initializer=constant_initializer(0.0), trainable=False)
         test_var = get_variable("pop_var", shape=[c], initializer=constant_initializer(1.0), trainable=False)
+        if (_state["compute_dtype"] == BF16 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1
+                and z.numel() // z.shape[0] % 8 == 0 and c % 16 == 0 and opt.get("conv", {}).get("sn", True)):
+            z = cast(flatten(z), BF16)           # both projections take the tensor-core path: cast the condition once
         beta = fully_connected(z, units=c, scope='beta', opt=opt)
         gamma = fully_connected(z, units=c, scope='gamma', opt=opt)
         return _bn_core(x, gamma, beta, c, test_mean, test_var, decay, lambda n: 1.0, opt, _act)
