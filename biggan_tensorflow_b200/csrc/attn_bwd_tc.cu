@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
     for (int i = 0; i < p.nqt; ++i) {
       const int qi = i * AB_T + row;
       const bool qv = qi < p.Nq;
-      const float lse = qv ? p.lse[(long)b * p.Nq + qi] : 0.f;
+      const float nlL = qv ? -p.lse[(long)b * p.Nq + qi] * LOG2E : -INFINITY;      // exp2(s*log2e - lse*log2e); 0 for rows past Nq
       const float dl = qv ? p.delta[(long)b * p.Nq + qi] : 0.f;
+      const bool kmask = (j + 1) * AB_T > p.Nk;                                     // partial last key block (block-uniform)
       mbar_wait(smem_u32(&s_full), (uint32_t)(i & 1));
       tc_fence_after();
       mbar_wait(smem_u32(&pds_empty), (uint32_t)((i & 1) ^ 1));
@@ -152,8 +153,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
           float pv[2], dv2[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int key = j * AB_T + c0 + 2 * e + h;
-            const float pr = (qv && key < p.Nk) ? exp2f((__uint_as_float(rs[2 * e + h]) - lse) * LOG2E) : 0.f;
+            float pr = fast_exp2(fmaf(__uint_as_float(rs[2 * e + h]), LOG2E, nlL));     // nlL = -inf for rows past Nq
+            if (kmask && j * AB_T + c0 + 2 * e + h >= p.Nk) pr = 0.f;
             pv[h] = pr;
             dv2[h] = pr * (__uint_as_float(rp[2 * e + h]) - dl);
           }
@@ -267,9 +268,10 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dq_kernel(const __grid_consta
     const float LOG2E = 1.4426950408889634f;
     const int qi = i * AB_T + row;
     const bool qv = qi < p.Nq;
-    const float lse = qv ? p.lse[(long)b * p.Nq + qi] : 0.f;
+    const float nlL = qv ? -p.lse[(long)b * p.Nq + qi] * LOG2E : -INFINITY;
     const float dl = qv ? p.delta[(long)b * p.Nq + qi] : 0.f;
     for (int j = 0; j < p.nkb; ++j) {
+      const bool kmask = (j + 1) * AB_T > p.Nk;
       mbar_wait(smem_u32(&s_full), (uint32_t)(j & 1));
       tc_fence_after();
       mbar_wait(smem_u32(&ds_empty), (uint32_t)((j & 1) ^ 1));
@@ -283,8 +285,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dq_kernel(const __grid_consta
           float d2[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int key = j * AB_T + c0 + 2 * e + h;
-            const float pr = (qv && key < p.Nk) ? exp2f((__uint_as_float(rs[2 * e + h]) - lse) * LOG2E) : 0.f;
+            float pr = fast_exp2(fmaf(__uint_as_float(rs[2 * e + h]), LOG2E, nlL));     // nlL = -inf for rows past Nq
+            if (kmask && j * AB_T + c0 + 2 * e + h >= p.Nk) pr = 0.f;
             d2[h] = pr * (__uint_as_float(rp[2 * e + h]) - dl);
           }
           __nv_bfloat162 hd = __floats2bfloat162_rn(d2[0], d2[1]);

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
-    float m = -INFINITY, sum = 0.f, sum_true = 0.f;
+    float m = -INFINITY, sum_true = 0.f;
     for (int it = 0; it < T; ++it) {
       const int j = it % p.nkb;
       const bool pass2 = it >= p.nkb;
@@ -121,15 +121,19 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
       mbar_wait(smem_u32(&s_full), (uint32_t)(it & 1));
       tc_fence_after();
       if (pass2) mbar_wait(smem_u32(&p_empty), (uint32_t)(((it - p.nkb) & 1) ^ 1));
+      const bool kmask = (j + 1) * AT_KB > p.Nk;       // only the last key block can be partial (block-uniform)
+      const float mL = m * LOG2E;
       for (int cc = 0; cc < 64; cc += 16) {
         const int c0 = half * 64 + cc;
         uint32_t r[16];
         tmem_ld_x16(tS + lane_base + (uint32_t)c0, r);
         float v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          v[e] = __uint_as_float(r[e]);
-          if (j * AT_KB + c0 + e >= p.Nk) v[e] = -INFINITY;
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+        if (kmask) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (j * AT_KB + c0 + e >= p.Nk) v[e] = -INFINITY;
         }
         if (!pass2) {
 #pragma unroll
@@ -138,10 +142,9 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
           uint32_t pk[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float p0 = exp2f((v[2 * e] - m) * LOG2E), p1 = exp2f((v[2 * e + 1] - m) * LOG2E);
+            const float p0 = fast_exp2(fmaf(v[2 * e], LOG2E, -mL)), p1 = fast_exp2(fmaf(v[2 * e + 1], LOG2E, -mL));
             __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-            sum += __low2float(h) + __high2float(h);       // normalise O by what the MMA actually sees
-            sum_true += p0 + p1;                            // exact normaliser for the saved log-sum-exp
+            sum_true += p0 + p1;      // fp32 normaliser (the bf16 rounding of P is unbiased noise, as in flash attention)
             pk[e] = *reinterpret_cast<uint32_t*>(&h);
           }
           // P[row][c0..c0+15] -> K-major SWIZZLE_128B tile(s): 16-byte chunk index XOR (row & 7)
@@ -161,15 +164,13 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
       }
     }
     // combine the halves' row sums
-    xch[0][half][row] = sum;
     xch[1][half][row] = sum_true;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    sum = xch[0][0][row] + xch[0][1][row];
     sum_true = xch[1][0][row] + xch[1][1][row];
     mbar_wait(smem_u32(&o_full), 0);
     tc_fence_after();
     const int qi = q0 + row;
-    const float inv = 1.f / sum;
+    const float inv = 1.f / sum_true;
     const int csplit = ((p.dv / 16 + 1) / 2) * 16;
     const int cbeg = half ? csplit : 0, cend = half ? p.dv : csplit;
     for (int c0 = cbeg; c0 < cend; c0 += 16) {

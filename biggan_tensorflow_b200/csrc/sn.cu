@@ -17,8 +17,13 @@
 #define SN_STAGED_MAX_C 4096          // column partials live in registers: 4 float4 per thread
 static inline bool sn_staged(int C) { return (C % 4 == 0) && C <= SN_STAGED_MAX_C; }
 static inline int sn_rows_per_block(int K, int C) {
-  long rt = bg_cdiv(K, 4L * bg_num_sms());
-  if (sn_staged(C) && rt > SN_TILE_FLOATS / C) rt = SN_TILE_FLOATS / C;
+  long rt;
+  if (sn_staged(C)) {
+    rt = SN_TILE_FLOATS / C;                         // one 32 KB chunk; the CTA count follows from sn_rows_per_cta
+    if (rt > K) rt = K;
+  } else {
+    rt = bg_cdiv(K, 4L * bg_num_sms());
+  }
   if (rt < 1) rt = 1;
   if (rt > SN_MAX_RT) rt = SN_MAX_RT;
   return (int)rt;
@@ -31,7 +36,7 @@ static inline int sn_rows_per_cta(int K, int C, int RT) {
   if (chunks < 1) chunks = 1;
   return (int)(RT * chunks);
 }
-static inline size_t sn_matvec_smem(int C, int RT) { return sn_staged(C) ? (size_t)2 * RT * C * sizeof(float) : 0; }
+static inline size_t sn_matvec_smem(int C, int RT) { return sn_staged(C) ? ((size_t)2 * RT * C + C) * sizeof(float) : 0; }
 
 // ---------------------------------------------------------------------------------------------
 // device bodies (blk = block index within the matrix)
@@ -104,6 +109,8 @@ __device__ __forceinline__ void sn_matvec_staged_body(const float* __restrict__ 
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   issue(0);
+  float* us = tile + 2 * RT * C;                       // u staged once per CTA (read by every row of every chunk)
+  for (int c = threadIdx.x * 4; c < C; c += 1024) *reinterpret_cast<float4*>(us + c) = __ldg(reinterpret_cast<const float4*>(u + c));
   for (int ci = 0; ci < nchunk; ++ci) {
     if (ci + 1 < nchunk) {
       issue(ci + 1);
@@ -120,7 +127,7 @@ __device__ __forceinline__ void sn_matvec_staged_body(const float* __restrict__ 
       float s = 0.f;
       for (int c = lane * 4; c < C; c += 128) {
         float4 w4 = *reinterpret_cast<const float4*>(row + c);
-        float4 u4 = __ldg(reinterpret_cast<const float4*>(u + c));
+        float4 u4 = *reinterpret_cast<const float4*>(us + c);
         s += w4.x * u4.x + w4.y * u4.y + w4.z * u4.z + w4.w * u4.w;
       }
       s = bg_warp_sum(s);
@@ -334,7 +341,7 @@ sn_matvec_kernel(const float* W, const float* u, float* vraw, float* pcol, int K
 static int sn_matvec_attr() {
   static bool done = false;
   if (!done) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(sn_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SN_TILE_FLOATS * (int)sizeof(float)));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(sn_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * SN_TILE_FLOATS + SN_STAGED_MAX_C) * (int)sizeof(float)));
     done = true;
   }
   return BG_OK;
@@ -612,7 +619,7 @@ extern "C" int bg_sn_group_forward(const void* plan_dev, const int* totals, void
   const SnMap* m2 = m1 + totals[2];
   static bool attr_set = false;
   if (!attr_set) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(sng_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SN_TILE_FLOATS * (int)sizeof(float)));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(sng_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * SN_TILE_FLOATS + SN_STAGED_MAX_C) * (int)sizeof(float)));
     attr_set = true;
   }
   sng_matvec_kernel<<<totals[1], 256, (size_t)totals[7], st>>>(its, m0);

@@ -104,6 +104,12 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one MUFU.EX2 (exp2f() adds range scaling around it); inputs here are <= 0 or -inf, outputs feed bf16 operands
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // 32 lanes x 16 consecutive fp32 columns: thread i gets row (lane base + i)
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
   asm volatile(

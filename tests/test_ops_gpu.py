@@ -60,7 +60,7 @@ def run_case(prod_fn, ref_fn, inputs, dtype, tol=None, fp32_inputs=(), check_sta
             # softmax is invariant to a shift of all keys: this gradient is analytically zero and both
             # sides only hold summation noise
             assert float(g.abs().max()) <= 1e-9 * max(gscale, 1.0)
-            assert float(pv.grad.float().abs().max()) <= 1e-3 * gscale, n
+            assert float(pv.grad.float().abs().max()) <= 2e-3 * gscale, n      # bf16 P / dS rounding noise, relative to the largest gradient
             continue
         # max-pooled attention branches under bf16: see tests/test_bf16_conditioning.py
         vtol = 1.5e-1 if (tol >= 1e-3 and ("f_conv/kernel" in n or "h_conv/kernel" in n)) else tol

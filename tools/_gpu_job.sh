@@ -1,4 +1,4 @@
 cd /root/repo
-timeout 120 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x -k "condition or step" > gpurun_out/t30.log 2>&1; tail -3 gpurun_out/t30.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n2d.log 2>&1; echo rc=$?; grep -o "\"value\": [0-9.]*, \"unit\": \"img/s\", \"n_gpus\": [0-9]*" gpurun_out/bench_n2d.log; tail -3 gpurun_out/bench_n2d.log | cut -c1-400
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dist_check.py > gpurun_out/dist2b.log 2>&1; tail -3 gpurun_out/dist2b.log; timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/dist_check.py bf16 > gpurun_out/dist2c.log 2>&1; tail -3 gpurun_out/dist2c.log
+timeout 300 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/t31.log 2>&1; tail -5 gpurun_out/t31.log
+timeout 120 python tools/sn_bench.py > gpurun_out/sn_bench5.log 2>&1; tail -4 gpurun_out/sn_bench5.log
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-json gpurun_out/prof_b256_23.json > gpurun_out/bench_g16.log 2>&1; grep -o "\"value\": [0-9.]*, \"unit\": \"img/s\", \"n_gpus\"" gpurun_out/bench_g16.log
