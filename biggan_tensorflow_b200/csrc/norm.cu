@@ -7,8 +7,8 @@
 #define BN_CPB 128   // channels per block (32 lanes x 4)
 
 static inline int bn_nchunk(int B, long rows, int C) {
-  // chunks of one sample's HW rows; B * nchunk * channel-blocks ~ 8 CTAs per SM
-  long want = bg_cdiv(8L * bg_num_sms(), (long)B);
+  // chunks of one sample's HW rows; B * nchunk * channel-blocks ~ 16 CTAs per SM
+  long want = bg_cdiv(16L * bg_num_sms(), (long)B);
   long mx = bg_cdiv(rows, 32);
   long n = want < mx ? want : mx;
   if (n < 1) n = 1;
@@ -36,7 +36,7 @@ static inline bool bn_vec_ok(int C, int dtype) { return C % (dtype == BG_F32 ? 4
 
 // MODE 0: q1 = x, q2 = x^2.   MODE 1: g = dy * act'(y); q1 = g, q2 = g * xhat
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                  const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int gb_bstride, int act, float eps, float* __restrict__ part, long HW, int C, int nchunk, int TPRB, int R) {
@@ -50,18 +50,22 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
   float s1[V], s2[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
-  float inv[V], shift[V], mu[V], rs[V];
+  // bf16 storage: accumulate sum(g) and sum(g * x) and form sum(g * xhat) = rs * (sum(g x) - mu sum(g)) once at the end --
+  // the per-thread mean / rstd vectors would cost 16 registers and a third of the occupancy; the fp32 (parity) path keeps
+  // the term-by-term form
+  constexpr bool LEAN = (MODE == 1) && (sizeof(T) == 2);
+  float inv[V], shift[V], mu[LEAN ? 1 : V], rs[LEAN ? 1 : V];
   if (MODE == 1) {
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      rs[e] = rsqrtf(var[c + e] + eps);
-      mu[e] = mean[c + e];
-      inv[e] = rs[e] * gamma[(long)b * gb_bstride + c + e];
-      shift[e] = beta[(long)b * gb_bstride + c + e] - mu[e] * inv[e];
+      const float rse = rsqrtf(var[c + e] + eps), mue = mean[c + e];
+      if constexpr (!LEAN) { rs[e] = rse; mu[e] = mue; }
+      inv[e] = rse * gamma[(long)b * gb_bstride + c + e];
+      shift[e] = beta[(long)b * gb_bstride + c + e] - mue * inv[e];
     }
   }
   const long base = (long)b * HW * C + c;
-#pragma unroll 2
+#pragma unroll (MODE == 0 ? 4 : 2)
   for (long r = r0 + r_in; r < r1; r += R) {
     float xe[V];
     Vec<T>::ld(x, base + r * C, xe);
@@ -76,9 +80,14 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
         float g = de[e];
         if (act == BG_ACT_RELU && !(xe[e] * inv[e] + shift[e] > 0.f)) g = 0.f;
         s1[e] += g;
-        s2[e] = fmaf(g, (xe[e] - mu[e]) * rs[e], s2[e]);
+        if constexpr (LEAN) s2[e] = fmaf(g, xe[e], s2[e]);
+        else s2[e] = fmaf(g, (xe[e] - mu[e]) * rs[e], s2[e]);
       }
     }
+  }
+  if constexpr (LEAN) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) s2[e] = rsqrtf(var[c + e] + eps) * (s2[e] - mean[c + e] * s1[e]);
   }
   const int CB = TPRB * V;                            // channels of this block
   float* sh1 = bn_sh;

@@ -64,6 +64,8 @@ def run_case(prod_fn, ref_fn, inputs, dtype, tol=None, fp32_inputs=(), check_sta
             continue
         # max-pooled attention branches under bf16: see tests/test_bf16_conditioning.py
         vtol = 1.5e-1 if (tol >= 1e-3 and ("f_conv/kernel" in n or "h_conv/kernel" in n)) else tol
+        if tol >= 1e-3 and n.endswith("g_conv/bias"):
+            vtol = 1.5e-1          # sum over all queries of dQ (mixed signs): bf16 P / dS operand rounding does not average out
         assert_close(pv.grad.float().cpu().numpy(), g.numpy(), vtol, "d/d" + n)
     if check_state:
         for n, v in rs.vars.items():
