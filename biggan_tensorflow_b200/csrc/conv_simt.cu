@@ -372,7 +372,10 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 // host side
 // ------------------------------------------------------------------------------------------------
 int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
-                     const float* bias, const void* residual, void* out, int act, cudaStream_t st, int* taken);
+                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, cudaStream_t st,
+                     int* taken);
+size_t bg_tc_fwd_splitk_bytes(const BgGeom& g);
+static inline size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw,
                      void* ws, size_t ws_bytes, cudaStream_t st, int* taken);
 size_t bg_tc_conv_wgrad_ws(const BgGeom& g, const bg_conv_desc* d);
@@ -456,10 +459,11 @@ static inline bool fc_shape(const bg_conv_desc* d) {
 }
 
 extern "C" size_t bg_conv2d_fwd_workspace_bytes(const bg_conv_desc* d, int dtype) {
-  if (dtype == BG_BF16 && reflect_padded(d)) return padded_bytes(d, 2);
   BgGeom g;
-  if (dtype == BG_F32 && bg_build_geom(d, BG_OP_FWD, &g) == BG_OK) return fwd_ksplit_bytes(g);
-  return 0;
+  if (bg_build_geom(d, BG_OP_FWD, &g) != BG_OK) return 0;
+  if (dtype == BG_F32) return fwd_ksplit_bytes(g);
+  // bf16: [reflect-padded copy (only when the caller did not pre-pad)][tensor-core split-K partials]
+  return (reflect_padded(d) ? align256(padded_bytes(d, 2)) : 0) + bg_tc_fwd_splitk_bytes(g);
 }
 
 extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const void* w_t, const float* bias,
@@ -476,14 +480,21 @@ extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w
     if (wk && (!pad || (ws && ws_bytes >= padded_bytes(d, 2)))) {
       const void* in = x;
       int inH = d->Hi, inW = d->Wi, sy = 0, sx = 0;
+      char* sk = (char*)ws;
+      size_t sk_bytes = ws ? ws_bytes : 0;
       if (pad && g.Ci % 8 == 0 && g.Ci >= 16 && g.Co % 16 == 0) {
         rc = bg_reflect_pad(x, ws, d->B, d->Hi, d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r, dtype, stream);
         if (rc) return rc;
         in = ws; inH += d->pad_t + d->pad_b; inW += d->pad_l + d->pad_r; sy = d->pad_t; sx = d->pad_l;
       }
+      if (pad) {
+        const size_t used = align256(padded_bytes(d, 2));
+        sk = (sk_bytes > used) ? sk + used : nullptr;
+        sk_bytes = (sk_bytes > used) ? sk_bytes - used : 0;
+      }
       if (!pad || in == ws) {
         int taken = 0;
-        rc = bg_tc_fwd_launch(g, in, inH, inW, sy, sx, wk, bias, residual, y, act, st, &taken);
+        rc = bg_tc_fwd_launch(g, in, inH, inW, sy, sx, wk, bias, residual, y, act, sk, sk_bytes, st, &taken);
         if (rc) return rc;
         if (taken) return BG_OK;
       }
@@ -499,14 +510,18 @@ static bool dgrad_padded(const bg_conv_desc* d) {
   return !d->transposed && d->pad_mode == BG_PAD_REFLECT && (d->pad_t | d->pad_b | d->pad_l | d->pad_r);
 }
 
-extern "C" size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype) {
-  if (!dgrad_padded(d)) {
-    BgGeom g;
-    if (dtype == BG_F32 && bg_build_geom(d, BG_OP_DGRAD, &g) == BG_OK) return fwd_ksplit_bytes(g);
-    return 0;
-  }
+static size_t dgrad_padded_bytes(const bg_conv_desc* d, int dtype) {
   size_t es = dtype == BG_F32 ? 4 : 2;
-  return (size_t)d->B * (d->Hi + d->pad_t + d->pad_b) * (d->Wi + d->pad_l + d->pad_r) * d->Ci * es + 256;
+  return align256((size_t)d->B * (d->Hi + d->pad_t + d->pad_b) * (d->Wi + d->pad_l + d->pad_r) * d->Ci * es + 256);
+}
+extern "C" size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype) {
+  BgGeom g;
+  const bool geom_ok = bg_build_geom(d, BG_OP_DGRAD, &g) == BG_OK;
+  // [padded-domain gradient (reflect convs)][tensor-core split-K partials (bf16) | SIMT split-K partials (fp32, unpadded)]
+  size_t n = dgrad_padded(d) ? dgrad_padded_bytes(d, dtype) : 0;
+  if (geom_ok && dtype == BG_BF16) n += bg_tc_fwd_splitk_bytes(g);
+  if (geom_ok && dtype == BG_F32 && !dgrad_padded(d)) n += fwd_ksplit_bytes(g);
+  return n;
 }
 
 extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void* w, const void* w_t, const void* residual,
@@ -516,15 +531,22 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool padded = dgrad_padded(d);
-  if (padded) BG_REQUIRE(ws && ws_bytes >= bg_conv2d_dgrad_workspace_bytes(d, dtype), BG_ERR_WORKSPACE, "dgrad workspace too small");
+  if (padded) BG_REQUIRE(ws && ws_bytes >= dgrad_padded_bytes(d, dtype), BG_ERR_WORKSPACE, "dgrad workspace too small");
   void* gout = padded ? ws : dx;
   const void* gres = padded ? nullptr : residual;
+  char* sk = (char*)ws;
+  size_t sk_bytes = ws ? ws_bytes : 0;
+  if (padded) {
+    const size_t used = dgrad_padded_bytes(d, dtype);
+    sk = (sk_bytes > used) ? sk + used : nullptr;
+    sk_bytes = (sk_bytes > used) ? sk_bytes - used : 0;
+  }
   bool done = false;
   if (!force_simt && dtype == BG_BF16) {
     const void* wk = d->transposed ? w_t : w;     // dgrad contracts over Co: HWIO [tap][ci][co] is K-major natively
     if (wk) {
       int taken = 0;
-      rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, gres, gout, BG_ACT_NONE, st, &taken);
+      rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, gres, gout, BG_ACT_NONE, sk, sk_bytes, st, &taken);
       if (rc) return rc;
       done = taken != 0;
     }

@@ -31,6 +31,9 @@ struct TcFwdParams {
   int MT;                    // 128-pixel sub-tiles per CTA sharing every weight tile (B operand)
   int tw, th, tb;            // tiles per phase
   int nkb, BN, act, stages;
+  int ksplit;                // split-K: each tile's (tap, k-block) stage sequence is cut into ksplit work items whose fp32
+  float* part;               //   partial accumulators go to part[split * part_stride + out offset] (summed by tc_splitk_reduce_kernel)
+  long part_stride;
   int dry;                   // tuning: skip the MMAs (measures the bare TMA ingest rate of the tile stream)
   int ktail;                 // 16-channel MMA steps holding data in the last 64-channel k-block (the rest is OOB zero fill)
   int oy0[4], ox0[4], Hp[4], Wp[4], ntaps[4];
@@ -56,7 +59,9 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
     const int row = q * 32 + lane;
     const int w = row % p.bw, h = (row / p.bw) % p.bh, bl = row / (p.bw * p.bh);
     int lt = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+    const int S = p.ksplit;
+    for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
+      const int tile = wi / S, split = wi - tile * S;
       const int nt = tile % ntn; int t = tile / ntn;
       const int phase = t / tiles_pp; t -= phase * tiles_pp;
       const int j0 = (t % p.tw) * p.bw; t /= p.tw;
@@ -71,6 +76,26 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
       // residual (fused accumulate / skip connection) is read in groups of 4 x 16 channels, one group ahead of its use; the
       // first group is in flight while this warp still waits for the accumulator, so the global-load latency is off the
       // per-tile critical path
+      if (S > 1) {                                   // split-K work item: raw fp32 partials, finished by the reduce kernel
+        mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
+        tc_fence_after();
+        float* pp = p.part + (long)split * p.part_stride + obase;
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), r);
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(pp + c0);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                                 __uint_as_float(r[4 * e + 3]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+        continue;
+      }
       const bool use_res = (p.residual != nullptr) && valid;
       uint4 rb[2][4][2];
       auto load_group = [&](int g, int cg) {
@@ -177,26 +202,27 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
     if (elect_one_sync()) {
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, par = 1, sa = smem_base;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int S = p.ksplit;
+      for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x) {
+        const int tile = wi / S, split = wi - tile * S;
         const int nt = tile % ntn; int t = tile / ntn;
         const int phase = t / tiles_pp; t -= phase * tiles_pp;
         const int j0 = (t % p.tw) * p.bw; t /= p.tw;
         const int i0 = (t % p.th) * p.bh; t /= p.th;
         const int b0 = t * p.bb;
         const int n0 = nt * p.BN;
-        const int ntaps = p.ntaps[phase];
-        for (int tp = 0; tp < ntaps; ++tp) {
-          const TcTap tap = p.taps[phase][tp];
-          const CUtensorMap* am = &p.amap[tap.map];
-          const int cx = j0 + tap.dx, cy = i0 + tap.dy;
-          for (int kb = 0; kb < p.nkb; ++kb) {
-            mbar_wait(empty0 + s * 8u, par);
-            const uint32_t fb = full0 + s * 8u;
-            mbar_expect_tx(fb, stage_bytes);
-            tma_load_4d(sa, am, fb, kb * 64, cx, cy, b0);
-            tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
-            if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
-          }
+        const int total = p.ntaps[phase] * p.nkb;
+        const int lo = total * split / S, hi = total * (split + 1) / S;     // this work item's (tap, k-block) stages
+        int tp = lo / p.nkb, kb = lo - tp * p.nkb;
+        TcTap tap = p.taps[phase][tp];
+        for (int li = lo; li < hi; ++li) {
+          mbar_wait(empty0 + s * 8u, par);
+          const uint32_t fb = full0 + s * 8u;
+          mbar_expect_tx(fb, stage_bytes);
+          tma_load_4d(sa, &p.amap[tap.map], fb, kb * 64, j0 + tap.dx, i0 + tap.dy, b0);
+          tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
+          if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
+          if (++kb == p.nkb) { kb = 0; ++tp; if (li + 1 < hi) tap = p.taps[phase][tp]; }
         }
       }
     }
@@ -208,16 +234,19 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
       const uint32_t dry = (uint32_t)p.dry;
       uint32_t s = 0, par = 0, a_lo = a_lo0;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int S = p.ksplit;
+      for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
+        const int tile = wi / S, split = wi - tile * S;
         const int phase = (tile / ntn) / tiles_pp;
         const int total = p.ntaps[phase] * p.nkb;
+        const int lo = total * split / S, hi = total * (split + 1) / S;
         const int buf = lt & 1;
         mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
-        int kb = 0;
+        int kb = lo % p.nkb;
         uint32_t acc = 0u;
-        for (int li = 0; li < total; ++li) {
+        for (int li = lo; li < hi; ++li) {
           mbar_wait(full0 + s * 8u, par);
           tc_fence_after();
           const int nk = (kb == p.nkb - 1) ? p.ktail : 4;
@@ -442,29 +471,101 @@ static int pick_bn(int Co) {
 
 static inline int floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 
+// out = act(sum_z part[z] + bias + residual) -> bf16, 8 channels per thread (Co % 16 == 0)
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const float* __restrict__ part, long stride, int nz, const float* __restrict__ bias, const bf16* residual,
+                        bf16* out, long n8, int Co, int act) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const long e0 = i * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    for (int z = 0; z < nz; ++z) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(part + (long)z * stride + e0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(part + (long)z * stride + e0 + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (bias) {
+      const int c = (int)(e0 % Co);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += bias[c + e];
+    }
+    if (residual) {
+      float r[8];
+      Vec<bf16>::ld(residual, e0, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = bg_apply_act(v[e], act);
+    Vec<bf16>::st(out, e0, v);
+  }
+}
+
+// Tiling + split-K plan of the forward-type kernel (shared by the launcher and the workspace query).
+// Split-K: when the tile count leaves most SMs idle (small maps / small per-GPU batch) or its last wave is mostly empty,
+// each tile's (tap, k-block) stage sequence is cut into S work items with fp32 partials in workspace.
+struct TcFwdPlan { int ok, BN, bw, bh, bb, tw, th, tb, ntiles, ksplit; };
+static TcFwdPlan tc_fwd_plan(const BgGeom& g) {
+  TcFwdPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  if (!tc_device_ok()) return pl;
+  if (g.Ci % 8 != 0 || g.Ci < 16 || g.Co % 16 != 0 || g.nphase < 1) return pl;
+  int min_taps = 1 << 30;
+  for (int ph = 0; ph < g.nphase; ++ph) {
+    if (g.ph[ph].Hp != g.ph[0].Hp || g.ph[ph].Wp != g.ph[0].Wp) return pl;
+    if (g.ph[ph].ntaps < 1 || g.ph[ph].ntaps > TC_MAX_TAPS) return pl;
+    min_taps = min(min_taps, g.ph[ph].ntaps);
+  }
+  pl.BN = pick_bn(g.Co);
+  if (!pl.BN) return pl;
+  pl.bw = 128; pl.bh = 1; pl.bb = 1;
+  choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 128, &pl.bw, &pl.bh, &pl.bb);
+  pl.tw = (int)bg_cdiv(g.ph[0].Wp, pl.bw); pl.th = (int)bg_cdiv(g.ph[0].Hp, pl.bh); pl.tb = (int)bg_cdiv(g.B, pl.bb);
+  pl.ntiles = pl.tw * pl.th * pl.tb * g.nphase * (g.Co / pl.BN);
+  pl.ksplit = 1;
+  static int sk_env = -1;
+  if (sk_env < 0) { const char* e = getenv("BG_TC_SPLITK"); sk_env = e ? atoi(e) : 8; }
+  const int sms = bg_num_sms();
+  const int total = min_taps * (int)bg_cdiv(g.Ci, 64);
+  if (sk_env > 1 && pl.ntiles < 4 * sms && total >= 12) {
+    // microsecond model: waves x (stages per item x ~0.3 us + 1 us per item) + the reduce pass (launch + fp32 partial
+    // write and read at ~4 TB/s); splitting pays for the 4x4 / 8x8 maps at small per-GPU batch, not for large outputs
+    const double out_mb = (double)g.B * g.Ho * g.Wo * g.Co * 4.0 / 1e6;
+    double best = (double)bg_cdiv(pl.ntiles, sms) * (total * 0.3 + 1.0);
+    for (int S = 2; S <= sk_env && S <= 8 && total / S >= 6; ++S) {
+      const double t = (double)bg_cdiv((long)pl.ntiles * S, sms) * ((double)total / S * 0.3 + 1.0) + 3.0 + (2.0 * S + 1.0) * out_mb / 4.0;
+      if (t < 0.85 * best) { best = t; pl.ksplit = S; }
+    }
+  }
+  pl.ok = 1;
+  return pl;
+}
+size_t bg_tc_fwd_splitk_bytes(const BgGeom& g) {
+  const TcFwdPlan pl = tc_fwd_plan(g);
+  if (!pl.ok || pl.ksplit <= 1) return 0;
+  return (size_t)pl.ksplit * g.B * g.Ho * g.Wo * g.Co * sizeof(float) + 256;
+}
+
 static int g_cnt_tc_fwd = 0, g_cnt_tc_wgrad = 0;   // launches taken by the tensor-core kernels (tests / bench)
 // `in` must already be zero-pad semantics (reflect inputs are pre-padded by the caller, with
 // tap offsets shifted accordingly through pad_shift_y/x).
 int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
-                     const float* bias, const void* residual, void* out, int act, cudaStream_t st, int* taken) {
+                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, cudaStream_t st,
+                     int* taken) {
   *taken = 0;
-  if (!tc_device_ok()) return BG_OK;
-  if (g.Ci % 8 != 0 || g.Ci < 16 || g.Co % 16 != 0 || g.nphase < 1) return BG_OK;
-  for (int ph = 0; ph < g.nphase; ++ph) {
-    if (g.ph[ph].Hp != g.ph[0].Hp || g.ph[ph].Wp != g.ph[0].Wp) return BG_OK;
-    if (g.ph[ph].ntaps < 1 || g.ph[ph].ntaps > TC_MAX_TAPS) return BG_OK;
-  }
+  const TcFwdPlan pl = tc_fwd_plan(g);
+  if (!pl.ok) return BG_OK;
   if (((uintptr_t)in | (uintptr_t)w_kmajor | (uintptr_t)out | (uintptr_t)residual) & 15) return BG_OK;
   static TcFwdParams P;      // large struct: keep it off the stack (host calls are single-threaded per process)
   memset(&P, 0, sizeof(P));
-  const int BN = pick_bn(g.Co);
-  if (BN == 0) return BG_OK;
-  int bw = 128, bh = 1, bb = 1;
-  choose_box(g.ph[0].Wp, g.ph[0].Hp, g.B, 128, &bw, &bh, &bb);
+  const int BN = pl.BN;
+  int bw = pl.bw, bh = pl.bh, bb = pl.bb;
+  bool box_override = false;
   {
     const char* e = getenv("BG_TC_BOX");          // tuning knob: "bw,bh,bb" (product 128)
     int a = 0, b = 0, c = 0;
-    if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a * b * c == 128) { bw = a; bh = b; bb = c; }
+    if (e && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a * b * c == 128) { bw = a; bh = b; bb = c; box_override = true; }
     const char* dry = getenv("BG_TC_DRY");
     P.dry = (dry && dry[0] == '1') ? 1 : 0;
   }
@@ -508,7 +609,13 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   }
   P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
   const long ntiles = (long)P.tw * P.th * P.tb * g.nphase * (g.Co / BN);
-  dim3 grid((unsigned)min(ntiles, (long)bg_num_sms()));
+  const long out_numel = (long)g.B * g.Ho * g.Wo * g.Co;
+  P.ksplit = 1;
+  if (pl.ksplit > 1 && !box_override && sk_ws && sk_bytes >= (size_t)pl.ksplit * out_numel * sizeof(float) &&
+      (((uintptr_t)sk_ws) & 15) == 0) {
+    P.ksplit = pl.ksplit; P.part = (float*)sk_ws; P.part_stride = out_numel;
+  }
+  dim3 grid((unsigned)min(ntiles * P.ksplit, (long)bg_num_sms()));
   // halo mode: stride-1 layer tiled in full 128-pixel row segments -> taps differing only in dx share one activation box
   {
     const char* he = getenv("BG_TC_HALO");        // tuning / A-B knob, read per call
@@ -518,7 +625,7 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     const int hstage = TC_HALO_ABYTES + 3 * BN * 128;
     int hstages = (200 * 1024) / hstage;
     if (hstages > 8) hstages = 8;
-    if (halo_env && g.nphase == 1 && s == 1 && bw == 128 && bh == 1 && bb == 1 && hstages >= 3) {
+    if (halo_env && P.ksplit == 1 && g.nphase == 1 && s == 1 && bw == 128 && bh == 1 && bb == 1 && hstages >= 3) {
       TcTap srt[TC_MAX_TAPS];
       const int nt = g.ph[0].ntaps;
       for (int t = 0; t < nt; ++t) srt[t] = P.taps[0][t];
@@ -584,6 +691,12 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   else TC_LAUNCH(512);
 #undef TC_LAUNCH
   BG_LAUNCH_CHECK();
+  if (P.ksplit > 1) {
+    const long n8 = out_numel / 8;
+    const int blocks = (int)min(bg_cdiv(n8, 256), (long)bg_num_sms() * 8);
+    tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(P.part, P.part_stride, P.ksplit, bias, (const bf16*)residual, (bf16*)out, n8, g.Co, act);
+    BG_LAUNCH_CHECK();
+  }
   g_cnt_tc_fwd++;
   *taken = 1;
   return BG_OK;

@@ -1,3 +1,5 @@
 cd /root/repo
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n4b.log 2>&1; echo rc=$?; grep -o "\"value\": [0-9.]*, \"unit\": \"img/s\", \"n_gpus\": [0-9]*" gpurun_out/bench_n4b.log
-timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --impl reference --gpus 4 --steps 1 --warmup 1 > gpurun_out/bench_ref_n4.log 2>&1; echo rc=$?; tail -1 gpurun_out/bench_ref_n4.log | cut -c1-200
+timeout 300 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/t35.log 2>&1; tail -3 gpurun_out/t35.log
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-json gpurun_out/prof_b256_26.json > gpurun_out/bench_g19.log 2>&1; grep -o "\"value\": [0-9.]*, \"unit\": \"img/s\", \"n_gpus\"" gpurun_out/bench_g19.log
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --batch 32 --profile-json gpurun_out/prof_b32_6.json > gpurun_out/bench_g19_b32.log 2>&1; grep -o "\"value\": [0-9.]*, \"unit\": \"img/s\", \"n_gpus\"" gpurun_out/bench_g19_b32.log
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --batch 64 > gpurun_out/bench_g19_b64.log 2>&1; grep -o "\"value\": [0-9.]*, \"unit\": \"img/s\", \"n_gpus\"" gpurun_out/bench_g19_b64.log
