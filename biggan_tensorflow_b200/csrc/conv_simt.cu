@@ -280,6 +280,54 @@ reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, 
   }
 }
 
+// Fold restricted to the band of target pixels that have pad-ring preimages (rows 1..pt, H-1-pb..H-2 and the matching
+// columns): the tensor-core dgrad already wrote every interior preimage (+ residual) straight into dx; this adds the ring
+// preimages kept in the padded-domain buffer.  Requires H >= pt + pb + 2 and W >= pl + pr + 2 (disjoint bands).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+reflect_fold_band_kernel(const T* __restrict__ ring, T* dx, int B, int H, int W, int C, int pt, int pl, int pb, int pr) {
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  const int CV = C / VEC;
+  const int nR = pt + pb, nC = pl + pr;
+  const long band = (long)nR * W + (long)(H - nR) * nC;
+  const long total = (long)B * band * CV;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV); long k = idx / CV;
+    const int b = (int)(k / band); k -= (long)b * band;
+    int y, x;
+    if (k < (long)nR * W) {
+      const int ri = (int)(k / W);
+      x = (int)(k - (long)ri * W);
+      y = ri < pt ? 1 + ri : H - 1 - pb + (ri - pt);
+    } else {
+      k -= (long)nR * W;
+      const int jj = (int)(k / nC), ci = (int)(k - (long)jj * nC);
+      x = ci < pl ? 1 + ci : W - 1 - pr + (ci - pl);
+      y = jj == 0 ? 0 : (jj == H - nR - 1 ? H - 1 : pt + jj);
+    }
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = y + pt;
+    if (y >= 1 && y <= pt) ys[ny++] = pt - y;
+    if (y >= H - 1 - pb && y <= H - 2) ys[ny++] = 2 * (H - 1) - y + pt;
+    xs[nx++] = x + pl;
+    if (x >= 1 && x <= pl) xs[nx++] = pl - x;
+    if (x >= W - 1 - pr && x <= W - 2) xs[nx++] = 2 * (W - 1) - x + pl;
+    const long o = (((long)b * H + y) * W + x) * C + (long)cv * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(dx, o + e); acc[e] = v.x; acc[e + 1] = v.y; acc[e + 2] = v.z; acc[e + 3] = v.w; }
+    for (int a = 0; a < ny; ++a)
+      for (int q = 0; q < nx; ++q) {
+        if (a == 0 && q == 0) continue;             // the interior preimage is already in dx
+        const long src = (((long)b * Hp + ys[a]) * Wp + xs[q]) * C + (long)cv * VEC;
+#pragma unroll
+        for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(ring, src + e); acc[e] += v.x; acc[e + 1] += v.y; acc[e + 2] += v.z; acc[e + 3] += v.w; }
+      }
+#pragma unroll
+    for (int e = 0; e < VEC; e += 4) bg_st4(dx, o + e, f4{acc[e], acc[e + 1], acc[e + 2], acc[e + 3]});
+  }
+}
+
 template <typename T>
 __global__ void reflect_fold_scalar_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, int H, int W, int C,
                                            int pt, int pl, int pb, int pr) {
@@ -372,8 +420,9 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 // host side
 // ------------------------------------------------------------------------------------------------
 int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
-                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, cudaStream_t st,
-                     int* taken);
+                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, const struct BgTcFold* fold,
+                     cudaStream_t st, int* taken);
+struct BgTcFold { int pt, pl, Hi, Wi; void* ring; };
 size_t bg_tc_fwd_splitk_bytes(const BgGeom& g);
 static inline size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw,
@@ -494,7 +543,7 @@ extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w
       }
       if (!pad || in == ws) {
         int taken = 0;
-        rc = bg_tc_fwd_launch(g, in, inH, inW, sy, sx, wk, bias, residual, y, act, sk, sk_bytes, st, &taken);
+        rc = bg_tc_fwd_launch(g, in, inH, inW, sy, sx, wk, bias, residual, y, act, sk, sk_bytes, nullptr, st, &taken);
         if (rc) return rc;
         if (taken) return BG_OK;
       }
@@ -546,7 +595,26 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
     const void* wk = d->transposed ? w_t : w;     // dgrad contracts over Co: HWIO [tap][ci][co] is K-major natively
     if (wk) {
       int taken = 0;
-      rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, gres, gout, BG_ACT_NONE, sk, sk_bytes, st, &taken);
+      static int fold_env = -1;
+      if (fold_env < 0) { const char* e = getenv("BG_TC_FOLD"); fold_env = e ? atoi(e) : 1; }
+      // reflect-padded conv: interior straight into dx (+ residual), pad ring into the padded buffer, band fold afterwards
+      const bool band = fold_env && padded && d->Ci % 8 == 0 && d->Hi >= d->pad_t + d->pad_b + 2 && d->Wi >= d->pad_l + d->pad_r + 2 &&
+                        bg_tc_fwd_splitk_bytes(g) == 0;
+      if (band) {
+        BgTcFold fold = {d->pad_t, d->pad_l, d->Hi, d->Wi, ws};
+        rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, residual, dx, BG_ACT_NONE, nullptr, 0, &fold, st, &taken);
+        if (rc) return rc;
+        if (taken) {
+          const long total = (long)d->B * ((long)(d->pad_t + d->pad_b) * d->Wi + (long)(d->Hi - d->pad_t - d->pad_b) * (d->pad_l + d->pad_r)) *
+                             (d->Ci / 8);
+          const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
+          reflect_fold_band_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)ws, (bf16*)dx, d->B, d->Hi, d->Wi, d->Ci, d->pad_t,
+                                                                  d->pad_l, d->pad_b, d->pad_r);
+          BG_LAUNCH_CHECK();
+          return BG_OK;
+        }
+      }
+      rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, gres, gout, BG_ACT_NONE, sk, sk_bytes, nullptr, st, &taken);
       if (rc) return rc;
       done = taken != 0;
     }

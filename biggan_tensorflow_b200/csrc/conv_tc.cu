@@ -31,6 +31,10 @@ struct TcFwdParams {
   int MT;                    // 128-pixel sub-tiles per CTA sharing every weight tile (B operand)
   int tw, th, tb;            // tiles per phase
   int nkb, BN, act, stages;
+  // fold mode (dgrad of a reflect-padded conv): the kernel iterates the PADDED domain; interior pixels go straight to `out`
+  // (unpadded tensor, + residual), the ring of pad pixels to `ring` (padded-domain buffer), folded back by a band kernel
+  int fold, f_pt, f_pl, f_Hi, f_Wi;
+  bf16* ring;
   int ksplit;                // split-K: each tile's (tap, k-block) stage sequence is cut into ksplit work items whose fp32
   float* part;               //   partial accumulators go to part[split * part_stride + out offset] (summed by tc_splitk_reduce_kernel)
   long part_stride;
@@ -71,7 +75,14 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
       const int pi = i0 + h, pj = j0 + w, b = b0 + bl;
       const bool valid = (b < p.B) && (pi < p.Hp[phase]) && (pj < p.Wp[phase]);
       const int oy = p.oy0[phase] + pi * p.ostep, ox = p.ox0[phase] + pj * p.ostep;
-      const long obase = (((long)b * p.Ho + oy) * p.Wo + ox) * p.Co + n0;
+      long obase = (((long)b * p.Ho + oy) * p.Wo + ox) * p.Co + n0;
+      bf16* outb = p.out;
+      bool res_ok = true;
+      if (p.fold) {
+        const int iy = oy - p.f_pt, ix = ox - p.f_pl;
+        if (iy >= 0 && iy < p.f_Hi && ix >= 0 && ix < p.f_Wi) obase = (((long)b * p.f_Hi + iy) * p.f_Wi + ix) * p.Co + n0;
+        else { outb = p.ring; res_ok = false; }
+      }
       const int buf = lt & 1;
       // residual (fused accumulate / skip connection) is read in groups of 4 x 16 channels, one group ahead of its use; the
       // first group is in flight while this warp still waits for the accumulator, so the global-load latency is off the
@@ -96,7 +107,7 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
         continue;
       }
-      const bool use_res = (p.residual != nullptr) && valid;
+      const bool use_res = (p.residual != nullptr) && valid && res_ok;
       uint4 rb[2][4][2];
       auto load_group = [&](int g, int cg) {
 #pragma unroll
@@ -127,7 +138,7 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
             }
-            if (p.residual) {
+            if (use_res) {
               const uint4 r0 = gsel == 0 ? rb[0][j][0] : rb[1][j][0], r1 = gsel == 0 ? rb[0][j][1] : rb[1][j][1];
               const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
               const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
@@ -152,7 +163,7 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
               q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
               q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+            uint4* op = reinterpret_cast<uint4*>(outb + obase + c0);
             op[0] = o0;
             op[1] = o1;
           }
@@ -506,6 +517,7 @@ tc_splitk_reduce_kernel(const float* __restrict__ part, long stride, int nz, con
 // Split-K: when the tile count leaves most SMs idle (small maps / small per-GPU batch) or its last wave is mostly empty,
 // each tile's (tap, k-block) stage sequence is cut into S work items with fp32 partials in workspace.
 struct TcFwdPlan { int ok, BN, bw, bh, bb, tw, th, tb, ntiles, ksplit; };
+struct BgTcFold { int pt, pl, Hi, Wi; void* ring; };
 static TcFwdPlan tc_fwd_plan(const BgGeom& g) {
   TcFwdPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -551,8 +563,8 @@ static int g_cnt_tc_fwd = 0, g_cnt_tc_wgrad = 0;   // launches taken by the tens
 // `in` must already be zero-pad semantics (reflect inputs are pre-padded by the caller, with
 // tap offsets shifted accordingly through pad_shift_y/x).
 int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
-                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, cudaStream_t st,
-                     int* taken) {
+                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, const BgTcFold* fold,
+                     cudaStream_t st, int* taken) {
   *taken = 0;
   const TcFwdPlan pl = tc_fwd_plan(g);
   if (!pl.ok) return BG_OK;
@@ -610,8 +622,9 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
   const long ntiles = (long)P.tw * P.th * P.tb * g.nphase * (g.Co / BN);
   const long out_numel = (long)g.B * g.Ho * g.Wo * g.Co;
+  if (fold) { P.fold = 1; P.f_pt = fold->pt; P.f_pl = fold->pl; P.f_Hi = fold->Hi; P.f_Wi = fold->Wi; P.ring = (bf16*)fold->ring; }
   P.ksplit = 1;
-  if (pl.ksplit > 1 && !box_override && sk_ws && sk_bytes >= (size_t)pl.ksplit * out_numel * sizeof(float) &&
+  if (pl.ksplit > 1 && !fold && !box_override && sk_ws && sk_bytes >= (size_t)pl.ksplit * out_numel * sizeof(float) &&
       (((uintptr_t)sk_ws) & 15) == 0) {
     P.ksplit = pl.ksplit; P.part = (float*)sk_ws; P.part_stride = out_numel;
   }
