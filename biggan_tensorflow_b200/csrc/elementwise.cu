@@ -383,3 +383,105 @@ extern "C" int bg_pad_channels(const void* src, int src_dtype, void* dst, int ds
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// im2col of the 3-channel image tensors (bf16, stored zero-padded to Cx channels): the first D convs
+// (ops.py:49-113 with Cin = 3) become a 1x1 tensor-core GEMM with K = kh*kw*3 (padded to Cz) instead
+// of kh*kw passes over 16 padded channels.
+//   z[b, oy, ox, (ky*kw + kx)*3 + c] = x[b, R(oy*s + ky - pt), R(ox*s + kx - pl), c],  R = reflect / zero
+// col2im is its adjoint (gather form: deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rgb_src_index(int p, int n, int reflect) {     // padded coordinate -> source index or -1
+  if (p >= 0 && p < n) return p;
+  if (!reflect) return -1;
+  if (p < 0) p = -p;
+  if (p >= n) p = 2 * (n - 1) - p;
+  return (p >= 0 && p < n) ? p : -1;
+}
+
+__global__ void __launch_bounds__(256)
+im2col_rgb_kernel(const bf16* __restrict__ x, bf16* __restrict__ z, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int s,
+                  int pt, int pl, int reflect, int Cz) {
+  const long total = (long)B * Ho * Wo;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo); const long r = idx / Wo;
+    const int oy = (int)(r % Ho); const int b = (int)(r / Ho);
+    bf16* zp = z + idx * Cz;
+    int k = 0;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int iy = rgb_src_index(oy * s + ky - pt, H, reflect);
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ix = rgb_src_index(ox * s + kx - pl, W, reflect);
+        bf16 v0 = __float2bfloat16(0.f), v1 = v0, v2 = v0;
+        if (iy >= 0 && ix >= 0) {
+          const bf16* xp = x + (((long)b * H + iy) * W + ix) * Cx;
+          v0 = xp[0]; v1 = xp[1]; v2 = xp[2];
+        }
+        zp[k] = v0; zp[k + 1] = v1; zp[k + 2] = v2;
+        k += 3;
+      }
+    }
+    for (; k < Cz; ++k) zp[k] = __float2bfloat16(0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+col2im_rgb_kernel(const bf16* __restrict__ dz, bf16* __restrict__ dx, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int s,
+                  int pt, int pl, int pb, int pr, int reflect, int Cz) {
+  const long total = (long)B * H * W;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W); const long r = idx / W;
+    const int y = (int)(r % H); const int b = (int)(r / H);
+    // padded coordinates that read this pixel
+    int py[3], px[3], ny = 0, nx = 0;
+    py[ny++] = y;
+    px[nx++] = x;
+    if (reflect) {
+      if (y >= 1 && y <= pt) py[ny++] = -y;
+      if (y >= H - 1 - pb && y <= H - 2) py[ny++] = 2 * (H - 1) - y;
+      if (x >= 1 && x <= pl) px[nx++] = -x;
+      if (x >= W - 1 - pr && x <= W - 2) px[nx++] = 2 * (W - 1) - x;
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int i = 0; i < ny; ++i)
+      for (int ky = 0; ky < kh; ++ky) {
+        const int ty = py[i] + pt - ky;
+        if (ty < 0 || ty % s) continue;
+        const int oy = ty / s;
+        if (oy >= Ho) continue;
+        for (int j = 0; j < nx; ++j)
+          for (int kx = 0; kx < kw; ++kx) {
+            const int tx = px[j] + pl - kx;
+            if (tx < 0 || tx % s) continue;
+            const int ox = tx / s;
+            if (ox >= Wo) continue;
+            const bf16* zp = dz + (((long)b * Ho + oy) * Wo + ox) * Cz + (ky * kw + kx) * 3;
+            a0 += __bfloat162float(zp[0]); a1 += __bfloat162float(zp[1]); a2 += __bfloat162float(zp[2]);
+          }
+      }
+    bf16* xp = dx + idx * Cx;
+    xp[0] = __float2bfloat16(a0); xp[1] = __float2bfloat16(a1); xp[2] = __float2bfloat16(a2);
+    for (int c = 3; c < Cx; ++c) xp[c] = __float2bfloat16(0.f);
+  }
+}
+
+extern "C" int bg_im2col_rgb(const void* x, void* z, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int stride, int pad_t,
+                             int pad_l, int pad_mode, int Cz, void* stream) {
+  BG_REQUIRE(Cx >= 3 && Cz >= kh * kw * 3 && B > 0, BG_ERR_SHAPE, "im2col_rgb: bad shape");
+  const long total = (long)B * Ho * Wo;
+  const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
+  im2col_rgb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)z, B, H, W, Cx, Ho, Wo, kh, kw, stride, pad_t, pad_l,
+                                                             pad_mode == BG_PAD_REFLECT ? 1 : 0, Cz);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_col2im_rgb(const void* dz, void* dx, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int stride, int pad_t,
+                             int pad_l, int pad_b, int pad_r, int pad_mode, int Cz, void* stream) {
+  BG_REQUIRE(Cx >= 3 && Cz >= kh * kw * 3 && B > 0, BG_ERR_SHAPE, "col2im_rgb: bad shape");
+  const long total = (long)B * H * W;
+  const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
+  col2im_rgb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dz, (bf16*)dx, B, H, W, Cx, Ho, Wo, kh, kw, stride, pad_t, pad_l,
+                                                             pad_b, pad_r, pad_mode == BG_PAD_REFLECT ? 1 : 0, Cz);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

@@ -372,6 +372,23 @@ def _conv_geometry(x, channels, kernel, stride, pad, opt):
     return ConvDesc(B, H, W, Cin, Ho, Wo, channels, kernel, kernel, stride, pt, pl, pb, pr, mode, 0)
 
 
+def _im2col_rgb(x, desc, cz):
+    """[B,H,W,Cx] (3 real channels) -> [B,Ho,Wo,cz] patches (bg_im2col_rgb); backward = its adjoint (bg_col2im_rgb)."""
+    z = Tensor(empty([desc.B, desc.Ho, desc.Wo, cz], x.dtype), requires_grad=x.requires_grad)
+    args = (desc.B, desc.Hi, desc.Wi, x.shape[-1], desc.Ho, desc.Wo, desc.kh, desc.kw, desc.stride)
+    call("bg_im2col_rgb", x.data, z.data, *args, desc.pad_t, desc.pad_l, desc.pad_mode, cz, stream(), tag="im2col_rgb")
+    if recording(x):
+        def bw():
+            if z.grad is None:
+                return
+            g = torch.empty_like(x.data)
+            call("bg_col2im_rgb", z.grad, g, *args, desc.pad_t, desc.pad_l, desc.pad_b, desc.pad_r, desc.pad_mode, cz, stream(),
+                 tag="col2im_rgb")
+            accumulate_grad(x, g, own=True)
+        record(bw)
+    return z
+
+
 def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True, scope='conv_0',
          _residual=None, _act=_lib.ACT_NONE, _pad_cout_to=0):
     """ops.py:49-113."""
@@ -386,6 +403,22 @@ def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True,
         cin_x, cin = x.shape[-1], c_real(x)          # x may carry zero-padded channels (RGB tensors)
         w = get_variable("kernel", shape=[kernel, kernel, cin, channels], initializer=weight_init)
         c_pad = round_up(channels, _pad_cout_to) if _pad_cout_to else channels
+        if (cin == 3 and cin_x != cin and x.dtype == BF16 and c_pad % 16 == 0 and kernel * kernel * 3 <= 32
+                and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1):
+            # image input in tensor-core mode: im2col the 3 real channels (K = k*k*3 -> 32) and run ONE 1x1 GEMM instead of
+            # k*k passes over 16 zero-padded channels; the HWIO kernel [k,k,3,Co] read as [27, Co] is already the GEMM operand
+            z = _im2col_rgb(x, desc, 32)
+            wn = _sn_weight(w, 1, True, x.dtype, pad_c=c_pad, pad_r=32)
+            bias = None
+            if use_bias:
+                bias = get_variable("bias", [channels], initializer=constant_initializer(0.0))
+                if c_pad != channels:
+                    bias = _padded_bias(bias, c_pad)
+            d1 = ConvDesc(desc.B, desc.Ho, desc.Wo, 32, desc.Ho, desc.Wo, c_pad, 1, 1, 1, 0, 0, 0, 0, _lib.PAD_ZERO, 0)
+            y = _conv_op(z, wn, bias, d1, act=_act, residual=_residual)
+            if c_pad != channels:
+                y.aux = {"c_real": channels}
+            return y
         wn = _sn_weight(w, kernel * kernel, True, x.dtype, pad_c=c_pad, pad_r=cin_x if cin_x != cin else 0)
         bias = None
         if use_bias:

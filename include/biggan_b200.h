@@ -199,6 +199,14 @@ int bg_pad_channels(const void* src, int src_dtype, void* dst, int dst_dtype, lo
                     void* stream);
 int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr,
                    int dtype, void* stream);
+/* bf16 image tensors stored zero-padded to Cx >= 3 channels (ops.py:49-113 with Cin = 3, the first D convs):
+ * z[b,oy,ox,(ky*kw+kx)*3+c] = x[b, R(oy*stride+ky-pad_t), R(ox*stride+kx-pad_l), c] (R: reflect / zero), channels
+ * kh*kw*3..Cz-1 zero -- the conv then runs as a 1x1 GEMM with K = Cz.  col2im is the adjoint (gather, deterministic):
+ * dx[..., 0..2] = sum of the dz entries that read the pixel, channels 3..Cx-1 zero. */
+int bg_im2col_rgb(const void* x, void* z, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int stride,
+                  int pad_t, int pad_l, int pad_mode, int Cz, void* stream);
+int bg_col2im_rgb(const void* dz, void* dx, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int stride,
+                  int pad_t, int pad_l, int pad_b, int pad_r, int pad_mode, int Cz, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses -- ops.py:753-797 (discriminator_loss 'hinge'), :799-840 (generator_loss 'hinge'),

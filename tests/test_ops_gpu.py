@@ -148,6 +148,24 @@ def test_conv(case, dtype):
              {"x": x}, dtype)
 
 
+@pytest.mark.parametrize("case", [(2, 16, 32, 3, 2, 1, True, "reflect"), (3, 9, 16, 3, 2, 1, False, "reflect"),
+                                  (2, 8, 32, 3, 1, 1, True, "zero"), (2, 12, 96, 3, 1, 1, False, "reflect")])
+def test_conv_rgb_im2col(case):
+    """First D convs in tensor-core mode: the image is stored zero-padded to 16 channels (ops.rgb_pad()), conv() im2cols
+    its 3 real channels (bg_im2col_rgb) and runs one 1x1 GEMM with K = 27 -> 32; dx comes back through bg_col2im_rgb."""
+    from biggan_tensorflow_b200 import ops
+    B, H, Cout, k, s, pad, bias, padtype = case
+    po, ro = _opt(pad=padtype)
+    x = np.random.default_rng(3).standard_normal((B, H, H, 3)).astype(np.float32)
+
+    def prod(xs):
+        xp = ops.pad_channels(xs["x"], 16)
+        return ops.conv(xp, Cout, po, kernel=k, stride=s, pad=pad, use_bias=bias)
+
+    run_case(prod, lambda rs, xs: R.conv(rs, xs["x"], Cout, ro, kernel=k, stride=s, pad=pad, use_bias=bias),
+             {"x": x}, torch.bfloat16)
+
+
 DECONV_CASES = [(2, 4, 32, 16, 4, 2), (2, 8, 16, 16, 3, 1), (2, 4, 16, 8, 3, 2), (1, 4, 8, 8, 6, 2),   # deconv4/3/6
                 (2, 5, 64, 64, 4, 2), (2, 4, 128, 64, 4, 2), (2, 4, 16, 16, 4, 1),
                 (4, 8, 256, 128, 4, 2), (2, 16, 128, 128, 3, 1), (3, 4, 512, 512, 4, 2), (2, 32, 96, 96, 3, 1)]
