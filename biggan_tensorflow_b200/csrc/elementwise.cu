@@ -460,8 +460,53 @@ col2im_rgb_kernel(const bf16* __restrict__ dz, bf16* __restrict__ dx, int B, int
           }
       }
     bf16* xp = dx + idx * Cx;
-    xp[0] = __float2bfloat16(a0); xp[1] = __float2bfloat16(a1); xp[2] = __float2bfloat16(a2);
-    for (int c = 3; c < Cx; ++c) xp[c] = __float2bfloat16(0.f);
+    if (Cx == 16 && (((uintptr_t)dx) & 15) == 0) {
+      __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h2 = __floats2bfloat162_rn(a2, 0.f);
+      uint4 o0 = make_uint4(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h2), 0u, 0u);
+      reinterpret_cast<uint4*>(xp)[0] = o0;
+      reinterpret_cast<uint4*>(xp)[1] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      xp[0] = __float2bfloat16(a0); xp[1] = __float2bfloat16(a1); xp[2] = __float2bfloat16(a2);
+      for (int c = 3; c < Cx; ++c) xp[c] = __float2bfloat16(0.f);
+    }
+  }
+}
+
+// 3x3 fast paths: everything in registers, 8-byte pixel loads, 16-byte stores
+__global__ void __launch_bounds__(256)
+im2col_rgb3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ z, int B, int H, int W, int Cx, int Ho, int Wo, int s, int pt, int pl,
+                     int reflect) {       // Cz == 32, Cx % 4 == 0
+  const long total = (long)B * Ho * Wo;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo); const long r = idx / Wo;
+    const int oy = (int)(r % Ho); const int b = (int)(r / Ho);
+    unsigned short v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = rgb_src_index(oy * s + ky - pt, H, reflect);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = rgb_src_index(ox * s + kx - pl, W, reflect);
+        if (iy >= 0 && ix >= 0) {
+          const uint2 px = __ldg(reinterpret_cast<const uint2*>(x + (((long)b * H + iy) * W + ix) * Cx));
+          v[(ky * 3 + kx) * 3] = (unsigned short)(px.x & 0xffffu);
+          v[(ky * 3 + kx) * 3 + 1] = (unsigned short)(px.x >> 16);
+          v[(ky * 3 + kx) * 3 + 2] = (unsigned short)(px.y & 0xffffu);
+        }
+      }
+    }
+    uint4* zp = reinterpret_cast<uint4*>(z + idx * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      o.x = (uint32_t)v[8 * q] | ((uint32_t)v[8 * q + 1] << 16);
+      o.y = (uint32_t)v[8 * q + 2] | ((uint32_t)v[8 * q + 3] << 16);
+      o.z = (uint32_t)v[8 * q + 4] | ((uint32_t)v[8 * q + 5] << 16);
+      o.w = (uint32_t)v[8 * q + 6] | ((uint32_t)v[8 * q + 7] << 16);
+      zp[q] = o;
+    }
   }
 }
 
@@ -470,8 +515,12 @@ extern "C" int bg_im2col_rgb(const void* x, void* z, int B, int H, int W, int Cx
   BG_REQUIRE(Cx >= 3 && Cz >= kh * kw * 3 && B > 0, BG_ERR_SHAPE, "im2col_rgb: bad shape");
   const long total = (long)B * Ho * Wo;
   const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
-  im2col_rgb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)z, B, H, W, Cx, Ho, Wo, kh, kw, stride, pad_t, pad_l,
-                                                             pad_mode == BG_PAD_REFLECT ? 1 : 0, Cz);
+  if (kh == 3 && kw == 3 && Cz == 32 && Cx % 4 == 0 && (((uintptr_t)x | (uintptr_t)z) & 15) == 0)
+    im2col_rgb3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)z, B, H, W, Cx, Ho, Wo, stride, pad_t, pad_l,
+                                                                  pad_mode == BG_PAD_REFLECT ? 1 : 0);
+  else
+    im2col_rgb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)z, B, H, W, Cx, Ho, Wo, kh, kw, stride, pad_t, pad_l,
+                                                               pad_mode == BG_PAD_REFLECT ? 1 : 0, Cz);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
