@@ -5,8 +5,9 @@
 // forward-type tile: D[128 output pixels, BN channels] (fp32, TMEM) = sum over taps, 64-channel
 // k-blocks of  A[128 pixels, 64 ch] (TMA box of the NHWC activation, OOB zero-fill = zero padding,
 // SWIZZLE_128B)  x  B[BN, 64 ch] (TMA box of the K-major weights [tap][n][k]).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issue,
-// warps 2-5 = epilogue (tcgen05.ld -> bias / residual / act -> bf16 -> global).
+// Warp roles (320 threads, persistent CTA): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issue (one ELECTED lane each:
+// `elect_one_sync()`, never `lane == 0`, see tc_ptx.cuh), warps 2-9 = epilogue (tcgen05.ld -> bias / residual / act -> bf16).
+// Variants: halo kernel (taps of one dy share an activation box), split-K work items, fold mode (reflect-conv dgrad).
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,8 +28,7 @@ struct TcFwdParams {
   CUtensorMap bmap;
   int B, Ho, Wo, Co;
   int nphase, ostep;
-  int bw, bh, bb;            // pixel box (bw*bh*bb == 128*MT)
-  int MT;                    // 128-pixel sub-tiles per CTA sharing every weight tile (B operand)
+  int bw, bh, bb;            // pixel box (bw*bh*bb == 128)
   int tw, th, tb;            // tiles per phase
   int nkb, BN, act, stages;
   // fold mode (dgrad of a reflect-padded conv): the kernel iterates the PADDED domain; interior pixels go straight to `out`
@@ -47,7 +47,6 @@ struct TcFwdParams {
   bf16* out;
   // halo mode (tc_fwd_halo_kernel): taps that differ only in dx share ONE activation box widened by their dx span
   int ngroups, halo_w;       // tap groups; box width in pixels (128 + span)
-  int halo_bo;               // encode the row phase in the descriptor's matrix-base-offset field
   TcGroup groups[TC_MAX_GROUPS];
 };
 
@@ -593,7 +592,7 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   if ((rc = make_w_map(&P.bmap, w_kmajor, maxw + 1, g.Co, g.Ci, BN))) return rc;
   P.B = g.B; P.Ho = g.Ho; P.Wo = g.Wo; P.Co = g.Co;
   P.nphase = g.nphase; P.ostep = g.ostep;
-  P.bw = bw; P.bh = bh; P.bb = bb; P.MT = 1;
+  P.bw = bw; P.bh = bh; P.bb = bb;
   P.tw = (int)bg_cdiv(g.ph[0].Wp, bw); P.th = (int)bg_cdiv(g.ph[0].Hp, bh); P.tb = (int)bg_cdiv(g.B, bb);
   P.nkb = (int)bg_cdiv(g.Ci, 64);
   P.ktail = (int)bg_cdiv(g.Ci - (P.nkb - 1) * 64, 16);
@@ -633,8 +632,6 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   {
     const char* he = getenv("BG_TC_HALO");        // tuning / A-B knob, read per call
     const int halo_env = he ? atoi(he) : 1;
-    const char* hb = getenv("BG_TC_HALO_BO");
-    P.halo_bo = hb ? atoi(hb) : 0;             // measured: the UMMA swizzle is a function of the absolute smem address, the field must stay 0
     const int hstage = TC_HALO_ABYTES + 3 * BN * 128;
     int hstages = (200 * 1024) / hstage;
     if (hstages > 8) hstages = 8;
