@@ -497,6 +497,34 @@ def cls_loss_logistic(truth, answer, cls_weights=1.0):
     return (xent * cls_weights).mean()
 
 
+def cosine_similarity(a, b):
+    """utils.py:180-183: rows l2-normalised (tf.nn.l2_normalize(axis=1), eps 1e-12), then a b^T."""
+    na = a * torch.rsqrt(torch.clamp((a * a).sum(dim=1, keepdim=True), min=1e-12))
+    nb = b * torch.rsqrt(torch.clamp((b * b).sum(dim=1, keepdim=True), min=1e-12))
+    return na @ nb.t()
+
+
+def orthogonal_regularizer(scale, type="ortho"):
+    """utils.py:185-235 (conv and FC forms differ only in the reshape): scale * l2_loss(reg),
+    reg = W^T W - I ('ortho') or cosine_similarity(W^T W, 1 - I) ('ortho_cosine')."""
+    def ortho_reg(w):
+        c = w.shape[-1]
+        wm = w.reshape(-1, c)                                                   # :192
+        identity = torch.eye(c, dtype=w.dtype)                                  # :195
+        w_mul = wm.t() @ wm                                                     # :197-198
+        if type == "ortho":
+            reg = w_mul - identity                                              # :200
+        elif type == "ortho_cosine":
+            reg = cosine_similarity(w_mul, torch.ones_like(identity) - identity)   # :202
+        else:
+            raise ValueError("Unknown regularization method.")
+        return scale * (reg * reg).sum() / 2                                    # :207-209 tf.nn.l2_loss
+    return ortho_reg
+
+
+orthogonal_regularizer_fc = orthogonal_regularizer
+
+
 # --------------------------------------------------------------------------------------------
 # DiffAugment_tf.py -- randomness is an INPUT (dict of per-sample arrays), see SURVEY 8d
 # --------------------------------------------------------------------------------------------
