@@ -1,7 +1,8 @@
 """CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  Independent, literal numpy restatement of the integer
 index work of DiffAugment_tf.py (pad + gather_nd + scatter_nd, lines 40-66), written op-by-op the way
 the TF graph executes it, so that the closed forms used by oracle/ref_ops.py and by the CUDA kernels
-can be checked against a second implementation (two-implementation agreement; PARITY UNPINNED)."""
+can be checked against a second implementation (two-implementation agreement; both also reproduce the vectors the
+reference's own DiffAugment_tf.py yields over the eager TF-1 stand-in, tests/golden/ref_diffaug.npz)."""
 import numpy as np
 
 

@@ -1,4 +1,5 @@
-"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/ref_ops.py header; PARITY UNPINNED).
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/ref_ops.py header: parity pinned to the reference's source
+through tests/golden/ref_net64.npz, TensorFlow's kernel layer restated).
 
 Restates the default-flag wiring of the reference's generator / discriminator / loss / optimizer
 (BigGAN.py:246-582, :591-715, :790-930, :1061-1084; utils.py:252-267) on top of oracle/ref_ops.py.

@@ -5,10 +5,17 @@ A literal torch-CPU restatement (float64 or float32) of the reference's operator
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
 import this package; the product package ``biggan_tensorflow_b200`` never does.
 
-PARITY UNPINNED: the reference ships no tests / golden vectors and TensorFlow 1.x cannot be
-installed in this image.  What pins this restatement instead: the
-analytic known-answer tests in ``tests/test_oracle_kat.py``, an independent numpy restatement
-of the index ops (``oracle/ref_diffaug_np.py``) and float64 finite-difference gradient checks.
+PARITY: pinned to the reference's own SOURCE.  `tests/golden/ref_*.npz` are produced by importing ops.py,
+utils.py, DiffAugment_tf.py and BigGAN.py unmodified from /root/reference and executing them over
+`oracle/tf1_eager.py`, an eager stand-in for the slice of the TF-1.x API they call
+(`oracle/make_reference_golden.py`); this restatement reproduces those vectors to 2e-9 in float64
+(`tests/test_reference_golden.py`: every op with gradients and state, spectral-norm `u` over two runs,
+losses, regularisers, DiffAugment, and the 64x64 generator / discriminator with identical variable
+names and shapes).  NOT pinned: TensorFlow's own kernels (TF 1.x cannot be installed in this image,
+SURVEY.md section 8c) -- the stand-in's primitives follow TF's documented semantics and are checked
+against the API docs' worked examples and brute-force loops (`tests/test_tf1_eager_shim.py`).  Also kept:
+the analytic known-answer tests (`tests/test_oracle_kat.py`), an independent numpy restatement of the
+index ops (`oracle/ref_diffaug_np.py`) and float64 finite-difference gradient checks.
 
 Every function cites the reference file:line it follows.  Tensors are NHWC like the reference.
 TF-1.x op semantics follow SURVEY.md appendix A.4.

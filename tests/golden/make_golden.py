@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Generates tests/golden/oracle_step_cfg0_b4.npz.
 
-NOT reference-generated: the reference's arithmetic runs on TensorFlow 1.x, which cannot be installed here (DESIGN.md §3,
-"parity unpinned"), so these vectors are produced by the CPU oracle (oracle/, float64) -- they freeze the oracle's
+ORACLE-generated (the reference-generated vectors are tests/golden/ref_*.npz): BigGAN-32 is an extrapolated
+shape the reference's generator() does not accept (BigGAN.py:290-294), so these vectors come from the CPU oracle
+(oracle/, float64, itself pinned to the reference's source by tests/test_reference_golden.py) -- they freeze the oracle's
 behaviour (a regression guard: `tests/test_golden.py` fails if the oracle drifts) and give the GPU tests a fixed target
 that does not depend on running the oracle.  Regenerate with:  python tests/golden/make_golden.py
 """

@@ -1,5 +1,6 @@
 """Golden vectors of one BigGAN-32 training iteration (batch 4): `tests/golden/oracle_step_cfg0_b4.npz`, written by
-`tests/golden/make_golden.py` FROM THE ORACLE (the reference cannot be executed here: DESIGN.md §3, parity unpinned).
+`tests/golden/make_golden.py` FROM THE ORACLE (the reference's generator() has no 32x32 table; the reference-generated
+vectors live in tests/test_reference_golden.py).
 CPU: the oracle still reproduces them bit-for-bit-ish (drift guard).  GPU: the CUDA path reproduces them through the C ABI."""
 import importlib.util
 import os
