@@ -12,10 +12,11 @@ comes out of the reference's functions:
                    alone over two runs; hinge losses + flood (ops.py:753-848); utils.cls_loss_fn('logistic');
                    utils.orthogonal_regularizer(_fc) for 'ortho' and 'ortho_cosine' (utils.py:180-235)
   ref_diffaug.npz  DiffAugment_tf.DiffAugment with the random draws supplied (and logged)
-  ref_net64.npz    BigGAN.generator() / BigGAN.discriminator() on a BigGAN object initialised by the reference's own
-                   __init__ from main.parse_args() with the canonical flags, 64x64, composed into the D
-                   and G losses the way build_model() does (BigGAN.py:806-898): losses, logits, fake images,
-                   gradient norms of every trainable variable, a few full gradients, post-run state
+  ref_net*.npz     BigGAN.generator() / BigGAN.discriminator() on a BigGAN object initialised by the reference's own
+                   __init__ from main.parse_args() with the canonical flags, at 64 / 128 (+DiffAugment
+                   'full') / 256 / 512 pixels with narrow channels, composed into the D and G losses the way
+                   build_model() does (BigGAN.py:806-898): losses, logits, fake images, gradient norms of every
+                   trainable variable, a few full gradients, every variable's name and shape, all state after each phase
 
 Initial variable values come from the oracle's name-seeded initialiser so that oracle, CUDA path and reference
 hold identical weights; inputs from tests/golden/ref_cases.py.  Outputs are stored as float64.
@@ -189,8 +190,8 @@ def gen_diffaug(DA):
     return out
 
 
-def gen_net64(BigGAN, main, utils, ops, DA):
-    kw = C.NET64
+def gen_net(kw, BigGAN, main, utils, ops, DA):
+    da = kw.get("da_policy", "")
     argv = ["main.py", "--img_size", str(kw["img_size"]), "--ch", str(kw["ch"]), "--batch_size", str(kw["batch_size"]),
             "--n_labels", str(kw["n_labels"]), "--z_dim", str(kw["z_dim"]),
             # canonical flag set, SURVEY.md 8(d)
@@ -198,27 +199,47 @@ def gen_net64(BigGAN, main, utils, ops, DA):
             "--conv_padding", "reflect", "--upsampling_method", "deconv4", "--g_conv", "deconv3",
             "--downsampling_method", "strided_conv3", "--bias_in_sa", "true", "--bias_in_d", "false", "--bn_in_d", "false",
             "--first_split_ratio", "3", "--g_first_level_dense_layer", "true", "--g_regularization", "none",
-            "--d_flood", "0", "--g_flood", "0", "--da_policy", "none"]
+            "--d_flood", "0", "--g_flood", "0", "--da_policy", "full" if da else "none"]
     old = sys.argv
     sys.argv = argv
     try:
         args = main.parse_args()
     finally:
         sys.argv = old
-    args.da_policy = ""
+    if not da:
+        args.da_policy = ""
     # BigGAN.__init__ (BigGAN.py:14-231) reads the dataset directory and creates the sample folder: neutralise the two
     # filesystem helpers it took from utils, run the reference's own flag processing
     BigGAN.load_data = lambda **k: ([], [])
     BigGAN.check_folder = lambda d: d
     gan = BigGAN.BigGAN(None, args)
+    assert gan.da_policy == da, (gan.da_policy, da)              # GANBase.py:53-55 expands 'full'
     cfg = M.Config(**kw)
     batch = M.synthetic_batch(cfg, B=kw["batch_size"])
     fresh({"generator/self_attention/gamma": [kw["sa_gamma_init"]], "discriminator/self_attention/gamma": [kw["sa_gamma_init"]]})
     out = {}
+    if da:                                                       # draws for D(real), D(fake) [D phase], D(fake) [G phase]
+        from oracle.ref_ops import draw_diffaug_randoms
+        rng = np.random.Generator(np.random.PCG64(5))
+        order = ["brightness", "saturation", "contrast", "translation_x", "translation_y", "cutout_x", "cutout_y"]
+        for i in range(3):
+            rnd = draw_diffaug_randoms(rng, kw["batch_size"], kw["img_size"], kw["img_size"])
+            E.STATE.random_queue += [rnd[k] for k in order]
+            for k in order:
+                out["rnd%d/%s" % (i, k)] = rnd[k]
     cls_loss = utils.cls_loss_fn(gan.cls_loss_type, tens(gan.cls_loss_weights, False))
 
     def names(sub):
         return [v.full for v in E.STATE.vars.values() if v.trainable and sub in v.full]
+
+    def pick(nl):
+        """Full gradients kept: the first and last three trainables, the attention gamma and its f_conv kernel."""
+        return sorted(set(nl[:3] + nl[-3:] + [n for n in nl if n.endswith("self_attention/gamma") or n.endswith("f_conv/kernel")]))
+
+    def state(tag):
+        for v in E.STATE.vars.values():
+            if not v.trainable:
+                put(out, tag + v.full, v.t.detach().numpy())
 
     # ---- D phase: BigGAN.py:806-807, :853, :857-883 -------------------------------------------------
     real = tens(batch["real"], False)
@@ -241,15 +262,10 @@ def gen_net64(BigGAN, main, utils, ops, DA):
     put(out, "d_fake_images", fake.t.detach().numpy())
     out["D_grad_norms"] = np.array([0.0 if g is None else float(g.norm()) for g in grads])
     gd = dict(zip(dn, grads))
-    for n in ("discriminator/D_logit/kernel", "discriminator/DC_logit/dense/kernel", "discriminator/resblock_down_1/res1/conv_0/kernel",
-              "discriminator/self_attention/f_conv/conv_0/kernel" if "discriminator/self_attention/f_conv/conv_0/kernel" in gd
-              else "discriminator/self_attention/f_conv/kernel", "discriminator/self_attention/gamma"):
+    for n in pick(dn):
         put(out, "D_grad/" + n, gd[n].numpy())
     E.end_run()
-    for n in ("discriminator/D_logit/u", "discriminator/resblock_down_1/res1/conv_0/u", "generator/dense2/u",
-              "generator/resblock_up_8/res1/batch_norm/pop_mean", "generator/resblock_up_8/res1/batch_norm/pop_var",
-              "generator/batch_norm/moving_mean", "generator/batch_norm/moving_variance"):
-        out["state_after_D/" + n] = E.STATE.vars[n].t.detach().numpy().copy()
+    state("state_after_D/")
 
     # ---- G phase (no optimizer step in between): BigGAN.py:883, :857, :894-896 ------------------------
     fake = gan.generator(tens(batch["z_g"], False), labels, reuse=True)
@@ -264,20 +280,24 @@ def gen_net64(BigGAN, main, utils, ops, DA):
     put(out, "g_fake_images", fake.t.detach().numpy())
     out["G_grad_norms"] = np.array([0.0 if g is None else float(g.norm()) for g in grads])
     gg = dict(zip(gn, grads))
-    for n in ("generator/G_logit/kernel", "generator/dense1/kernel", "generator/resblock_up_8/res1/batch_norm/gamma/kernel",
-              "generator/resblock_up_2/skip/deconv_0/kernel", "generator/self_attention/gamma", "generator/batch_norm/gamma"):
+    for n in pick(gn):
         put(out, "G_grad/" + n, gg[n].numpy())
     E.end_run()
-    for n in ("discriminator/D_logit/u", "generator/dense2/u", "generator/resblock_up_8/res1/batch_norm/pop_mean"):
-        out["state_after_G/" + n] = E.STATE.vars[n].t.detach().numpy().copy()
+    assert not E.STATE.random_queue
+    state("state_after_G/")
     return out
 
 
 def main_():
     tf, ops, utils, DA, BigGAN, main = import_reference()
     gold = os.path.join(ROOT, "tests", "golden")
-    for fname, data in (("ref_ops.npz", gen_ops(ops, utils)), ("ref_diffaug.npz", gen_diffaug(DA)),
-                        ("ref_net64.npz", gen_net64(BigGAN, main, utils, ops, DA))):
+    only = sys.argv[1:]
+    jobs = [("ref_ops.npz", lambda: gen_ops(ops, utils)), ("ref_diffaug.npz", lambda: gen_diffaug(DA))]
+    jobs += [("ref_%s.npz" % name, (lambda kw=kw: gen_net(kw, BigGAN, main, utils, ops, DA))) for name, kw in C.NETS.items()]
+    for fname, job in jobs:
+        if only and fname not in only:
+            continue
+        data = job()
         np.savez_compressed(os.path.join(gold, fname), **data)
         print(fname, len(data), "arrays", os.path.getsize(os.path.join(gold, fname)) // 1024, "KiB")
 

@@ -93,9 +93,16 @@ DIFFAUG_CASES = [  # (name, policy, shape)
     ("full", "color,translation,cutout", (4, 32, 32, 3)),
 ]
 
-# whole-network case: the reference's generator()/discriminator() (BigGAN.py:246-582, :591-715) at the smallest
-# image size they accept, canonical flags, one D phase and one G phase (losses and gradients, no optimizer)
-NET64 = dict(img_size=64, ch=32, batch_size=4, n_labels=6, z_dim=128, sa_gamma_init=0.1)
+# whole-network cases: the reference's generator()/discriminator() (BigGAN.py:246-582, :591-715), canonical flags,
+# one D phase and one G phase (losses and gradients, no optimizer)
+NETS = {
+    "net64": dict(img_size=64, ch=32, batch_size=4, n_labels=6, z_dim=128, sa_gamma_init=0.1),
+    # BASELINE configs 1-4 as wiring cases (block tables, attention placement, z split, names) at narrow width
+    "net128da": dict(img_size=128, ch=16, batch_size=2, n_labels=5, z_dim=120, sa_gamma_init=0.1, da_policy="color,translation,cutout"),
+    "net256": dict(img_size=256, ch=8, batch_size=2, n_labels=4, z_dim=64, sa_gamma_init=0.1),
+    "net512": dict(img_size=512, ch=8, batch_size=2, n_labels=4, z_dim=64, sa_gamma_init=0.1),
+}
+NET64 = NETS["net64"]
 
 
 WHOLE_LIMIT = 4096      # golden arrays up to this size are stored whole; larger ones as a strided sample + sum + norm
