@@ -105,16 +105,25 @@ def collect(out, prefix, y, inputs, dy):
             out[prefix + "/state/" + v.full] = v.t.detach().numpy().copy()
 
 
-def gen_ops(ops, utils):
+def gen_cases(ops, cases):
     out = {}
-    for case in C.OP_CASES:
+    acts = {"relu": ops.relu, "prelu": ops.prelu, "lrelu": lambda x: ops.lrelu(x, 0.2)}     # BigGAN.py:71-84
+    for case in cases:
         fresh(case["var_init"])
-        opt = C.make_opt(ops.relu, case["opt"])
+        opt = C.make_opt(acts, case["opt"])
         xs = {k: tens(v) for k, v in C.case_inputs(case).items()}
-        y = getattr(ops, case["fn"])(*xs.values(), **case["kw"], opt=opt)
+        if case["fn"] in ("prelu", "lrelu"):
+            y = getattr(ops, case["fn"])(*xs.values())
+        else:
+            y = getattr(ops, case["fn"])(*xs.values(), **case["kw"], opt=opt)
         if case["relu_after"]:
             y = opt["act"](y)
         collect(out, case["name"], y, xs, C.case_dy(case, tuple(y.shape)))
+    return out
+
+
+def gen_ops(ops, utils):
+    out = gen_cases(ops, C.OP_CASES)
     tf = sys.modules["tensorflow"]
     for K, Cc in C.SN_CASES:                                      # spectral_norm alone, two consecutive runs
         fresh()
@@ -195,11 +204,13 @@ def gen_net(kw, BigGAN, main, utils, ops, DA):
     argv = ["main.py", "--img_size", str(kw["img_size"]), "--ch", str(kw["ch"]), "--batch_size", str(kw["batch_size"]),
             "--n_labels", str(kw["n_labels"]), "--z_dim", str(kw["z_dim"]),
             # canonical flag set, SURVEY.md 8(d)
-            "--gan_type", "hinge", "--activation", "relu", "--sn", "true", "--bn_type", "batch_norm", "--bn_momentum", "0.98",
-            "--conv_padding", "reflect", "--upsampling_method", "deconv4", "--g_conv", "deconv3",
-            "--downsampling_method", "strided_conv3", "--bias_in_sa", "true", "--bias_in_d", "false", "--bn_in_d", "false",
-            "--first_split_ratio", "3", "--g_first_level_dense_layer", "true", "--g_regularization", "none",
-            "--d_flood", "0", "--g_flood", "0", "--da_policy", "full" if da else "none"]
+            "--gan_type", "hinge", "--activation", kw.get("activation", "relu"), "--sn", "true", "--bn_type", "batch_norm",
+            "--bn_momentum", "0.98", "--conv_padding", "reflect", "--upsampling_method", kw.get("upsampling_method", "deconv4"),
+            "--g_conv", kw.get("g_conv", "deconv3"), "--downsampling_method", kw.get("downsampling_method", "strided_conv3"),
+            "--bias_in_sa", "true", "--bias_in_d", "false", "--bn_in_d", "true" if kw.get("bn_in_d") else "false",
+            "--first_split_ratio", "3", "--g_first_level_dense_layer", "true",
+            "--g_regularization", kw.get("g_regularization", "none"), "--g_regularization_factor", str(kw.get("g_regularization_factor", 1e-4)),
+            "--d_flood", str(kw.get("d_flood", 0)), "--g_flood", str(kw.get("g_flood", 0)), "--da_policy", "full" if da else "none"]
     old = sys.argv
     sys.argv = argv
     try:
@@ -272,6 +283,12 @@ def gen_net(kw, BigGAN, main, utils, ops, DA):
     d_fake = gan.discriminator(DA.DiffAugment(fake, policy=gan.da_policy), reuse=True)
     g_cls = gan.g_cls_loss_weight * cls_loss(labels, d_fake["cls"])
     g_loss = ops.generator_loss(gan.gan_type, fake=d_fake["real"], real=d_real["real"], flood_level=gan.g_flood) + g_cls
+    if gan.g_regularization_method != 'none':                    # BigGAN.py:897-898
+        tf = sys.modules["tensorflow"]
+        regs = tf.losses.get_regularization_losses()
+        out["n_regularization_losses"] = np.array(len(regs))
+        out["regularization_loss_sum"] = tf.add_n(regs).t.detach().numpy()
+        g_loss = tf.add_n([g_loss] + regs)
     gn = names("generator")
     grads = torch.autograd.grad(g_loss.t, [E.STATE.vars[n].t for n in gn], allow_unused=True)
     out["g_loss"] = g_loss.t.detach().numpy()
@@ -293,7 +310,9 @@ def main_():
     gold = os.path.join(ROOT, "tests", "golden")
     only = sys.argv[1:]
     jobs = [("ref_ops.npz", lambda: gen_ops(ops, utils)), ("ref_diffaug.npz", lambda: gen_diffaug(DA))]
-    jobs += [("ref_%s.npz" % name, (lambda kw=kw: gen_net(kw, BigGAN, main, utils, ops, DA))) for name, kw in C.NETS.items()]
+    jobs += [("ref_ops_next.npz", lambda: gen_cases(ops, C.NEXT_OP_CASES))]
+    jobs += [("ref_%s.npz" % name, (lambda kw=kw: gen_net(kw, BigGAN, main, utils, ops, DA)))
+             for name, kw in list(C.NETS.items()) + list(C.NEXT_NETS.items())]
     for fname, job in jobs:
         if only and fname not in only:
             continue

@@ -36,6 +36,14 @@ class Config:
     d_cls_loss_weight: float = 5.0
     g_cls_loss_weight: float = 1.0
     sa_gamma_init: float = 0.0     # the reference initialises to 0 (ops.py:486); parity tests use 0.1
+    # SURVEY 8(f) "next" rows: the fork's CLI-default extras and layer variants (main.py:49-67)
+    activation: str = "relu"                   # relu | prelu | lrelu            (BigGAN.py:71-84)
+    upsampling_method: str = "deconv4"         # ops.py:200-218
+    downsampling_method: str = "strided_conv3"  # ops.py:269-291
+    g_conv: str = "deconv3"                    # ops.py:220-230
+    bn_in_d: bool = False
+    g_regularization: str = "none"             # none | ortho | ortho_cosine    (BigGAN.py:257-271)
+    g_regularization_factor: float = 1e-4
 
     @property
     def depth(self):
@@ -89,16 +97,33 @@ def d_block_info(img_size):
     raise ValueError("Invalid image size specified: " + str(img_size))
 
 
-def make_opts(cfg, is_training=True):
+def activation_fn(store, cfg):
+    """BigGAN.py:71-84."""
+    if cfg.activation == "relu":
+        return R.relu
+    if cfg.activation == "prelu":
+        return R.make_prelu(store)
+    if cfg.activation == "lrelu":
+        return lambda x: R.lrelu(x, 0.2)
+    raise ValueError("Unknown activation function: " + str(cfg.activation))
+
+
+def make_opts(cfg, is_training=True, store=None):
     bn_options = {"type": "batch_norm", "momentum": cfg.bn_momentum}            # GANBase.py:39-41
     conv_options = {"padding_type": "reflect", "sn": True}                      # GANBase.py:49-51
-    g_opt = {"sn": True, "is_training": is_training, "upsampling_method": "deconv4",
-             "g_conv": "deconv3", "act": R.relu, "self_attention_bias": True,
+    act = activation_fn(store, cfg)
+    g_opt = {"sn": True, "is_training": is_training, "upsampling_method": cfg.upsampling_method,
+             "g_conv": cfg.g_conv, "act": act, "self_attention_bias": True,
              "bn": copy.deepcopy(bn_options), "conv": copy.deepcopy(conv_options),
              "fc_regularizer": None}                                            # BigGAN.py:248-274
     g_opt["conv"]["regularizer"] = None
-    d_opt = {"sn": True, "is_training": is_training, "bn_in_d": False, "act": R.relu,
-             "downsampling_method": "strided_conv3", "self_attention_bias": True,
+    if is_training and cfg.g_regularization != "none":                          # BigGAN.py:257-271
+        if cfg.g_regularization not in ("ortho", "ortho_cosine"):
+            raise ValueError("Unknown regularization method: " + str(cfg.g_regularization))
+        g_opt["conv"]["regularizer"] = R.orthogonal_regularizer(cfg.g_regularization_factor, type=cfg.g_regularization)
+        g_opt["fc_regularizer"] = R.orthogonal_regularizer_fc(cfg.g_regularization_factor, type=cfg.g_regularization)
+    d_opt = {"sn": True, "is_training": is_training, "bn_in_d": cfg.bn_in_d, "act": act,
+             "downsampling_method": cfg.downsampling_method, "self_attention_bias": True,
              "bn": copy.deepcopy(bn_options), "conv": copy.deepcopy(conv_options)}  # BigGAN.py:593-600
     return g_opt, d_opt
 
@@ -116,7 +141,7 @@ def z_split_sizes(cfg):
 
 def generator(store, cfg, z, cls_z, is_training=True):
     """BigGAN.py:246-582, canonical flags.  z [B,1,1,z_dim], cls_z [B,n_labels]."""
-    opt, _ = make_opts(cfg, is_training)
+    opt, _ = make_opts(cfg, is_training, store)
     with store.variable_scope("generator"):
         split_sizes = z_split_sizes(cfg)
         block_info = g_block_info(cfg.img_size)
@@ -129,9 +154,15 @@ def generator(store, cfg, z, cls_z, is_training=True):
         ch = round_up(int(cfg.ch * 2.0 ** (n_blocks - 0 - 1)), 8)               # :428, :242-243
         zi = 0
         f_width = round_up((split_sizes[0] + cfg.n_labels) * 1.85, 8)           # :433
-        x = R.fully_connected(store, z_split[0], units=f_width, scope="dense1", opt=opt)   # :436
-        x = R.relu(x)
-        x = R.fully_connected(store, x, units=4 * 4 * ch, scope="dense2", opt=opt)         # :438
+        if opt["act"] == R.relu:                                                # :434 (no scope, backward compatibility)
+            x = R.fully_connected(store, z_split[0], units=f_width, scope="dense1", opt=opt)   # :436
+            x = R.relu(x)
+            x = R.fully_connected(store, x, units=4 * 4 * ch, scope="dense2", opt=opt)         # :438
+        else:
+            with store.variable_scope("first"):                                 # :440-443
+                x = R.fully_connected(store, z_split[0], units=f_width, scope="dense1", opt=opt)
+                x = opt["act"](x)
+                x = R.fully_connected(store, x, units=4 * 4 * ch, scope="dense2", opt=opt)
         zi += 1
         x = x.reshape(-1, 4, 4, ch)                                             # :446
         b_i = 0
@@ -150,7 +181,7 @@ def generator(store, cfg, z, cls_z, is_training=True):
             ch = round_up(int(cfg.ch * 2.0 ** (n_blocks - b_i - 1)), 8)         # :488
             ch_mul = ch_mul // 2
         x = R.bn(store, x, opt=opt)                                             # :491
-        x = R.relu(x)                                                           # :492
+        x = opt["act"](x)                                                       # :492
         x = R.conv(store, x, channels=cfg.c_dim, kernel=3, stride=1, pad=1, use_bias=False,
                    opt=opt, scope="G_logit")                                    # :570
         return R.tanh(x)                                                        # :580
@@ -165,7 +196,7 @@ def _sa2(store, cfg, x, ch, opt):
 
 def discriminator(store, cfg, x, is_training=True):
     """BigGAN.py:591-715, canonical flags.  Returns {"real": [B,1], "cls": [B,n_labels]}."""
-    _, opt = make_opts(cfg, is_training)
+    _, opt = make_opts(cfg, is_training, store)
     outputs = {}
     with store.variable_scope("discriminator"):
         block_info = d_block_info(cfg.img_size)
@@ -185,7 +216,7 @@ def discriminator(store, cfg, x, is_training=True):
             ch_mul = ch_mul * 2
         ch = round_up(int(cfg.ch * 2.0 ** (b_i - 1)), 8)                        # :666
         x = R.resblock(store, x, channels=ch, use_bias=False, opt=opt, scope="resblock")   # :668
-        x = R.relu(x)                                                           # :669
+        x = opt["act"](x)                                                       # :669
         features = R.global_sum_pooling(x)                                      # :671
         x = R.fully_connected(store, features, units=1, opt=opt, scope="D_logit")          # :681-684
         outputs["real"] = x
@@ -275,6 +306,9 @@ def g_update(store, cfg, z, cls_z, rnd_fake=None, opt_state=None, apply=True):
         g_cls = cfg.g_cls_loss_weight * R.cls_loss_logistic(cls_t, d_fake["cls"])   # :894
     g_loss = R.generator_loss(cfg.gan_type, fake=d_fake["real"], real=None,
                               flood_level=cfg.g_flood) + g_cls                   # :896
+    if cfg.g_regularization != "none":
+        for rl in store.regularization_losses():                                # :897-898 tf.add_n([g_loss] + reg losses)
+            g_loss = g_loss + rl
     g_vars = store.trainables("generator")                                      # :917
     names = list(g_vars.keys())
     grads = torch.autograd.grad(g_loss, [g_vars[n] for n in names], allow_unused=True)

@@ -69,6 +69,9 @@ class RefStore:
         self.strict = strict
         self.sn_cache = {}          # per update-phase cache of spectral_norm outputs
         self.pending_u = {}
+        self.phase_snapshot = {}    # moving statistics as they were when the phase began (assign_sub semantics)
+        self.regularizers = {}      # full variable name -> callable (tf REGULARIZATION_LOSSES, one entry per variable)
+        self.default_names = {}     # parent scope -> {base: count}  (tf.variable_scope(None, default_name=...))
         if params:
             for k, v in params.items():
                 self.vars[k] = torch.as_tensor(np.asarray(v), dtype=dtype).clone()
@@ -83,9 +86,19 @@ class RefStore:
             return self
 
         def __exit__(self, *a):
+            # TF resets the default-name counters of everything below a scope when the scope is left, so the
+            # second instantiation of a network (reuse=True) names its 'prelu' scopes the same way again
+            full = self.store.full_name()
+            for k in [k for k in self.store.default_names if k == full or k.startswith(full + "/")]:
+                del self.store.default_names[k]
             self.store.scope.pop()
 
-    def variable_scope(self, name):
+    def variable_scope(self, name=None, default_name=None):
+        if name is None:                                   # ops.py:533: variable_scope(name_or_scope=None, default_name="prelu")
+            d = self.default_names.setdefault(self.full_name(), {})
+            k = d.get(default_name, 0)
+            d[default_name] = k + 1
+            name = default_name if k == 0 else "%s_%d" % (default_name, k)
         return RefStore._Scope(self, name)
 
     def full_name(self, name=None):
@@ -94,8 +107,10 @@ class RefStore:
             parts.append(name)
         return "/".join(parts)
 
-    def get_variable(self, name, shape, kind="trunc_normal", value=0.0, trainable=True):
+    def get_variable(self, name, shape, kind="trunc_normal", value=0.0, trainable=True, regularizer=None):
         full = self.full_name(name)
+        if regularizer is not None:
+            self.regularizers[full] = regularizer
         if full not in self.vars:
             if self.strict:
                 raise KeyError(full)
@@ -113,6 +128,11 @@ class RefStore:
     def begin_phase(self):
         """One sess.run: spectral_norm of a variable is evaluated once, `u` advances once."""
         self.sn_cache = {}
+        self.phase_snapshot = {}
+
+    def regularization_losses(self):
+        """tf.losses.get_regularization_losses(): regularizer(variable) for every variable created with one."""
+        return [fn(self.vars[n]) for n, fn in self.regularizers.items()]
 
     def trainables(self, substr):
         return {k: v for k, v in self.vars.items() if self.trainable.get(k, False) and substr in k}
@@ -203,7 +223,8 @@ def conv(store, x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bia
                 raise ValueError("Unsupported padding type: " + str(pad_type))
         if not opt.get("conv", {}).get("sn", True):
             raise NotImplementedError("tf.layers.conv2d path (sn=False) is out of scope")
-        w = store.get_variable("kernel", [kernel, kernel, x.shape[-1], channels])   # :88-92
+        reg = opt.get("conv", {}).get("regularizer", None) if "generator" in store.full_name() else None   # :87-92
+        w = store.get_variable("kernel", [kernel, kernel, x.shape[-1], channels], regularizer=reg)
         wn = spectral_norm(store, w)                                            # :94
         xn = _nchw(x)
         if pads is not None:
@@ -226,7 +247,8 @@ def deconv(store, x, channels, opt, kernel=4, stride=2, padding="SAME", use_bias
         if padding != "SAME":
             raise NotImplementedError("VALID deconv is off the hot path")
         B, H, W, Cin = x.shape
-        w = store.get_variable("kernel", [kernel, kernel, channels, Cin])        # :127
+        w = store.get_variable("kernel", [kernel, kernel, channels, Cin],
+                               regularizer=opt.get("conv", {}).get("regularizer", None))   # :127
         wn = spectral_norm(store, w)                                            # :128
         # forward conv this is the adjoint of: input size H*stride, SAME pad
         pb_h, _ = tf_same_pad(H * stride, kernel, stride)
@@ -251,14 +273,16 @@ def fully_connected(store, x, units, opt, use_bias=True, lrmul=1.0, scope="fully
         x = x.reshape(x.shape[0], -1)                                           # :150
         channels = x.shape[-1]
         if opt.get("conv", {}).get("sn", True):
-            w = store.get_variable("kernel", [channels, units])                 # :156-158
+            reg = opt.get("fc_regularizer") if "generator" in store.full_name() else None   # :155-158
+            w = store.get_variable("kernel", [channels, units], regularizer=reg)
             if use_bias:
                 b = store.get_variable("bias", [units], kind="const", value=0.0)
                 return x @ spectral_norm(store, w) + b                          # :163
             return x @ spectral_norm(store, w)                                  # :165
         # tf.layers.dense (no SN): variables live under '<scope>/dense/{kernel,bias}'
         with store.variable_scope("dense"):                                     # :167-173
-            w = store.get_variable("kernel", [channels, units])
+            reg = opt.get("fc_regularizer") if "generator" in store.full_name() else None
+            w = store.get_variable("kernel", [channels, units], regularizer=reg)
             y = x @ w
             if use_bias:
                 b = store.get_variable("bias", [units], kind="const", value=0.0)
@@ -272,6 +296,43 @@ def relu(x):
 
 def tanh(x):
     return torch.tanh(x)                                                        # ops.py:539-540
+
+
+def lrelu(x, alpha=0.2):
+    return torch.maximum(x, alpha * x)                                          # ops.py:525-526 tf.nn.leaky_relu
+
+
+def make_prelu(store):
+    """ops.py:532-537 bound to a store: alpha [C] (init 0) under '<scope>/prelu[_k]/alpha'."""
+    def prelu(x, scope=None, init_val=0.0):
+        with store.variable_scope(scope, default_name="prelu"):
+            alphas = store.get_variable("alpha", [x.shape[-1]], kind="const", value=init_val)
+            pos = torch.relu(x)
+            neg = alphas * (x - torch.abs(x)) * 0.5
+            return _r(pos + neg)
+    return prelu
+
+
+def avg_pooling(x):
+    return _nhwc(F.avg_pool2d(_nchw(x), 2, 2))                                  # ops.py:512-514 (even maps)
+
+
+def up_sample(x, scale_factor=2):
+    """ops.py:516-519 tf.image.resize_nearest_neighbor to an integer multiple."""
+    return x.repeat_interleave(scale_factor, dim=1).repeat_interleave(scale_factor, dim=2)
+
+
+def depth_to_space(x, r):
+    b, h, w, c = x.shape                                                        # tf.nn.depth_to_space, NHWC
+    x = x.reshape(b, h, w, r, r, c // (r * r)).permute(0, 1, 3, 2, 4, 5)
+    return x.reshape(b, h * r, w * r, c // (r * r))
+
+
+def subpixel_conv(store, x, channels, opt, kernel=3, scale=2, use_bias=True, scope="subpixel_conv_0"):
+    """ops.py:23-27."""
+    r2 = scale * scale
+    x = conv(store, x, channels * r2, opt=opt, kernel=kernel, stride=1, use_bias=use_bias, pad=(kernel - 1) / 2.0, scope=scope)
+    return depth_to_space(x, scale)
 
 
 def global_sum_pooling(x):
@@ -327,10 +388,13 @@ def batch_norm(store, x, opt={}, scope="batch_norm"):
             n = x.shape[0] * x.shape[1] * x.shape[2]
             mean = x.mean(dim=(0, 1, 2))
             var = ((x - mean) ** 2).mean(dim=(0, 1, 2))
-            # fused BN updates moving_variance with the Bessel-corrected variance
-            store.assign(store.full_name("moving_mean"), mm * momentum + mean * (1 - momentum))
-            store.assign(store.full_name("moving_variance"),
-                         mv * momentum + var * (n / max(n - 1, 1)) * (1 - momentum))
+            # fused BN updates moving_variance with the Bessel-corrected variance.  The update is an
+            # assign_sub of (value_at_phase_start - batch_stat) * (1 - momentum): with one instantiation per phase this
+            # is the usual moving average; two instantiations (D(real), D(fake) with bn_in_d) both apply their delta
+            for nm, cur, stat in (("moving_mean", mm, mean), ("moving_variance", mv, var * (n / max(n - 1, 1)))):
+                full = store.full_name(nm)
+                snap = store.phase_snapshot.setdefault(full, cur.detach().clone())
+                store.assign(full, cur.detach() - (snap - stat.detach()) * (1 - momentum))
         else:
             mean, var = mm, mv
         inv = torch.rsqrt(var + 1e-05) * gamma
@@ -391,6 +455,15 @@ def upconv(store, x, channels, opt, use_bias=True):
         return deconv(store, x, channels, kernel=4, stride=2, use_bias=use_bias, opt=opt)
     if m == "deconv6":
         return deconv(store, x, channels, kernel=6, stride=2, use_bias=use_bias, opt=opt)
+    if m == "subpixel2":
+        return subpixel_conv(store, x, channels, kernel=2, scale=2, use_bias=use_bias, opt=opt)
+    if m == "subpixel3":
+        return subpixel_conv(store, x, channels, kernel=3, scale=2, use_bias=use_bias, opt=opt)
+    if m == "resize_conv":
+        x = up_sample(x, 2)
+        return conv(store, x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt)
+    if m == "nn":
+        return up_sample(x, 2)
     raise ValueError("Invalid upsampling method specified: " + str(m))
 
 
@@ -414,6 +487,16 @@ def downconv(store, x, channels, opt, use_bias=True, method=None):
         method = opt["downsampling_method"]
     if method == "strided_conv3":
         return conv(store, x, channels, kernel=3, stride=2, pad=1, use_bias=use_bias, opt=opt)
+    if method == "resize_conv1":
+        x = conv(store, x, channels, kernel=1, stride=1, pad=0, use_bias=use_bias, opt=opt)
+        return avg_pooling(x)
+    if method == "resize_conv3":
+        x = conv(store, x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt)
+        return avg_pooling(x)
+    if method == "pool_only":
+        return avg_pooling(x)
+    if method == "max_pool_only":
+        return max_pooling(x)
     raise ValueError("Invalid downsampling method specified: " + str(method))
 
 

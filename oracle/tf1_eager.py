@@ -157,6 +157,7 @@ class _State:
         self.scope = []                # list of (name, reuse)
         self.vars = {}                 # full name -> Variable (creation order kept)
         self.pending = {}              # full name -> torch value committed by end_run()
+        self.pending_sub = {}          # full name -> accumulated assign_sub deltas committed by end_run()
         self.regularizers = []         # (callable, Variable)
         self.default_names = {}        # parent scope -> {base: count}
         self.random_queue = []         # values handed out by tf.random.uniform, in call order
@@ -177,7 +178,10 @@ def end_run():
     """End of one sess.run: commit the assigns made during the run."""
     for name, val in STATE.pending.items():
         STATE.vars[name]._set(val)
+    for name, delta in STATE.pending_sub.items():
+        STATE.vars[name]._set(STATE.vars[name].t.detach() - delta)
     STATE.pending = {}
+    STATE.pending_sub = {}
 
 
 class Variable(Tensor):
@@ -198,6 +202,13 @@ class Variable(Tensor):
         assert tuple(v.shape) == tuple(self._t.shape), (self.full, v.shape, self._t.shape)
         STATE.pending[self.full] = v
         return Tensor(v)
+
+    def assign_sub(self, delta):
+        """In-place subtraction (what moving_averages.assign_moving_average emits): several of them in one run compose
+        additively, each delta having been computed from the pre-run value."""
+        d = _t(delta).detach()
+        STATE.pending_sub[self.full] = STATE.pending_sub.get(self.full, 0) + d
+        return Tensor(d)
 
     def read_value(self):
         return Tensor(self._t)
@@ -756,8 +767,9 @@ def layers_batch_normalization(inputs, momentum=0.99, epsilon=1e-3, training=Fal
     """tf.layers.batch_normalization(axis=-1, center, scale): variables gamma (1), beta (0), moving_mean (0),
     moving_variance (1) under scope `name`.  training=True: normalise with the batch mean / BIASED variance;
     the update ops (collected in UPDATE_OPS, run by the reference with every train op, utils.py:255) move
-    moving_mean / moving_variance by (1 - momentum), the fused NHWC kernel feeding the UNBIASED (n/(n-1))
-    variance into the moving average."""
+    moving_mean / moving_variance by (1 - momentum) with an assign_sub (two instantiations of one layer in a run
+    -- D(real), D(fake) with --bn_in_d -- both apply their delta), the fused NHWC kernel feeding the UNBIASED
+    (n/(n-1)) variance into the moving average."""
     if renorm:
         raise NotImplementedError("batch renorm is off the hot path")
     x = _t(inputs)
@@ -774,8 +786,9 @@ def layers_batch_normalization(inputs, momentum=0.99, epsilon=1e-3, training=Fal
             n *= x.shape[a]
         mean = x.mean(dim=ax)
         var = ((x - mean) ** 2).mean(dim=ax)
-        mm.assign(mm.t * momentum + mean * (1 - momentum))
-        mv.assign(mv.t * momentum + var * (n / max(n - 1, 1)) * (1 - momentum))
+        # moving_averages.assign_moving_average: variable -= (variable - value) * (1 - momentum)
+        mm.assign_sub((mm.t - mean) * (1 - momentum))
+        mv.assign_sub((mv.t - var * (n / max(n - 1, 1))) * (1 - momentum))
     else:
         mean, var = mm.t, mv.t
     return batch_normalization(x, mean, var, beta, gamma, epsilon)

@@ -17,15 +17,16 @@ OPT = {"is_training": True, "bn_in_d": False, "act": "relu", "upsampling_method"
        "fc_regularizer": None}
 
 
-def make_opt(relu_fn, overrides=None):
+def make_opt(act, overrides=None):
+    """act: the implementation's relu, or a dict {"relu": fn, "prelu": fn, "lrelu": fn} when a case selects the activation."""
     import copy
     o = copy.deepcopy(OPT)
-    o["act"] = relu_fn
     for k, v in (overrides or {}).items():
         if isinstance(v, dict):
             o[k].update(v)
         else:
             o[k] = v
+    o["act"] = act[o["act"]] if isinstance(act, dict) else act
     return o
 
 
@@ -78,6 +79,37 @@ OP_CASES = [
     _c("resblock", "resblock", [("x", (2, 4, 4, 64))], dict(channels=64, use_bias=False), 13),
 ]
 
+# SURVEY 8(f) "next" rows (ranks 1 and 3): activations and up/down-sampling / g_conv variants, bn_in_d.  -> ref_ops_next.npz
+NEXT_OP_CASES = [
+    _c("prelu", "prelu", [("x", (2, 4, 4, 16))], {}, 40,
+       var_init={"prelu/alpha": [0.25, -0.5, 0.1, 0.0, 1.0, 0.3, -0.2, 0.05, 0.6, 0.15, -1.0, 0.2, 0.45, 0.0, 0.35, 0.8]}),
+    _c("lrelu", "lrelu", [("x", (2, 4, 4, 16))], {}, 41),
+    _c("upconv_deconv3", "upconv", [("x", (2, 4, 4, 16))], dict(channels=8), 42, opt={"upsampling_method": "deconv3"}),
+    _c("upconv_deconv6", "upconv", [("x", (2, 4, 4, 16))], dict(channels=8), 42, opt={"upsampling_method": "deconv6"}),
+    _c("upconv_subpixel2", "upconv", [("x", (2, 4, 4, 16))], dict(channels=8), 42, opt={"upsampling_method": "subpixel2"}),
+    _c("upconv_subpixel3", "upconv", [("x", (2, 4, 4, 16))], dict(channels=8), 42, opt={"upsampling_method": "subpixel3"}),
+    _c("upconv_resize_conv", "upconv", [("x", (2, 4, 4, 16))], dict(channels=8), 42, opt={"upsampling_method": "resize_conv"}),
+    _c("upconv_nn", "upconv", [("x", (2, 4, 4, 16))], dict(channels=8), 42, opt={"upsampling_method": "nn"}),
+    _c("g_conv_deconv4", "g_conv", [("x", (2, 8, 8, 16))], dict(channels=8), 43, opt={"g_conv": "deconv4"}),
+    _c("g_conv_conv3", "g_conv", [("x", (2, 8, 8, 16))], dict(channels=8), 43, opt={"g_conv": "conv3"}),
+    _c("g_conv_conv5", "g_conv", [("x", (2, 8, 8, 16))], dict(channels=8), 43, opt={"g_conv": "conv5"}),
+    _c("downconv_resize_conv1", "downconv", [("x", (2, 8, 8, 16))], dict(channels=8), 44, opt={"downsampling_method": "resize_conv1"}),
+    _c("downconv_resize_conv3", "downconv", [("x", (2, 8, 8, 16))], dict(channels=8), 44, opt={"downsampling_method": "resize_conv3"}),
+    _c("downconv_pool_only", "downconv", [("x", (2, 8, 8, 16))], dict(channels=16), 44, opt={"downsampling_method": "pool_only"}),
+    _c("downconv_max_pool_only", "downconv", [("x", (2, 8, 8, 16))], dict(channels=16), 44, opt={"downsampling_method": "max_pool_only"}),
+    _c("resblock_down_resize_conv1", "resblock_down", [("x", (2, 8, 8, 16))], dict(channels=32, use_bias=False, scope="resblock_down_1"), 45,
+       opt={"downsampling_method": "resize_conv1"}),
+    _c("resblock_down_bn_in_d", "resblock_down", [("x", (3, 8, 8, 16))], dict(channels=32, use_bias=True, scope="resblock_down_1"), 46,
+       opt={"bn_in_d": True}),
+    _c("resblock_bn_in_d_prelu", "resblock", [("x", (3, 4, 4, 16))], dict(channels=16, use_bias=False), 47, opt={"bn_in_d": True, "act": "prelu"},
+       var_init={"resblock/res1/prelu/alpha": [0.2] * 16}),
+    _c("resblock_up_condition_prelu", "resblock_up_condition", [("x", (2, 4, 4, 32)), ("z", (2, 1, 1, 12))],
+       dict(channels=16, use_bias=False, scope="resblock_up_4"), 48, opt={"act": "prelu"},
+       var_init={"resblock_up_4/res1/prelu/alpha": [0.3] * 32, "resblock_up_4/res2/prelu/alpha": [-0.2] * 16}),
+    _c("resblock_up_condition_lrelu_subpixel3_conv5", "resblock_up_condition", [("x", (2, 4, 4, 32)), ("z", (2, 1, 1, 12))],
+       dict(channels=16, use_bias=True, scope="resblock_up_4"), 49, opt={"act": "lrelu", "upsampling_method": "subpixel3", "g_conv": "conv5"}),
+]
+
 # names of inputs that stay fp32 on the CUDA side in bf16 mode (the CBN condition vector)
 FP32_INPUTS = ("z",)
 
@@ -103,6 +135,16 @@ NETS = {
     "net512": dict(img_size=512, ch=8, batch_size=2, n_labels=4, z_dim=64, sa_gamma_init=0.1),
 }
 NET64 = NETS["net64"]
+
+# the fork's CLI defaults on top of the hinge configuration: prelu, ortho_cosine regulariser, flood levels,
+# DiffAugment 'full' (main.py:49-50, :63, :66-67, :80)
+NEXT_NETS = {
+    "net64cli": dict(img_size=64, ch=16, batch_size=4, n_labels=6, z_dim=128, sa_gamma_init=0.1, da_policy="color,translation,cutout",
+                     activation="prelu", g_regularization="ortho_cosine", g_regularization_factor=1e-4, d_flood=0.1, g_flood=0.05),
+    "net64variants": dict(img_size=64, ch=16, batch_size=4, n_labels=6, z_dim=128, sa_gamma_init=0.1, activation="lrelu",
+                          upsampling_method="resize_conv", g_conv="conv3", downsampling_method="resize_conv1", bn_in_d=True,
+                          g_regularization="ortho", g_regularization_factor=1e-4),
+}
 
 
 WHOLE_LIMIT = 4096      # golden arrays up to this size are stored whole; larger ones as a strided sample + sum + norm
@@ -144,6 +186,10 @@ def check(gold, key, value, tol, what=None, l2=False):
     else:
         err = float(np.abs(v - ref).max()) / scale
     assert err <= tol + store_eps, "%s: error %.3e > %.1e" % (what, err, tol)
+
+
+def golden_absmax(gold, key):
+    return float(np.abs(gold[key] if key in gold.files else gold[key + "#sub"]).max())
 
 
 def case_inputs(case):
