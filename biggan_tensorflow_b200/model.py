@@ -9,8 +9,9 @@ import torch
 
 from . import _lib
 from .ops import (bn, cast, compute_dtype, rgb_pad, constant_initializer, conv, fully_connected, get_variable,
-                  global_sum_pooling, relu, reshape, resblock, resblock_down, resblock_up_condition,
+                  global_sum_pooling, lrelu, prelu, relu, reshape, resblock, resblock_down, resblock_up_condition,
                   round_up, self_attention_2, variable_scope)
+from .utils import orthogonal_regularizer, orthogonal_regularizer_fc
 from .tensor import F32, Tensor
 
 
@@ -36,6 +37,15 @@ class Config:
     d_cls_loss_weight: float = 5.0
     g_cls_loss_weight: float = 1.0
     sa_gamma_init: float = 0.0     # ops.py:486 initialises to 0; parity tests use 0.1
+    # SURVEY 8(f) "next" rows: the fork's CLI-default extras and layer variants (main.py:49-67)
+    activation: str = "relu"                    # relu | prelu | lrelu            (BigGAN.py:71-84)
+    upsampling_method: str = "deconv4"          # ops.py:200-218
+    downsampling_method: str = "strided_conv3"  # ops.py:269-291
+    g_conv: str = "deconv3"                     # ops.py:220-230
+    bn_in_d: bool = False
+    g_regularization: str = "none"              # none | ortho | ortho_cosine    (BigGAN.py:257-271)
+    g_regularization_factor: float = 1e-4
+    virtual_batches: int = 1                    # gradient accumulation, utils.py:242-267
 
     @property
     def depth(self):
@@ -70,14 +80,35 @@ _D_BLOCKS = {      # BigGAN.py:607-610
 }
 
 
+def _lrelu_02(x):
+    return lrelu(x, 0.2)
+
+
+def activation_fn(cfg):
+    """BigGAN.py:71-84."""
+    if cfg.activation == 'relu':
+        return relu
+    if cfg.activation == 'prelu':
+        return prelu
+    if cfg.activation == 'lrelu':
+        return _lrelu_02
+    raise ValueError("Unknown activation function: " + str(cfg.activation))
+
+
 def _opts(cfg, is_training):
     bn_options = {"type": "batch_norm", "momentum": cfg.bn_momentum}            # GANBase.py:39-41
     conv_options = {"padding_type": "reflect", "sn": True, "regularizer": None}  # GANBase.py:49-51
-    g_opt = {"sn": True, "is_training": is_training, "upsampling_method": "deconv4", "g_conv": "deconv3",
-             "act": relu, "self_attention_bias": True, "bn": copy.deepcopy(bn_options),
+    act = activation_fn(cfg)
+    g_opt = {"sn": True, "is_training": is_training, "upsampling_method": cfg.upsampling_method, "g_conv": cfg.g_conv,
+             "act": act, "self_attention_bias": True, "bn": copy.deepcopy(bn_options),
              "conv": copy.deepcopy(conv_options), "fc_regularizer": None}        # BigGAN.py:248-274
-    d_opt = {"sn": True, "is_training": is_training, "bn_in_d": False, "act": relu,
-             "downsampling_method": "strided_conv3", "self_attention_bias": True,
+    if is_training and cfg.g_regularization != 'none':                          # BigGAN.py:257-271
+        if cfg.g_regularization not in ('ortho', 'ortho_cosine'):
+            raise ValueError("Unknown regularization method: " + str(cfg.g_regularization))
+        g_opt["conv"]["regularizer"] = orthogonal_regularizer(cfg.g_regularization_factor, type=cfg.g_regularization)
+        g_opt["fc_regularizer"] = orthogonal_regularizer_fc(cfg.g_regularization_factor, type=cfg.g_regularization)
+    d_opt = {"sn": True, "is_training": is_training, "bn_in_d": cfg.bn_in_d, "act": act,
+             "downsampling_method": cfg.downsampling_method, "self_attention_bias": True,
              "bn": copy.deepcopy(bn_options), "conv": copy.deepcopy(conv_options)}  # BigGAN.py:593-600
     return g_opt, d_opt
 
@@ -117,9 +148,15 @@ def generator(cfg, z, cls_z, is_training=True):
         ch_mul = 2 ** (n_blocks - 1)
         ch = round_up(int(cfg.ch * 2.0 ** (n_blocks - 1)), 8)                   # :428
         f_width = round_up((split_sizes[0] + cfg.n_labels) * 1.85, 8)           # :433
-        x = fully_connected(z_split[0], units=f_width, scope='dense1', opt=opt)  # :436
-        x = relu(x)
-        x = fully_connected(x, units=4 * 4 * ch, scope='dense2', opt=opt)       # :438
+        if opt["act"] is relu:                                                  # :434 (no scope, backward compatibility)
+            x = fully_connected(z_split[0], units=f_width, scope='dense1', opt=opt)  # :436
+            x = relu(x)
+            x = fully_connected(x, units=4 * 4 * ch, scope='dense2', opt=opt)   # :438
+        else:
+            with variable_scope('first'):                                       # :440-443
+                x = fully_connected(z_split[0], units=f_width, scope='dense1', opt=opt)
+                x = opt["act"](x)
+                x = fully_connected(x, units=4 * 4 * ch, scope='dense2', opt=opt)
         x = reshape(x, [-1, 4, 4, ch])                                          # :446
         x = cast(x, compute_dtype())
         zi = 1
@@ -137,7 +174,10 @@ def generator(cfg, z, cls_z, is_training=True):
                 x = _attention(cfg, x, ch, opt)                                 # :482-483
             ch = round_up(int(cfg.ch * 2.0 ** (n_blocks - b_i - 1)), 8)
             ch_mul = ch_mul // 2
-        x = bn(x, opt=opt, _act=_lib.ACT_RELU)                                  # :491-492 (BN + act fused)
+        if opt["act"] is relu:
+            x = bn(x, opt=opt, _act=_lib.ACT_RELU)                              # :491-492 (BN + act fused)
+        else:
+            x = opt["act"](bn(x, opt=opt))
         # bf16 tensor-core mode: the image is produced with zero-padded channels (3 -> 16) so that G_logit and
         # D's first convs are tcgen05 GEMMs; `ops.slice_channels(x, 3)` gives the plain RGB tensor
         x = conv(x, channels=cfg.c_dim, kernel=3, stride=1, pad=1, use_bias=False, opt=opt, scope='G_logit',
@@ -169,7 +209,10 @@ def discriminator(cfg, x, is_training=True):
             ch_mul = ch_mul * 2
         ch = round_up(int(cfg.ch * 2.0 ** (b_i - 1)), 8)                        # :666
         x = resblock(x, channels=ch, use_bias=False, opt=opt, scope='resblock')  # :668
-        features = global_sum_pooling(x, _relu_first=True)                      # :669-671
+        if opt["act"] is relu:
+            features = global_sum_pooling(x, _relu_first=True)                  # :669-671
+        else:
+            features = global_sum_pooling(opt["act"](x))
         features = cast(features, F32)
         x = fully_connected(features, units=1, opt=opt, scope='D_logit')        # :681-684
         outputs["real"] = x

@@ -401,7 +401,8 @@ def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True,
         if not opt.get("conv", {}).get("sn", True):
             raise ValueError("conv with sn=False (tf.layers.conv2d path) is not supported")
         cin_x, cin = x.shape[-1], c_real(x)          # x may carry zero-padded channels (RGB tensors)
-        w = get_variable("kernel", shape=[kernel, kernel, cin, channels], initializer=weight_init)
+        reg = opt.get("conv", {}).get("regularizer", None) if 'generator' in current_scope_name() else None   # ops.py:87-92
+        w = get_variable("kernel", shape=[kernel, kernel, cin, channels], initializer=weight_init, regularizer=reg)
         c_pad = round_up(channels, _pad_cout_to) if _pad_cout_to else channels
         if (cin == 3 and cin_x != cin and x.dtype == BF16 and c_pad % 16 == 0 and kernel * kernel * 3 <= 32
                 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1):
@@ -446,7 +447,8 @@ def deconv(x, channels, opt, kernel=4, stride=2, padding='SAME', use_bias=True, 
         p = tot // 2
         desc = ConvDesc(B, H, W, Cin, Ho, Wo, channels, kernel, kernel, stride, p, p, tot - p, tot - p,
                         _lib.PAD_ZERO, 1)
-        w = get_variable("kernel", shape=[kernel, kernel, channels, Cin], initializer=weight_init)
+        w = get_variable("kernel", shape=[kernel, kernel, channels, Cin], initializer=weight_init,
+                         regularizer=opt.get("conv", {}).get("regularizer", None))                                # ops.py:127
         wn = _sn_weight(w, kernel * kernel, False, x.dtype)
         bias = None
         if use_bias:
@@ -456,7 +458,7 @@ def deconv(x, channels, opt, kernel=4, stride=2, padding='SAME', use_bias=True, 
 
 def get_variable_with_custom_lr(name, shape, regularizer, lrmul):
     """ops.py:141-146 (lrmul == 1 on the hot path)."""
-    w = get_variable(name, shape, initializer=truncated_normal_initializer(mean=0.0, stddev=0.02 / lrmul))
+    w = get_variable(name, shape, initializer=truncated_normal_initializer(mean=0.0, stddev=0.02 / lrmul), regularizer=regularizer)
     if lrmul == 1.0:
         return w
     return scale(w, lrmul)
@@ -485,13 +487,15 @@ def fully_connected(x, units, opt, use_bias=True, lrmul=1.0, scope='fully_0'):
               and channels % 8 == 0 and channels >= 16 and units % 16 == 0)
         x = cast(x, BF16 if tc else F32)
         if sn:
-            w = get_variable_with_custom_lr("kernel", shape=[channels, units], regularizer=None, lrmul=lrmul)
+            reg = opt.get("fc_regularizer", None) if 'generator' in current_scope_name() else None             # ops.py:155-158
+            w = get_variable_with_custom_lr("kernel", shape=[channels, units], regularizer=reg, lrmul=lrmul)
             if use_bias:
                 bias = get_variable("bias", [units], initializer=constant_initializer(0.0))
             wn = _sn_weight(w, 1, True, BF16) if tc else spectral_norm(w, _out_dtype=F32)
         else:
             with variable_scope("dense"):                                      # tf.layers.dense (:167-173)
-                wn = get_variable("kernel", shape=[channels, units], initializer=weight_init)
+                reg = opt.get("fc_regularizer", None) if 'generator' in current_scope_name() else None
+                wn = get_variable("kernel", shape=[channels, units], initializer=weight_init, regularizer=reg)
                 if use_bias:
                     bias = get_variable("bias", [units], initializer=constant_initializer(0.0))
         x4 = reshape(x, [Bn, 1, 1, channels])
@@ -531,6 +535,15 @@ def upconv(x, channels, opt, use_bias=True, _residual=None):
         return deconv(x, channels, kernel=4, stride=2, use_bias=use_bias, opt=opt, _residual=_residual)
     elif m == 'deconv6':
         return deconv(x, channels, kernel=6, stride=2, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif m == 'subpixel2':
+        return _plus(subpixel_conv(x, channels, kernel=2, scale=2, use_bias=use_bias, opt=opt), _residual)
+    elif m == 'subpixel3':
+        return _plus(subpixel_conv(x, channels, kernel=3, scale=2, use_bias=use_bias, opt=opt), _residual)
+    elif m == 'resize_conv':
+        x = up_sample(x, 2)
+        return conv(x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif m == 'nn':
+        return _plus(up_sample(x, 2), _residual)
     else:
         raise ValueError("Invalid upsampling method specified: " + str(opt["upsampling_method"]))
 
@@ -544,6 +557,8 @@ def g_conv(x, channels, opt, use_bias=True, _residual=None):
         return deconv(x, channels, kernel=4, stride=1, use_bias=use_bias, opt=opt, _residual=_residual)
     elif m == 'conv3':
         return conv(x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif m == 'conv5':
+        return conv(x, channels, kernel=5, stride=1, pad=2, use_bias=use_bias, opt=opt, _residual=_residual)
     else:
         raise ValueError("Invalid generator convolution type specified: " + str(opt["g_conv"]))
 
@@ -574,6 +589,18 @@ def downconv(x, channels, opt, use_bias=True, method=None, _residual=None):
         method = opt["downsampling_method"]
     if method == 'strided_conv3':
         return conv(x, channels, kernel=3, stride=2, pad=1, use_bias=use_bias, opt=opt, _residual=_residual)
+    elif method == 'resize_conv1':
+        x = conv(x, channels, kernel=1, stride=1, pad=0, use_bias=use_bias, opt=opt)
+        return _plus(avg_pooling(x), _residual)
+    elif method == 'resize_conv3':
+        x = conv(x, channels, kernel=3, stride=1, pad=1, use_bias=use_bias, opt=opt)
+        return _plus(avg_pooling(x), _residual)
+    elif method == 'resize_conv35':
+        raise ValueError("channel-sliced multi-kernel conv (ops.py:52-59) is out of scope")
+    elif method == 'pool_only':
+        return _plus(avg_pooling(x), _residual)
+    elif method == 'max_pool_only':
+        return _plus(max_pooling(x), _residual)
     else:
         raise ValueError("Invalid downsampling method specified: " + str(method))
 
@@ -592,7 +619,7 @@ def resblock_down(x_init, channels, opt, use_bias=True, scope='resblock_down'):
             res_method = opt["downsampling_method"]
             if res_method != 'strided_conv3':
                 res_method = 'resize_conv3'
-            fuse = opt["act"] is relu and not opt["bn_in_d"]
+            fuse = opt["act"] is relu and not opt["bn_in_d"] and res_method == 'strided_conv3'
             if fuse:
                 x = conv(x, channels, kernel=3, stride=2, pad=1, use_bias=use_bias, opt=opt, _act=_lib.ACT_RELU)
             else:
@@ -809,6 +836,121 @@ def relu(x):
                 fin()
         record(bw)
     return y
+
+
+def _plus(x, residual):
+    return x if residual is None else add(x, residual)
+
+
+def _keep_c_real(y, x):
+    y.aux = x.aux if isinstance(x.aux, dict) and "c_real" in x.aux else None
+    return y
+
+
+def lrelu(x, alpha=0.2):
+    """ops.py:525-526 (tf.nn.leaky_relu)."""
+    y = _keep_c_real(Tensor(empty(x.shape, x.dtype), requires_grad=x.requires_grad), x)
+    call("bg_lrelu_fwd", x.data, y.data, x.numel(), float(alpha), bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_lrelu_bwd", x.data, y.grad, dst, x.numel(), float(alpha), bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+def prelu(x, scope=None, init_val=0.0):
+    """ops.py:532-537: relu(x) + alpha * (x - |x|) / 2 with one trainable alpha per channel, created under
+    '<scope>/alpha' ('prelu', 'prelu_1', ... within the enclosing scope when no scope is given)."""
+    with variable_scope(scope, default_name="prelu"):
+        C, Cx = c_real(x), x.shape[-1]
+        alphas = get_variable('alpha', [C], initializer=constant_initializer(init_val))
+        a_dev = alphas.data
+        if Cx != C:                  # zero-padded image tensor (bf16 tensor-core mode): the pad channels are 0 and stay 0
+            a_dev = torch.zeros(Cx, dtype=F32, device=x.data.device)
+            a_dev[:C].copy_(alphas.data)
+        npix = x.numel() // Cx
+        y = _keep_c_real(Tensor(empty(x.shape, x.dtype), requires_grad=x.requires_grad or alphas.requires_grad), x)
+        call("bg_prelu_fwd", x.data, a_dev, y.data, npix, Cx, bg_dtype(x), stream())
+        if recording(x, alphas):
+            def bw():
+                if y.grad is None:
+                    return
+                dx, fin = grad_target(x) if x.requires_grad else (None, None)
+                da = empty([Cx], F32)
+                ws = workspace(query("bg_prelu_workspace_bytes", npix, Cx))
+                call("bg_prelu_bwd", x.data, a_dev, y.grad, dx, da, 0, npix, Cx, bg_dtype(x), ws, ws.numel(), stream())
+                if fin:
+                    fin()
+                if alphas.requires_grad:
+                    accumulate_grad(alphas, da[:C].contiguous() if Cx != C else da, own=True)
+            record(bw)
+        return y
+
+
+def avg_pooling(x):
+    """ops.py:512-514: tf.layers.average_pooling2d(2, 2, 'SAME') (even maps)."""
+    B, H, W, C = x.shape
+    y = _keep_c_real(Tensor(empty([B, H // 2, W // 2, C], x.dtype), requires_grad=x.requires_grad), x)
+    call("bg_avgpool2_fwd", x.data, y.data, B, H, W, C, bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_avgpool2_bwd", y.grad, dst, B, H, W, C, bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+def up_sample(x, scale_factor=2):
+    """ops.py:516-519: tf.image.resize_nearest_neighbor to scale_factor times the size."""
+    if scale_factor != 2:
+        raise ValueError("up_sample: only scale_factor=2 is supported")
+    B, H, W, C = x.shape
+    y = _keep_c_real(Tensor(empty([B, 2 * H, 2 * W, C], x.dtype), requires_grad=x.requires_grad), x)
+    call("bg_upsample2_fwd", x.data, y.data, B, H, W, C, bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_upsample2_bwd", y.grad, dst, B, H, W, C, bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+def depth_to_space(x, block_size):
+    """tf.nn.depth_to_space (NHWC)."""
+    B, H, W, C = x.shape
+    r = int(block_size)
+    y = Tensor(empty([B, H * r, W * r, C // (r * r)], x.dtype), requires_grad=x.requires_grad)
+    call("bg_depth_to_space", x.data, y.data, B, H, W, C, r, 0, bg_dtype(x), stream())
+    if recording(x):
+        def bw():
+            if y.grad is None:
+                return
+            dst, fin = grad_target(x)
+            call("bg_depth_to_space", y.grad, dst, B, H, W, C, r, 1, bg_dtype(x), stream())
+            if fin:
+                fin()
+        record(bw)
+    return y
+
+
+def subpixel_conv(x, channels, opt, kernel=3, scale=2, use_bias=True, scope='subpixel_conv_0'):
+    """ops.py:23-27."""
+    r2 = scale * scale
+    x = conv(x, channels * r2, opt=opt, kernel=kernel, stride=1, use_bias=use_bias, pad=(kernel - 1) / 2.0, scope=scope)
+    return depth_to_space(x, block_size=scale)
 
 
 def tanh(x):

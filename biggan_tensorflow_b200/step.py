@@ -99,6 +99,9 @@ class Trainer:
                           for net in ("generator", "discriminator")}
         if cfg.acgan:
             self.cls_weights = torch.ones(cfg.n_labels, device=dev)            # BigGAN.py:100
+        # one regularisation loss per generator weight created with a regulariser (BigGAN.py:257-271, :897-898)
+        self.regs = [(self.store.vars[n], r) for n, r in self.store.regularizers.items()]
+        self.reg_loss = None
         self.store.begin_phase()
         clear_tape()
         self._built = True
@@ -134,6 +137,13 @@ class Trainer:
         for v in ar["vars"]:
             if not v.grad_set:
                 v.grad_view.zero_()
+        self.reg_loss = None
+        if net == "generator" and self.regs:
+            # g_loss += sum of the regularisation losses (BigGAN.py:897-898).  Every rank holds the same weights and the
+            # gradient arenas are summed across ranks afterwards, so each rank adds 1/world of the regulariser's gradient.
+            self.reg_loss = torch.zeros(1, dtype=torch.float32, device=ar["grads"].device)
+            for v, reg in self.regs:
+                reg.evaluate(v.data, self.reg_loss, dW=v.grad_view, grad_scale=1.0 / self.world)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(ar["grads"], group=self.pg)          # NCCL over NVLink; sum == global-batch gradient
@@ -168,11 +178,22 @@ class Trainer:
             aug_fake = DiffAugment_tf.DiffAugment(fake, policy=cfg.da_policy)                       # :857
             x = Tensor(torch.cat([aug_real.data, aug_fake.data], dim=0))
             x.aux = aug_fake.aux
-        # D(real) and D(fake) share weights and have no batch statistics -> one pass over [real; fake]
-        out = discriminator(cfg, x)
-        real_logits, fake_logits = split_rows(out["real"], [Bl, Bl])
+        if cfg.bn_in_d:
+            # batch statistics inside D: the two instantiations (BigGAN.py:807, :857) normalise their own batch, so they
+            # cannot share one pass.  The moving statistics take the two updates in this order (TF leaves it unspecified).
+            out_r = discriminator(cfg, aug_real)
+            out_f = discriminator(cfg, aug_fake)
+            real_logits, fake_logits = out_r["real"], out_f["real"]
+            out = {"cls": out_r.get("cls")}
+        else:
+            # D(real) and D(fake) share weights and have no batch statistics -> one pass over [real; fake]
+            out = discriminator(cfg, x)
+            real_logits, fake_logits = split_rows(out["real"], [Bl, Bl])
         d_loss = ops.discriminator_loss(cfg.gan_type, real=real_logits, fake=fake_logits, flood_level=cfg.d_flood)   # :879
-        if cfg.acgan:
+        if cfg.acgan and cfg.bn_in_d:
+            cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
+            d_loss = d_loss + cfg.d_cls_loss_weight * cls_loss(labels, out["cls"])                 # :853
+        elif cfg.acgan:
             real_cls, _ = split_rows(out["cls"], [Bl, Bl])
             cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
             d_loss = d_loss + cfg.d_cls_loss_weight * cls_loss(labels, real_cls)                   # :853
@@ -197,15 +218,68 @@ class Trainer:
             g_loss = g_loss + cfg.g_cls_loss_weight * cls_loss(cls_z, out["cls"])                  # :894
         backward([(g_loss, torch.ones(1, device=z.device))])
         self._finish_grads("generator")
+        loss = g_loss.data
+        if self.reg_loss is not None:
+            loss = torch.empty_like(g_loss.data)
+            call("bg_add", g_loss.data, self.reg_loss, loss, 1, _lib.BG_F32, stream())
         if apply:
             self._adam("generator", cfg.g_lr)
-        return g_loss.data, {"fake": fake, "fake_logits": out["real"]}
+        return loss, {"fake": fake, "fake_logits": out["real"]}
 
     def train_step(self, real, labels, z_d, z_g, cls_z):
         """One iteration: D update, then G update (n_critic = 1, BigGAN.py:1080)."""
         d_loss, _ = self.d_update(real, labels, z_d, cls_z)
         g_loss, _ = self.g_update(z_g, cls_z)
         return d_loss, g_loss
+
+    # ------------------------------------------------------------------------------------------
+    # SURVEY 8(f): gradient accumulation over virtual batches, sampling with the EMA weights
+    # ------------------------------------------------------------------------------------------
+    def _accumulated_update(self, net, lr, run_one, batches):
+        """utils.virtual_batch_steps (utils.py:242-250): zero the accumulators, one gradient evaluation per virtual batch
+        (each its own run: spectral-norm `u` and BN statistics advance every time), then ONE optimizer step on acc / k."""
+        k = len(batches)
+        ar = self.store.arenas[net]
+        n = ar["grads"].numel()
+        acc = torch.zeros_like(ar["grads"])
+        losses = []
+        for b in batches:
+            loss, _ = run_one(*b, apply=False)
+            losses.append(loss)
+            call("bg_add", acc, ar["grads"], acc, n, _lib.BG_F32, stream())
+        call("bg_axpby", acc, None, None, 1.0 / k, 0.0, ar["grads"], n, _lib.BG_F32, stream())
+        self._adam(net, lr)
+        return losses
+
+    def d_update_virtual(self, batches):
+        """batches: list of (real, labels, z, cls_z), len == cfg.virtual_batches."""
+        return self._accumulated_update("discriminator", self.cfg.d_lr, self.d_update, batches)
+
+    def g_update_virtual(self, batches):
+        """batches: list of (z, cls_z)."""
+        return self._accumulated_update("generator", self.cfg.g_lr, self.g_update, batches)
+
+    def sample(self, z, cls_z, ema=True):
+        """Generator in inference mode (is_training=False: population BN statistics, BigGAN.py:771-787) with the EMA
+        shadow weights swapped in (MovingAverageOptimizer.swapping_saver semantics) when ema=True.  Returns the image
+        tensor [B, S, S, 3(+pad)].  Spectral norm still advances `u` (ops.py:743 has no training switch)."""
+        if not self._built:
+            self.build()
+        ar, o = self.store.arenas["generator"], self.opt["generator"]
+        saved = None
+        if ema and o["ema"] is not None:
+            saved = ar["params"].clone()
+            ar["params"].copy_(o["ema"])
+        try:
+            self.store.begin_phase()
+            clear_tape()
+            self.sn_groups["generator"].forward(self.store)
+            with no_grad():
+                img = generator(self.cfg, z, cls_z, is_training=False)
+        finally:
+            if saved is not None:
+                ar["params"].copy_(saved)
+        return img
 
     def grads(self, net):
         ar = self.store.arenas[net]

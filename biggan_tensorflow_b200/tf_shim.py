@@ -66,6 +66,8 @@ class VariableStore:
         self.scope = []
         self.sn_cache = {}       # per update-phase cache: one spectral_norm evaluation per variable
         self.arenas = {}
+        self.regularizers = {}   # full variable name -> regularizer (tf REGULARIZATION_LOSSES: one entry per variable)
+        self.default_names = {}  # parent scope -> {base: count} for variable_scope(None, default_name=...)
 
     def full_name(self, name=None):
         parts = list(self.scope)
@@ -73,8 +75,10 @@ class VariableStore:
             parts.append(name)
         return "/".join(parts)
 
-    def get_variable(self, name, shape, initializer=None, trainable=True, dtype=None):
+    def get_variable(self, name, shape, initializer=None, trainable=True, dtype=None, regularizer=None):
         full = self.full_name(name)
+        if regularizer is not None:
+            self.regularizers[full] = regularizer
         v = self.vars.get(full)
         shape = tuple(int(s) for s in shape)
         if v is None:
@@ -139,19 +143,32 @@ def set_store(store):
 
 
 @contextlib.contextmanager
-def variable_scope(name, reuse=None, **_unused):
+def variable_scope(name=None, reuse=None, default_name=None, name_or_scope=None, **_unused):
     """tf.variable_scope: pushes `name`; `reuse` is accepted for signature parity (get_variable
-    always returns the existing variable of that name, like reuse=tf.AUTO_REUSE)."""
+    always returns the existing variable of that name, like reuse=tf.AUTO_REUSE).  With name None the
+    `default_name` is made unique within the parent scope the way TF does ('prelu', 'prelu_1', ...; ops.py:533);
+    the counters of everything below a scope are reset when the scope is left, so a second instantiation of a
+    network names its default scopes identically."""
     st = _STORE
+    if name is None:
+        name = name_or_scope
+    if name is None:
+        d = st.default_names.setdefault(st.full_name(), {})
+        k = d.get(default_name, 0)
+        d[default_name] = k + 1
+        name = default_name if k == 0 else "%s_%d" % (default_name, k)
     st.scope.append(name)
     try:
         yield st
     finally:
+        full = st.full_name()
+        for key in [key for key in st.default_names if key == full or key.startswith(full + "/")]:
+            del st.default_names[key]
         st.scope.pop()
 
 
 def get_variable(name, shape=None, initializer=None, trainable=True, dtype=None, regularizer=None):
-    return _STORE.get_variable(name, shape, initializer, trainable, dtype)
+    return _STORE.get_variable(name, shape, initializer, trainable, dtype, regularizer)
 
 
 def current_scope_name():

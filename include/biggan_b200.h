@@ -247,6 +247,32 @@ int bg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, l
 int bg_adam_lr_step(float* state, float lr, float beta1, float beta2, void* stream);
 int bg_fill(void* p, float value, long n, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY 8(f) "next" rows (next_ops.cu): the fork's CLI-default extras and layer variants.
+ *   lrelu ops.py:525-526, prelu :532-537 (alpha [C] fp32), avg_pooling :512-514, up_sample :516-519,
+ *   tf.nn.depth_to_space of subpixel_conv :23-27, orthogonal regularisers utils.py:185-235.
+ * ------------------------------------------------------------------------------------------- */
+int bg_lrelu_fwd(const void* x, void* y, long n, float alpha, int dtype, void* stream);
+int bg_lrelu_bwd(const void* x, const void* dy, void* dx, long n, float alpha, int dtype, void* stream);
+size_t bg_prelu_workspace_bytes(long npix, int C);
+int bg_prelu_fwd(const void* x, const float* alpha, void* y, long npix, int C, int dtype, void* stream);
+/* dx may be NULL; dalpha [C] fp32 is overwritten (accumulate = 0) or added to (accumulate = 1) */
+int bg_prelu_bwd(const void* x, const float* alpha, const void* dy, void* dx, float* dalpha, int accumulate,
+                 long npix, int C, int dtype, void* ws, size_t ws_bytes, void* stream);
+/* x [B,H,W,C] -> y [B,H/2,W/2,C] (even H, W); the backward takes the INPUT size H, W */
+int bg_avgpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+int bg_avgpool2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+/* x [B,H,W,C] -> y [B,2H,2W,C] nearest neighbour; the backward sums the 2x2 windows of dy into dx [B,H,W,C] */
+int bg_upsample2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+int bg_upsample2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+/* deep [B,H,W,C] <-> shallow [B,H*r,W*r,C/r^2]; inverse = 0: src deep -> dst shallow (forward), 1: the adjoint */
+int bg_depth_to_space(const void* src, void* dst, int B, int H, int W, int C, int r, int inverse, int dtype,
+                      void* stream);
+/* G [C,C] fp32 = W^T W.  kind 0 'ortho' / 1 'ortho_cosine'.  Writes dLoss/dG, per-row loss terms (rowloss [C]),
+ * and loss[0] (= or += scale * l2_loss(reg)).  dLoss/dW = W (dG + dG^T) is left to the caller (bg_bgemm). */
+int bg_ortho_reg_rows(const float* G, float* dG, float* rowloss, float* loss, int accumulate, int C,
+                      float scale, int kind, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,8 +19,20 @@ TOL_SCALE = {"cbn_relu_4x4x64": (2.0, 2.0), "cbn_relu_8x8x32": (2.0, 2.0), "bn_t
 FP32_ONLY = {"fc_sn", "fc_dense", "cbn_inference", "sa_full_4x4x32"}     # as in tests/test_ops_gpu.py
 
 
+UNVERIFIED = pytest.mark.skipif(
+    os.environ.get("BG_RUN_UNVERIFIED") != "1",
+    reason="written after the round-1 GPU budget was spent: this code path compiles and its oracle side is pinned to the reference "
+           "source on CPU, but it has not run on hardware yet; enable with BG_RUN_UNVERIFIED=1")
+
+
+def _acts(ops):
+    return {"relu": ops.relu, "prelu": ops.prelu, "lrelu": lambda x: ops.lrelu(x, 0.2)}
+
+
 def _product_call(case, ops, _lib, xs, opt):
     fn, kw = case["fn"], dict(case["kw"])
+    if fn in ("prelu", "lrelu"):
+        return getattr(ops, fn)(*xs.values())
     if fn == "cond_bn" and case["relu_after"]:
         return ops.cond_bn(xs["x"], xs["z"], opt, _act=_lib.ACT_RELU)        # CBN + ReLU fused, as the resblocks call it
     y = getattr(ops, fn)(*xs.values(), **kw, opt=opt)
@@ -32,18 +44,30 @@ def _product_call(case, ops, _lib, xs, opt):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("case", C.OP_CASES, ids=[c["name"] for c in C.OP_CASES])
 def test_cuda_op_matches_reference_source(case, dtype):
-    from helpers import dev_tensor, new_product_store, seed_backward
-    from biggan_tensorflow_b200 import _lib, ops
     if dtype == torch.bfloat16 and case["name"] in FP32_ONLY:
         pytest.skip("fp32-only case (same split as tests/test_ops_gpu.py)")
-    g = gold("ref_ops.npz")
+    _cuda_op_case(case, dtype, "ref_ops.npz")
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+@pytest.mark.parametrize("case", C.NEXT_OP_CASES, ids=[c["name"] for c in C.NEXT_OP_CASES])
+def test_cuda_next_row_op_matches_reference_source(case):
+    """prelu / lrelu, up- and down-sampling and g_conv variants, bn_in_d (fp32 mode)."""
+    _cuda_op_case(case, torch.float32, "ref_ops_next.npz")
+
+
+def _cuda_op_case(case, dtype, fname):
+    from helpers import dev_tensor, new_product_store, seed_backward
+    from biggan_tensorflow_b200 import _lib, ops
+    g = gold(fname)
     p = case["name"]
     bf = dtype == torch.bfloat16
     tol = GPU_TOL[dtype] * TOL_SCALE.get(p, (1.0, 1.0))[1 if bf else 0]
     st = new_product_store(dtype)
     if case["var_init"]:
         st.load({k: np.asarray(v, np.float32) for k, v in case["var_init"].items()})
-    opt = C.make_opt(ops.relu, case["opt"])
+    opt = C.make_opt(_acts(ops), case["opt"])
     xs = {k: dev_tensor(v, torch.float32 if k in C.FP32_INPUTS else dtype) for k, v in C.case_inputs(case).items()}
     y = _product_call(case, ops, _lib, xs, opt)
     seed_backward(y, C.case_dy(case, tuple(y.shape)))
@@ -56,10 +80,11 @@ def test_cuda_op_matches_reference_source(case, dtype):
     ref_names = sorted(k.split("/varsum/")[1] for k in g.files if k.startswith(p + "/varsum/"))
     assert sorted(st.vars.keys()) == ref_names
     gkeys = sorted(set(k.split("#")[0] for k in g.files if k.startswith(p + "/gvar/")))
+    gscale = max([C.golden_absmax(g, k) for k in gkeys] + [0.0])
     for key in gkeys:
         n = key.split("/gvar/")[1]
-        if n.endswith("f_conv/bias"):
-            continue                                   # analytically zero; covered in tests/test_ops_gpu.py
+        if n.endswith("f_conv/bias") or C.golden_absmax(g, key) <= 1e-10 * gscale:
+            continue                                   # analytically zero (only rounding noise on both sides)
         pv = st.vars[n]
         assert pv.grad is not None, "no gradient reached variable " + n
         vtol = tol
@@ -113,12 +138,12 @@ def test_cuda_diffaugment_matches_reference_source(name, policy, shape):
     C.check(g, name + "/gx", tx.grad.float().cpu().numpy(), 1e-6 if exact else 1e-5)
 
 
-def _cuda_net(name, dtype=torch.float32):
+def _cuda_net(name, dtype=torch.float32, stol=2e-4):
     from biggan_tensorflow_b200 import DiffAugment_tf as D
     from biggan_tensorflow_b200.model import Config
     from biggan_tensorflow_b200.step import Trainer
     g = gold("ref_%s.npz" % name)
-    kw = C.NETS[name]
+    kw = C.NETS[name] if name in C.NETS else C.NEXT_NETS[name]
     b = M.synthetic_batch(M.Config(**kw), B=kw["batch_size"])
     tr = Trainer(Config(**kw), compute_dtype=dtype)
     tr.build()
@@ -134,7 +159,7 @@ def _cuda_net(name, dtype=torch.float32):
     state_g = tr.store.export()
     ref_shapes = {str(n): tuple(int(s) for s in str(sh).split(",") if s) for n, sh in zip(g["all_names"], g["all_shapes"])}
     assert {k: tuple(v.shape) for k, v in state_g.items()} == ref_shapes
-    check_net64(g, float(d_loss.cpu()), gd, None, state_d, float(g_loss.cpu()), gg, None, state_g, tol=1e-4, gtol=3e-4, stol=2e-4)
+    check_net64(g, float(d_loss.cpu()), gd, None, state_d, float(g_loss.cpu()), gg, None, state_g, tol=1e-4, gtol=3e-4, stol=stol)
 
 
 @pytest.mark.gpu
@@ -145,10 +170,79 @@ def test_cuda_network_matches_reference_generator_and_discriminator():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("BG_RUN_UNVERIFIED") != "1",
-                    reason="written without GPU access (round-1 GPU budget exhausted): narrow-channel 128/256/512 models take kernel shapes "
-                           "that have not run on hardware yet; enable with BG_RUN_UNVERIFIED=1")
+@UNVERIFIED
 @pytest.mark.parametrize("name", ["net128da", "net256", "net512"])
 def test_cuda_wiring_of_the_larger_configs_matches_reference(name):
-    """BASELINE configs 1-4 as wiring cases (block tables, attention placement, z split) at narrow width, fp32 mode."""
+    """BASELINE configs 1-4 as wiring cases (block tables, attention placement, z split) at narrow width, fp32 mode:
+    narrow-channel kernels shapes that have not run on hardware yet."""
     _cuda_net(name)
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+@pytest.mark.parametrize("name", list(C.NEXT_NETS))
+def test_cuda_next_row_networks_match_reference(name):
+    """the fork's CLI defaults (prelu, ortho_cosine, flood, DiffAugment) and the layer variants
+    (lrelu, resize_conv, conv3, resize_conv1, bn_in_d, ortho) on the CUDA path, fp32 mode.  With bn_in_d the moving
+    statistics of D take two updates per phase whose order TF leaves unspecified: O((1 - momentum)^2) slack on them."""
+    _cuda_net(name, stol=2e-4 if name == "net64cli" else 2e-3)
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+@pytest.mark.parametrize("kind", ["ortho", "ortho_cosine"])
+def test_cuda_orthogonal_regularizers_match_reference_source(kind):
+    """utils.py:180-235: loss and gradient for a conv-shaped and an FC-shaped weight."""
+    from helpers import dev_tensor, new_product_store
+    from biggan_tensorflow_b200 import utils
+    from biggan_tensorflow_b200.tensor import backward
+    g = gold("ref_ops.npz")
+    for wkey, lkey, gkey, fn in (("w4", "loss4", "g4", utils.orthogonal_regularizer), ("w2", "loss2", "g2", utils.orthogonal_regularizer_fc)):
+        new_product_store(torch.float32)
+        w = dev_tensor(g[kind + "/" + wkey].astype(np.float32))
+        L = fn(1e-4, type=kind)(w)
+        backward([(L, torch.ones(1, device="cuda"))])
+        torch.cuda.synchronize()
+        C.check(g, kind + "/" + lkey, L.numpy().reshape(()), 1e-4)
+        C.check(g, kind + "/" + gkey, w.grad.float().cpu().numpy(), 1e-4)
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_virtual_batches_and_ema_sampling():
+    """utils.virtual_batch_steps (utils.py:242-250): gradients of k virtual batches averaged, one Adam step -- against the
+    oracle doing the same; then the inference-mode generator with the EMA weights swapped in against the oracle's."""
+    from biggan_tensorflow_b200.model import Config
+    from biggan_tensorflow_b200.step import Trainer
+    from oracle import ref_ops as R
+    kw = dict(img_size=32, ch=32, batch_size=4, n_labels=10, sa_gamma_init=0.1)
+    cfg, rcfg = Config(virtual_batches=2, **kw), M.Config(**kw)
+    bs = [M.synthetic_batch(rcfg, B=4, seed=s) for s in (0, 10)]
+    tr = Trainer(cfg, compute_dtype=torch.float32)
+    tr.build()
+    dev = lambda a: torch.from_numpy(a).cuda()
+    tr.d_update_virtual([(dev(b["real"]), dev(b["labels"]), dev(b["z_d"]), dev(b["labels"])) for b in bs])
+    tr.g_update_virtual([(dev(b["z_g"]), dev(b["labels"])) for b in bs])
+    rs = R.RefStore(torch.float64)
+    for net, opt_state in (("D", M.AdamState(rcfg.d_lr, rcfg.beta1, rcfg.beta2)),
+                           ("G", M.AdamState(rcfg.g_lr, rcfg.beta1, rcfg.beta2, rcfg.moving_decay))):
+        acc = None
+        for b in bs:
+            if net == "D":
+                _, gd, _ = M.d_update(rs, rcfg, b["real"], b["labels"], b["z_d"], b["labels"], apply=False)
+            else:
+                _, gd, _ = M.g_update(rs, rcfg, b["z_g"], b["labels"], apply=False)
+            acc = gd if acc is None else {k: acc[k] + gd[k] for k in gd}
+        opt_state.apply(rs, {k: v / len(bs) for k, v in acc.items()})
+        og = opt_state
+    prod = tr.store.export()
+    from helpers import assert_close
+    for name, v in rs.vars.items():
+        if not rs.trainable.get(name, False):
+            assert_close(prod[name], v.detach().numpy(), 4e-4, "state " + name)
+    # sampling: EMA weights, population statistics
+    z, lab = bs[0]["z_g"], bs[0]["labels"]
+    img = tr.sample(dev(z), dev(lab), ema=True)
+    ema_store = R.RefStore(torch.float64, params={**rs.export(), **{k: v.numpy() for k, v in og.shadow.items()}})
+    ref = M.generator(ema_store, rcfg, torch.as_tensor(z, dtype=torch.float64), torch.as_tensor(lab, dtype=torch.float64), is_training=False)
+    assert_close(img.numpy()[..., :3], ref.detach().numpy(), 2e-4, "EMA sample")
