@@ -1,5 +1,10 @@
 // Shared helpers for libbiggan_b200 (sm_100a only).
 #pragma once
+#ifdef BG_HOST_EMULATION
+// CPU execution check of the simple kernels (tests/host_emul/cuda_host_emul.h, test infrastructure): never defined in the
+// product build (csrc/Makefile).
+#include "../../tests/host_emul/cuda_host_emul.h"
+#else
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -174,3 +179,7 @@ enum BgConvOp { BG_OP_FWD = 0, BG_OP_DGRAD = 1, BG_OP_WGRAD = 2 };
 // Builds the gather geometry of `op` for conv descriptor d.  For DGRAD with reflect padding the
 // output is the PADDED gradient (Ho/Wo = padded size); the caller folds it afterwards.
 int bg_build_geom(const bg_conv_desc* d, int op, BgGeom* g);
+
+// kernel launch on a stream (one spelling for nvcc and for the host emulation build of the simple kernels)
+#define BG_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif  // BG_HOST_EMULATION

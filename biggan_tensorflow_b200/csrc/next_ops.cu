@@ -5,6 +5,8 @@
 // at 16 CTAs per SM, deterministic fixed-order reductions (replica-consistent gradients).
 #include "bg_common.cuh"
 
+#include "next_ops_kernels.cuh"
+
 static inline int nx_blocks(long n) {
   long b = bg_cdiv(n, 256L);
   long mx = (long)bg_num_sms() * 16;
@@ -12,65 +14,17 @@ static inline int nx_blocks(long n) {
   if (b < 1) b = 1;
   return (int)b;
 }
-#define NX_LOOP(i, n) \
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x, _s = (long)gridDim.x * blockDim.x; i < (n); i += _s)
-
-// ------------------------------------------------------------------------------------------------------------
-// leaky relu: y = max(x, alpha x)  (tf.nn.leaky_relu);  dx = dy * (x > 0 ? 1 : alpha)  (LeakyReluGrad)
-// ------------------------------------------------------------------------------------------------------------
-template <typename T> __global__ void lrelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long n, float alpha) {
-  NX_LOOP(i, n) { const float v = bg_ld(x, i); bg_st(y, i, fmaxf(v, alpha * v)); }
-}
-template <typename T> __global__ void lrelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long n, float alpha) {
-  NX_LOOP(i, n) { const float g = bg_ld(dy, i); bg_st(dx, i, bg_ld(x, i) > 0.f ? g : alpha * g); }
-}
 extern "C" int bg_lrelu_fwd(const void* x, void* y, long n, float alpha, int dtype, void* stream) {
-  BG_DISPATCH_DTYPE(dtype, T, lrelu_fwd_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n, alpha));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(lrelu_fwd_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)x, (T*)y, n, alpha));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 extern "C" int bg_lrelu_bwd(const void* x, const void* dy, void* dx, long n, float alpha, int dtype, void* stream) {
-  BG_DISPATCH_DTYPE(dtype, T, lrelu_bwd_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy, (T*)dx, n, alpha));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(lrelu_bwd_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)x, (const T*)dy, (T*)dx, n, alpha));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// prelu (ops.py:532-537): y = relu(x) + alpha_c (x - |x|) / 2, alpha per channel (fp32 parameter).
-//   dx = dy * (x > 0 ? 1 : x < 0 ? alpha_c : alpha_c / 2);   dalpha_c = sum_pixels dy * min(x, 0)
-// The channel reduction is two fixed-order stages: each CTA sums a slab of pixels for every channel (threads along
-// the channel axis, coalesced), a second kernel adds the slabs in order.
-// ------------------------------------------------------------------------------------------------------------
-template <typename T> __global__ void prelu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ alpha, T* __restrict__ y, long n, int C) {
-  NX_LOOP(i, n) {
-    const float v = bg_ld(x, i);
-    bg_st(y, i, v > 0.f ? v : alpha[i % C] * v);
-  }
-}
-template <typename T> __global__ void prelu_bwd_dx_kernel(const T* __restrict__ x, const float* __restrict__ alpha, const T* __restrict__ dy,
-                                                          T* __restrict__ dx, long n, int C) {
-  NX_LOOP(i, n) {
-    const float v = bg_ld(x, i), g = bg_ld(dy, i), a = alpha[i % C];
-    bg_st(dx, i, v > 0.f ? g : (v < 0.f ? a * g : 0.5f * a * g));
-  }
-}
-template <typename T> __global__ void __launch_bounds__(256) prelu_bwd_dalpha_partial_kernel(const T* __restrict__ x, const T* __restrict__ dy,
-                                                                                          float* __restrict__ partial, long npix, int C, long rows_per_cta) {
-  const long r0 = (long)blockIdx.x * rows_per_cta;
-  const long r1 = r0 + rows_per_cta < npix ? r0 + rows_per_cta : npix;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (long r = r0; r < r1; ++r) acc += bg_ld(dy, r * C + c) * fminf(bg_ld(x, r * C + c), 0.f);
-    partial[(long)blockIdx.x * C + c] = acc;
-  }
-}
-__global__ void prelu_bwd_dalpha_final_kernel(const float* __restrict__ partial, float* __restrict__ dalpha, int nslab, int C, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float acc = 0.f;
-  for (int s = 0; s < nslab; ++s) acc += partial[(long)s * C + c];
-  dalpha[c] = accumulate ? dalpha[c] + acc : acc;
-}
 static inline int prelu_slabs(long npix) {
   long s = bg_cdiv(npix, 64);
   long mx = (long)bg_num_sms() * 8;
@@ -81,7 +35,7 @@ static inline int prelu_slabs(long npix) {
 extern "C" size_t bg_prelu_workspace_bytes(long npix, int C) { return (size_t)prelu_slabs(npix) * C * sizeof(float); }
 extern "C" int bg_prelu_fwd(const void* x, const float* alpha, void* y, long npix, int C, int dtype, void* stream) {
   const long n = npix * C;
-  BG_DISPATCH_DTYPE(dtype, T, prelu_fwd_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, alpha, (T*)y, n, C));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(prelu_fwd_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)x, alpha, (T*)y, n, C));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
@@ -93,156 +47,57 @@ extern "C" int bg_prelu_bwd(const void* x, const float* alpha, const void* dy, v
   const long rows = bg_cdiv(npix, slabs);
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
-    BG_DISPATCH_DTYPE(dtype, T, prelu_bwd_dx_kernel<T><<<nx_blocks(n), 256, 0, st>>>((const T*)x, alpha, (const T*)dy, (T*)dx, n, C));
+    BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(prelu_bwd_dx_kernel<T>, nx_blocks(n), 256, st, (const T*)x, alpha, (const T*)dy, (T*)dx, n, C));
     BG_LAUNCH_CHECK();
   }
-  BG_DISPATCH_DTYPE(dtype, T, prelu_bwd_dalpha_partial_kernel<T><<<slabs, 256, 0, st>>>((const T*)x, (const T*)dy, (float*)ws, npix, C, rows));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(prelu_bwd_dalpha_partial_kernel<T>, slabs, 256, st, (const T*)x, (const T*)dy, (float*)ws, npix, C, rows));
   BG_LAUNCH_CHECK();
-  prelu_bwd_dalpha_final_kernel<<<(unsigned)bg_cdiv(C, 128), 128, 0, st>>>((const float*)ws, dalpha, slabs, C, accumulate);
+  BG_LAUNCH(prelu_bwd_dalpha_final_kernel, (unsigned)bg_cdiv(C, 128), 128, st, (const float*)ws, dalpha, slabs, C, accumulate);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// 2x2/2 average pooling (tf.layers.average_pooling2d(2, 2, 'SAME') on even maps), nearest-neighbour x2 up-sampling
-// (tf.image.resize_nearest_neighbor to twice the size): each is the other's adjoint up to the factor 1/4.
-// ------------------------------------------------------------------------------------------------------------
-template <typename T> __global__ void pool2_sum_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, long n, float scale) {
-  const int Ho = H / 2, Wo = W / 2;       // x [B,H,W,C] -> y [B,H/2,W/2,C] = scale * (sum of the 2x2 window)
-  NX_LOOP(i, n) {
-    const int c = (int)(i % C); long r = i / C;
-    const int ox = (int)(r % Wo); r /= Wo;
-    const int oy = (int)(r % Ho); const long b = r / Ho;
-    const long base = ((b * H + 2 * oy) * W + 2 * ox) * C + c;
-    const float s = bg_ld(x, base) + bg_ld(x, base + C) + bg_ld(x, base + (long)W * C) + bg_ld(x, base + (long)W * C + C);
-    bg_st(y, i, s * scale);
-  }
-}
-template <typename T> __global__ void repeat2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, long n, float scale) {
-  const int Ho = 2 * H, Wo = 2 * W;       // x [B,H,W,C] -> y [B,2H,2W,C], y[.., oy, ox, ..] = scale * x[.., oy/2, ox/2, ..]
-  NX_LOOP(i, n) {
-    const int c = (int)(i % C); long r = i / C;
-    const int ox = (int)(r % Wo); r /= Wo;
-    const int oy = (int)(r % Ho); const long b = r / Ho;
-    bg_st(y, i, scale * bg_ld(x, ((b * H + oy / 2) * W + ox / 2) * C + c));
-  }
-}
 extern "C" int bg_avgpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream) {
   BG_REQUIRE(H % 2 == 0 && W % 2 == 0, BG_ERR_UNSUPPORTED, "avgpool2: odd size");
   const long n = (long)B * (H / 2) * (W / 2) * C;
-  BG_DISPATCH_DTYPE(dtype, T, pool2_sum_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C, n, 0.25f));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(pool2_sum_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)x, (T*)y, H, W, C, n, 0.25f));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 extern "C" int bg_avgpool2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream) {
   BG_REQUIRE(H % 2 == 0 && W % 2 == 0, BG_ERR_UNSUPPORTED, "avgpool2: odd size");     // H, W: size of the pooled INPUT (= of dx)
   const long n = (long)B * H * W * C;
-  BG_DISPATCH_DTYPE(dtype, T, repeat2_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (T*)dx, H / 2, W / 2, C, n, 0.25f));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(repeat2_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)dy, (T*)dx, H / 2, W / 2, C, n, 0.25f));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 extern "C" int bg_upsample2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream) {
   const long n = (long)B * (2 * H) * (2 * W) * C;                                      // H, W: size of x
-  BG_DISPATCH_DTYPE(dtype, T, repeat2_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, H, W, C, n, 1.0f));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(repeat2_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)x, (T*)y, H, W, C, n, 1.0f));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 extern "C" int bg_upsample2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream) {
   const long n = (long)B * H * W * C;                                                  // H, W: size of x (= of dx); dy is [B,2H,2W,C]
-  BG_DISPATCH_DTYPE(dtype, T, pool2_sum_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (T*)dx, 2 * H, 2 * W, C, n, 1.0f));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(pool2_sum_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)dy, (T*)dx, 2 * H, 2 * W, C, n, 1.0f));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// tf.nn.depth_to_space (NHWC, block r): y[b, h r + i, w r + j, c] = x[b, h, w, (i r + j) Co + c], Co = C / r^2.
-// inverse != 0 runs the adjoint (space_to_depth) with the same index map: x <- y.
-// ------------------------------------------------------------------------------------------------------------
-template <typename T> __global__ void depth_to_space_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C, int r, long n, int inverse) {
-  const int Co = C / (r * r);
-  NX_LOOP(i, n) {                          // i enumerates the [B, H r, W r, Co] tensor
-    const int c = (int)(i % Co); long t = i / Co;
-    const int ox = (int)(t % ((long)W * r)); t /= (long)W * r;
-    const int oy = (int)(t % ((long)H * r)); const long b = t / ((long)H * r);
-    const long deep = ((b * H + oy / r) * W + ox / r) * C + ((oy % r) * r + (ox % r)) * Co + c;
-    if (inverse) bg_st(dst, deep, bg_ld(src, i)); else bg_st(dst, i, bg_ld(src, deep));
-  }
-}
 extern "C" int bg_depth_to_space(const void* src, void* dst, int B, int H, int W, int C, int r, int inverse, int dtype, void* stream) {
   BG_REQUIRE(r >= 1 && C % (r * r) == 0, BG_ERR_SHAPE, "depth_to_space: C=%d is not a multiple of r^2 (r=%d)", C, r);
   const long n = (long)B * H * W * C;      // H, W, C: the DEEP tensor [B,H,W,C]
-  BG_DISPATCH_DTYPE(dtype, T, depth_to_space_kernel<T><<<nx_blocks(n), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, H, W, C, r, n, inverse));
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(depth_to_space_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const T*)src, (T*)dst, H, W, C, r, n, inverse));
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Orthogonal regularisers (utils.py:185-235) on the Gram matrix G = W^T W [C, C] (fp32):
-//   kind 0 'ortho':        reg = G - I
-//   kind 1 'ortho_cosine': reg = cosine_similarity(G, 1 - I):  na_i = G_i * rsqrt(max(|G_i|^2, 1e-12)),
-//                          reg_ij = (sum_k na_ik - na_ij) / sqrt(C - 1)       (every row of 1 - I has norm sqrt(C-1))
-//   loss = scale * sum(reg^2) / 2.
-// Every row of reg depends on one row of G only: one CTA per row writes dLoss/dG for that row and the row's loss term;
-// bg_ortho_reg_rows then adds the C row terms in order.  dLoss/dW = W (dG + dG^T) is two GEMMs on the caller's side.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ortho_rows_kernel(const float* __restrict__ G, float* __restrict__ dG, float* __restrict__ rowloss,
-                                                          int C, float scale, int kind) {
-  __shared__ float sh[40];
-  const int i = blockIdx.x;
-  const float* g = G + (long)i * C;
-  float* d = dG + (long)i * C;
-  if (kind == 0) {
-    float acc = 0.f;
-    for (int k = threadIdx.x; k < C; k += blockDim.x) {
-      const float r = g[k] - (k == i ? 1.f : 0.f);
-      d[k] = scale * r;
-      acc += r * r;
-    }
-    acc = bg_block_sum(acc, sh);
-    if (threadIdx.x == 0) rowloss[i] = 0.5f * scale * acc;
-    return;
-  }
-  float ss = 0.f, rs = 0.f;
-  for (int k = threadIdx.x; k < C; k += blockDim.x) { const float v = g[k]; ss += v * v; rs += v; }
-  ss = bg_block_sum(ss, sh);
-  rs = bg_block_sum(rs, sh);
-  const bool clamped = ss < 1e-12f;
-  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
-  const float rsn = rs * inv;                       // sum_k na_ik
-  const float q = C > 1 ? rsqrtf((float)(C - 1)) : 0.f;
-  // S_ik = (rsn - na_ik) q;  loss_i = scale/2 sum_k S_ik^2;  dS = scale S
-  // dna_ik = q (sum_j dS_ij - dS_ik);  dG_ik = inv (dna_ik - na_ik <dna_i, na_i>)
-  float l = 0.f, sds = 0.f;
-  for (int k = threadIdx.x; k < C; k += blockDim.x) { const float s = (rsn - g[k] * inv) * q; l += s * s; sds += s; }
-  l = bg_block_sum(l, sh);
-  sds = bg_block_sum(sds, sh) * scale;              // sum_j dS_ij
-  float dot = 0.f;
-  for (int k = threadIdx.x; k < C; k += blockDim.x) {
-    const float na = g[k] * inv;
-    const float dna = q * (sds - scale * (rsn - na) * q);
-    dot += dna * na;
-  }
-  dot = bg_block_sum(dot, sh);
-  for (int k = threadIdx.x; k < C; k += blockDim.x) {
-    const float na = g[k] * inv;
-    const float dna = q * (sds - scale * (rsn - na) * q);
-    d[k] = clamped ? inv * dna : inv * (dna - na * dot);      // under the eps clamp the normaliser is a constant
-  }
-  if (threadIdx.x == 0) rowloss[i] = 0.5f * scale * l;
-}
-__global__ void ortho_sum_rows_kernel(const float* __restrict__ rowloss, int C, float* __restrict__ loss, int accumulate) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    float acc = 0.f;
-    for (int i = 0; i < C; ++i) acc += rowloss[i];
-    loss[0] = accumulate ? loss[0] + acc : acc;
-  }
-}
 extern "C" int bg_ortho_reg_rows(const float* G, float* dG, float* rowloss, float* loss, int accumulate, int C, float scale, int kind,
                                  void* stream) {
   BG_REQUIRE(kind == 0 || kind == 1, BG_ERR_UNSUPPORTED, "Unknown regularization method.");
-  ortho_rows_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(G, dG, rowloss, C, scale, kind);
+  BG_LAUNCH(ortho_rows_kernel, C, 256, (cudaStream_t)stream, G, dG, rowloss, C, scale, kind);
   BG_LAUNCH_CHECK();
-  ortho_sum_rows_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rowloss, C, loss, accumulate);
+  BG_LAUNCH(ortho_sum_rows_kernel, 1, 32, (cudaStream_t)stream, rowloss, C, loss, accumulate);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
