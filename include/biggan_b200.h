@@ -273,6 +273,13 @@ int bg_depth_to_space(const void* src, void* dst, int B, int H, int W, int C, in
 int bg_ortho_reg_rows(const float* G, float* dG, float* rowloss, float* loss, int accumulate, int C,
                       float scale, int kind, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host utility (no device work): CRC-32C of `n` bytes continuing from `init` (0 = fresh); the 32 result bits
+ * are returned in the int.  The checksum of TensorFlow's checkpoint format (checkpoint.py; saver at BigGAN.py:1018,
+ * :1255-1284).
+ * ------------------------------------------------------------------------------------------- */
+int bg_crc32c(const void* data, size_t n, int init);
+
 #ifdef __cplusplus
 }
 #endif

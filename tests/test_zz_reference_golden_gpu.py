@@ -246,3 +246,31 @@ def test_cuda_virtual_batches_and_ema_sampling():
     ema_store = R.RefStore(torch.float64, params={**rs.export(), **{k: v.numpy() for k, v in og.shadow.items()}})
     ref = M.generator(ema_store, rcfg, torch.as_tensor(z, dtype=torch.float64), torch.as_tensor(lab, dtype=torch.float64), is_training=False)
     assert_close(img.numpy()[..., :3], ref.detach().numpy(), 2e-4, "EMA sample")
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_checkpoint_round_trip_in_the_reference_format(tmp_path):
+    """Trainer -> TensorBundle checkpoint with the swapping saver's names -> fresh Trainer: identical state and next step."""
+    from biggan_tensorflow_b200 import checkpoint as ck
+    from biggan_tensorflow_b200.model import Config
+    from biggan_tensorflow_b200.step import Trainer
+    kw = dict(img_size=32, ch=32, batch_size=4, n_labels=10, sa_gamma_init=0.1)
+    b = M.synthetic_batch(M.Config(**kw), B=4)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    args = (dev(b["real"]), dev(b["labels"]), dev(b["z_d"]), dev(b["z_g"]), dev(b["labels"]))
+    tr = Trainer(Config(**kw), compute_dtype=torch.float32)
+    tr.train_step(*args)
+    tr.train_step(*args)
+    prefix = ck.save(tr, str(tmp_path), step=2)
+    t = ck.read_bundle(prefix)
+    assert "generator/G_logit/kernel/ExponentialMovingAverage" in t and "discriminator/D_logit/kernel/Adam_1" in t
+    assert abs(float(t["beta2_power"]) - 0.9 ** 3) < 1e-6 and ck.latest_checkpoint(str(tmp_path)) == prefix
+    tr2 = Trainer(Config(**kw), compute_dtype=torch.float32)
+    assert ck.load(tr2, prefix) == 2
+    a, c = tr.store.export(), tr2.store.export()
+    assert sorted(a) == sorted(c) and all(np.array_equal(a[k], c[k]) for k in a)
+    assert torch.equal(tr.opt["generator"]["ema"], tr2.opt["generator"]["ema"]) and torch.equal(tr.opt["discriminator"]["v"], tr2.opt["discriminator"]["v"])
+    d1, g1 = tr.train_step(*args)
+    d2, g2 = tr2.train_step(*args)
+    assert float(d1.cpu()) == float(d2.cpu()) and float(g1.cpu()) == float(g2.cpu())
