@@ -22,13 +22,18 @@ ROOT = os.path.dirname(HERE)
 STANDALONE = {"prelu", "lrelu", "upconv_nn", "downconv_pool_only"}           # cases that need no conv kernel
 
 
-@pytest.fixture()
-def host_product(tmp_path_factory, monkeypatch):
-    from biggan_tensorflow_b200 import _lib, ops, tensor, tf_shim, utils
+@pytest.fixture(scope="module")
+def host_so(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("host_lib") / "host_lib.so")
     subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-x", "c++", "-shared", "-fPIC",
                     os.path.join(HERE, "host_emul", "host_lib.cpp"), "-o", so], check=True)
-    lib = ctypes.CDLL(so)
+    return so
+
+
+@pytest.fixture()
+def host_product(host_so, monkeypatch):
+    from biggan_tensorflow_b200 import _lib, ops, tensor, tf_shim, utils
+    lib = ctypes.CDLL(host_so)
     for name, (res, args) in _lib.DECLS.items():
         if hasattr(lib, name):
             fn = getattr(lib, name)
