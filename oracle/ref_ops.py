@@ -367,11 +367,76 @@ def condition_batch_norm(store, x, z, opt={}, scope="batch_norm"):
         return _r(x * inv + (beta - mean * inv))                                # :638
 
 
+def normalize_renorm_clipping_params(renorm_clipping):
+    """ops.py:587-597."""
+    if "rmax" not in renorm_clipping:
+        renorm_clipping["rmax"] = 1.5
+    if "dmax" not in renorm_clipping:
+        renorm_clipping["dmax"] = 0.5
+    if "rmax" in renorm_clipping and "rmin" not in renorm_clipping:
+        renorm_clipping["rmin"] = 1.0 / renorm_clipping["rmax"]
+    return renorm_clipping
+
+
+def condition_batch_renorm(store, x, z, opt={}, scope="batch_renorm"):
+    """ops.py:645-715: conditional batch RE-normalisation (training-time running statistics with a fade-in weight,
+    correction factors r, d clipped and treated as constants)."""
+    with store.variable_scope(scope):
+        c = x.shape[-1]
+        renorm_clipping = normalize_renorm_clipping_params(dict(opt.get("bn", {}).get("renorm_clipping", {})))   # :651
+        test_decay = opt.get("bn", {}).get("momentum", 0.98)
+        renorm_decay = opt.get("bn", {}).get("renorm_momentum", 0.9)
+        shared = opt.get("bn", {}).get("shared_renorm", False)
+        renorm_fadein_decay = opt.get("bn", {}).get("renorm_fadein_decay", 0.9999)
+        if not shared:
+            test_decay = renorm_decay                                           # :658-659
+        epsilon = 1e-05
+        test_mean = store.get_variable("pop_mean", [c], kind="const", value=0.0, trainable=False)
+        test_var = store.get_variable("pop_var", [c], kind="const", value=1.0, trainable=False)
+        if not shared:
+            renorm_mean = store.get_variable("renorm_mean", [c], kind="const", value=0.0, trainable=False)
+            renorm_var = store.get_variable("renorm_var", [c], kind="const", value=1.0, trainable=False)
+            renorm_weight = store.get_variable("renorm_weight", [], kind="const", value=0.0, trainable=False)
+        else:
+            renorm_mean, renorm_var, renorm_weight = test_mean, test_var, 1.0   # :671-674
+        beta = fully_connected(store, z, units=c, scope="beta", opt=opt).reshape(-1, 1, 1, c)
+        gamma = fully_connected(store, z, units=c, scope="gamma", opt=opt).reshape(-1, 1, 1, c)
+        if not opt["is_training"]:
+            inv = torch.rsqrt(test_var + epsilon) * gamma                       # :711-715
+            return _r(x * inv + (beta - test_mean * inv))
+        batch_mean = x.mean(dim=(0, 1, 2))
+        batch_var = ((x - batch_mean) ** 2).mean(dim=(0, 1, 2))
+        rmax, rmin, dmax = renorm_clipping["rmax"], renorm_clipping["rmin"], renorm_clipping["dmax"]
+        sigma = torch.sqrt(batch_var + epsilon)
+        renorm_sigma = torch.sqrt(renorm_var + epsilon)
+        weighted_renorm_sigma = renorm_weight * renorm_sigma + (1 - renorm_weight) * sigma          # :690
+        weighted_renorm_mean = renorm_weight * renorm_mean + (1 - renorm_weight) * batch_mean       # :691
+        r = torch.clamp(sigma / weighted_renorm_sigma, rmin, rmax).detach()                         # :692
+        d = torch.clamp((batch_mean - weighted_renorm_mean) / weighted_renorm_sigma, -dmax, dmax).detach()   # :693
+        store.assign(store.full_name("pop_mean"), test_mean * test_decay + batch_mean * (1 - test_decay))
+        store.assign(store.full_name("pop_var"), test_var * test_decay + batch_var * (1 - test_decay))
+        if not shared:
+            store.assign(store.full_name("renorm_mean"), renorm_mean * renorm_decay + batch_mean * (1 - renorm_decay))
+            store.assign(store.full_name("renorm_var"), renorm_var * renorm_decay + batch_var * (1 - renorm_decay))
+            store.assign(store.full_name("renorm_weight"),
+                         torch.as_tensor(renorm_weight) * renorm_fadein_decay + 1.0 * (1 - renorm_fadein_decay))
+        inv = torch.rsqrt(batch_var + epsilon) * (r * gamma)                    # :707 batch_normalization(x, mean, var, beta + d gamma, r gamma)
+        return _r(x * inv + ((beta + d * gamma) - batch_mean * inv))
+
+
 def cond_bn(store, x, z, opt={}, scope="batch_norm"):
     """ops.py:563-578."""
     type = opt.get("bn", {}).get("type", "bn")
+    if type == "batch_norm_broken_renorm":
+        type = "batch_norm"
+        if scope == "batch_norm":
+            scope = "batch_renorm"
     if type == "bn" or type == "batch_norm":
         return condition_batch_norm(store, x, z, opt=opt, scope=scope)
+    elif type == "batch_renorm":
+        if scope == "batch_norm":
+            scope = "batch_renorm"
+        return condition_batch_renorm(store, x, z, opt=opt, scope=scope)
     raise ValueError("Unknown BN type: " + str(type))
 
 

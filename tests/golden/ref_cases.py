@@ -106,6 +106,20 @@ NEXT_OP_CASES = [
     _c("resblock_up_condition_prelu", "resblock_up_condition", [("x", (2, 4, 4, 32)), ("z", (2, 1, 1, 12))],
        dict(channels=16, use_bias=False, scope="resblock_up_4"), 48, opt={"act": "prelu"},
        var_init={"resblock_up_4/res1/prelu/alpha": [0.3] * 32, "resblock_up_4/res2/prelu/alpha": [-0.2] * 16}),
+    # conditional batch renorm (ops.py:645-715): fresh state (weight 0: plain CBN with r = d = 1), a warmed-up state with
+    # clipping active, the shared-statistics variant, inference
+    _c("cbrn_fresh", "cond_bn", [("x", (4, 4, 4, 16)), ("z", (4, 1, 1, 12))], {}, 50, opt={"bn": {"type": "batch_renorm"}},
+       scale={"x": 1.5}, shift={"x": 0.3}),
+    _c("cbrn_warm", "cond_bn", [("x", (4, 4, 4, 16)), ("z", (4, 1, 1, 12))], {}, 50, scale={"x": 1.5}, shift={"x": 0.3},
+       opt={"bn": {"type": "batch_renorm", "renorm_clipping": {"rmax": 1.2, "dmax": 0.3}, "renorm_momentum": 0.8}},
+       var_init={"batch_renorm/renorm_weight": 0.7, "batch_renorm/renorm_mean": [0.1 * i - 0.5 for i in range(16)],
+                 "batch_renorm/renorm_var": [0.5 + 0.2 * i for i in range(16)]}),
+    _c("cbrn_shared", "cond_bn", [("x", (4, 4, 4, 16)), ("z", (4, 1, 1, 12))], {}, 50, scale={"x": 1.5}, shift={"x": 0.3},
+       opt={"bn": {"type": "batch_renorm", "shared_renorm": True}},
+       var_init={"batch_renorm/pop_mean": [0.05 * i for i in range(16)], "batch_renorm/pop_var": [1.0 + 0.1 * i for i in range(16)]}),
+    _c("cbrn_inference", "cond_bn", [("x", (2, 4, 4, 16)), ("z", (2, 1, 1, 12))], {}, 51,
+       opt={"is_training": False, "bn": {"type": "batch_renorm"}},
+       var_init={"batch_renorm/pop_mean": [0.05 * i for i in range(16)], "batch_renorm/pop_var": [1.0 + 0.1 * i for i in range(16)]}),
     _c("resblock_up_condition_lrelu_subpixel3_conv5", "resblock_up_condition", [("x", (2, 4, 4, 32)), ("z", (2, 1, 1, 12))],
        dict(channels=16, use_bias=True, scope="resblock_up_4"), 49, opt={"act": "lrelu", "upsampling_method": "subpixel3", "g_conv": "conv5"}),
 ]
