@@ -101,3 +101,25 @@ extern "C" int bg_ortho_reg_rows(const float* G, float* dG, float* rowloss, floa
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
+extern "C" int bg_renorm_factors(const float* mean, const float* var, float* rmean, float* rvar, const float* weight, float* weight_out,
+                                 float* r, float* d, int C, float eps, float rmin, float rmax, float dmax, float decay, float fade,
+                                 int update_state, void* stream) {
+  BG_LAUNCH(renorm_factors_kernel, (unsigned)bg_cdiv(C, 128), 128, (cudaStream_t)stream, mean, var, rmean, rvar, weight, weight_out, r, d, C,
+            eps, rmin, rmax, dmax, decay, fade, update_state);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_renorm_affine_fwd(const float* gamma, const float* beta, const float* r, const float* d, float* gamma2, float* beta2,
+                                    int B, int C, void* stream) {
+  const long n = (long)B * C;
+  BG_LAUNCH(renorm_affine_fwd_kernel, nx_blocks(n), 256, (cudaStream_t)stream, gamma, beta, r, d, gamma2, beta2, n, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_renorm_affine_bwd(const float* dgamma2, const float* dbeta2, const float* r, const float* d, float* dgamma, int B, int C,
+                                    void* stream) {
+  const long n = (long)B * C;
+  BG_LAUNCH(renorm_affine_bwd_kernel, nx_blocks(n), 256, (cudaStream_t)stream, dgamma2, dbeta2, r, d, dgamma, n, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

@@ -150,3 +150,49 @@ __global__ void ortho_sum_rows_kernel(const float* __restrict__ rowloss, int C, 
     loss[0] = accumulate ? loss[0] + acc : acc;
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Conditional batch RE-normalisation (ops.py:645-715).  Per channel, from the batch statistics and the training-time
+// running statistics (blended with the batch ones by the fade-in weight w):
+//   sigma = sqrt(var + eps), rsigma = sqrt(rvar + eps), wsig = w rsigma + (1-w) sigma, wmean = w rmean + (1-w) mean
+//   r = clip(sigma / wsig, rmin, rmax),   d = clip((mean - wmean) / wsig, -dmax, dmax)        (constants in the backward)
+// then, unless the statistics are the shared population ones (update_state = 0), the running statistics move by
+// `decay` and the fade-in weight by `fade`.  The normalisation itself is a conditional batch norm with
+//   gamma' = r gamma,  beta' = beta + d gamma      (per sample and channel)
+// whose adjoint is  dgamma = r dgamma' + d dbeta',  dbeta = dbeta'.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void renorm_factors_kernel(const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ rmean,
+                                      float* __restrict__ rvar, const float* __restrict__ weight, float* __restrict__ weight_out,
+                                      float* __restrict__ r, float* __restrict__ d, int C, float eps, float rmin, float rmax, float dmax,
+                                      float decay, float fade, int update_state) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const float w = weight ? weight[0] : 1.f;
+  if (c == 0 && weight_out) weight_out[0] = update_state ? w * fade + (1.f - fade) : w;
+  if (c >= C) return;
+  const float m = mean[c], v = var[c], rm = rmean[c], rv = rvar[c];
+  const float sigma = sqrtf(v + eps), rsigma = sqrtf(rv + eps);
+  const float wsig = w * rsigma + (1.f - w) * sigma;
+  const float wmean = w * rm + (1.f - w) * m;
+  r[c] = fminf(fmaxf(sigma / wsig, rmin), rmax);
+  d[c] = fminf(fmaxf((m - wmean) / wsig, -dmax), dmax);
+  if (update_state) {
+    rmean[c] = rm * decay + m * (1.f - decay);
+    rvar[c] = rv * decay + v * (1.f - decay);
+  }
+}
+__global__ void renorm_affine_fwd_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ r,
+                                         const float* __restrict__ d, float* __restrict__ gamma2, float* __restrict__ beta2, long n, int C) {
+  NX_LOOP(i, n) {
+    const int c = (int)(i % C);
+    const float g = gamma[i];
+    gamma2[i] = r[c] * g;
+    beta2[i] = beta[i] + d[c] * g;
+  }
+}
+__global__ void renorm_affine_bwd_kernel(const float* __restrict__ dgamma2, const float* __restrict__ dbeta2, const float* __restrict__ r,
+                                         const float* __restrict__ d, float* __restrict__ dgamma, long n, int C) {
+  NX_LOOP(i, n) {           // dbeta = dbeta2 needs no kernel
+    const int c = (int)(i % C);
+    dgamma[i] = r[c] * dgamma2[i] + d[c] * dbeta2[i];
+  }
+}

@@ -1037,6 +1037,82 @@ def condition_batch_norm(x, z, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
         return _bn_core(x, gamma, beta, c, test_mean, test_var, decay, lambda n: 1.0, opt, _act)
 
 
+def normalize_renorm_clipping_params(renorm_clipping):
+    """ops.py:587-597."""
+    if "rmax" not in renorm_clipping:
+        renorm_clipping["rmax"] = 1.5
+    if "dmax" not in renorm_clipping:
+        renorm_clipping["dmax"] = 0.5
+    if "rmax" in renorm_clipping and "rmin" not in renorm_clipping:
+        renorm_clipping["rmin"] = 1.0 / renorm_clipping["rmax"]
+    return renorm_clipping
+
+
+def _renorm_affine(gamma, beta, r, d):
+    """gamma' = r gamma, beta' = beta + d gamma over [B, C] (r, d [C] are constants in the backward, ops.py:692-693)."""
+    B, C = gamma.shape
+    g2 = Tensor(empty([B, C], F32), requires_grad=gamma.requires_grad)
+    b2 = Tensor(empty([B, C], F32), requires_grad=gamma.requires_grad or beta.requires_grad)
+    call("bg_renorm_affine_fwd", gamma.data, beta.data, r, d, g2.data, b2.data, B, C, stream())
+    if recording(gamma, beta):
+        def bw():
+            if g2.grad is None and b2.grad is None:
+                return
+            dg2 = g2.grad if g2.grad is not None else torch.zeros_like(gamma.data)
+            db2 = b2.grad if b2.grad is not None else torch.zeros_like(beta.data)
+            if gamma.requires_grad:
+                dg = empty([B, C], F32)
+                call("bg_renorm_affine_bwd", dg2, db2, r, d, dg, B, C, stream())
+                accumulate_grad(gamma, dg, own=True)
+            if beta.requires_grad:
+                accumulate_grad(beta, db2, own=False)
+        record(bw)
+    return g2, b2
+
+
+def condition_batch_renorm(x, z, opt={}, scope='batch_renorm', _act=_lib.ACT_NONE):
+    """ops.py:645-715.  The correction factors r, d come from one extra statistics pass; the normalisation itself is the
+    conditional batch norm kernel set with gamma' = r gamma, beta' = beta + d gamma."""
+    with variable_scope(scope):
+        B, H, W, c = x.shape
+        renorm_clipping = normalize_renorm_clipping_params(dict(opt.get("bn", {}).get("renorm_clipping", {})))
+        test_decay = opt.get("bn", {}).get("momentum", 0.98)
+        renorm_decay = opt.get("bn", {}).get("renorm_momentum", 0.9)
+        shared = opt.get("bn", {}).get("shared_renorm", False)
+        renorm_fadein_decay = opt.get("bn", {}).get("renorm_fadein_decay", 0.9999)
+        if not shared:
+            test_decay = renorm_decay                                           # :658-659
+        test_mean = get_variable("pop_mean", shape=[c], initializer=constant_initializer(0.0), trainable=False)
+        test_var = get_variable("pop_var", shape=[c], initializer=constant_initializer(1.0), trainable=False)
+        if not shared:
+            renorm_mean = get_variable("renorm_mean", shape=[c], initializer=constant_initializer(0.0), trainable=False)
+            renorm_var = get_variable("renorm_var", shape=[c], initializer=constant_initializer(1.0), trainable=False)
+            renorm_weight = get_variable("renorm_weight", shape=[], initializer=constant_initializer(0.0), trainable=False)
+        beta = fully_connected(z, units=c, scope='beta', opt=opt)
+        gamma = fully_connected(z, units=c, scope='gamma', opt=opt)
+        if opt["is_training"]:
+            HW = H * W
+            sums = empty([2 * c], torch.float64)
+            ws = workspace(query("bg_bn_workspace_bytes", B, HW, c))
+            call("bg_bn_stats", x.data, sums, B, HW, c, bg_dtype(x), ws, ws.numel(), stream())
+            dist.all_reduce_sum(sums)
+            mean, var = empty([c], F32), empty([c], F32)
+            scratch_m, scratch_v = torch.zeros_like(mean), torch.ones_like(var)        # finalize also moves running statistics: discard
+            call("bg_bn_finalize", sums, float(B * HW * dist.world_size), mean, var, scratch_m, scratch_v, 0.0, 1.0, c, stream())
+            r, d = empty([c], F32), empty([c], F32)
+            if shared:       # r, d against the population statistics as they were BEFORE this step's update (:671-673)
+                call("bg_renorm_factors", mean, var, test_mean.data, test_var.data, None, None, r, d, c, 1e-05,
+                     float(renorm_clipping["rmin"]), float(renorm_clipping["rmax"]), float(renorm_clipping["dmax"]), 0.0, 0.0, 0, stream())
+            else:
+                w_out = empty([1], F32)
+                call("bg_renorm_factors", mean, var, renorm_mean.data, renorm_var.data, renorm_weight.data, w_out, r, d, c, 1e-05,
+                     float(renorm_clipping["rmin"]), float(renorm_clipping["rmax"]), float(renorm_clipping["dmax"]),
+                     float(renorm_decay), float(renorm_fadein_decay), 1, stream())
+                renorm_weight.data.copy_(w_out.reshape(renorm_weight.data.shape))
+            gamma, beta = _renorm_affine(gamma, beta, r, d)
+        return _bn_core(x, gamma, beta, c, test_mean, test_var, test_decay, lambda n: 1.0, opt, _act)
+
+
 def batch_norm(x, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
     """ops.py:580-585 (tf.layers.batch_normalization; moving_variance takes the unbiased variance)."""
     with variable_scope(scope):
@@ -1074,7 +1150,9 @@ def cond_bn(x, z, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
     if type == 'bn' or type == 'batch_norm':
         return condition_batch_norm(x, z, opt=opt, scope=scope, _act=_act)
     elif type == 'batch_renorm':
-        raise ValueError("BN type batch_renorm is not supported (out of scope, SURVEY 8f rank 3)")
+        if scope == 'batch_norm':
+            scope = 'batch_renorm'
+        return condition_batch_renorm(x, z, opt=opt, scope=scope, _act=_act)
     else:
         raise ValueError("Unknown BN type: " + str(type))
 

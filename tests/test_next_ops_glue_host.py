@@ -127,3 +127,18 @@ def test_glue_of_the_orthogonal_regularizers_matches_reference_source(host_produ
         C.check(g, kind + "/" + gkey, dW.numpy(), 2e-5)
     with pytest.raises(ValueError, match="Unknown regularization method."):
         utils.orthogonal_regularizer(1e-4, type="l3")(_tensor(np.ones((2, 2), np.float32)))
+
+
+def test_glue_of_the_renorm_affine_map(host_product):
+    """ops._renorm_affine: gamma' = r gamma, beta' = beta + d gamma with r, d constant -> dgamma = r dgamma' + d dbeta', dbeta = dbeta'."""
+    from biggan_tensorflow_b200 import ops
+    from biggan_tensorflow_b200.tensor import backward
+    rng = np.random.default_rng(3)
+    gamma, beta = _tensor(rng.standard_normal((4, 9))), _tensor(rng.standard_normal((4, 9)))
+    r, d = torch.from_numpy(rng.random(9).astype(np.float32) + 0.5), torch.from_numpy(rng.standard_normal(9).astype(np.float32))
+    g2, b2 = ops._renorm_affine(gamma, beta, r, d)
+    dg2, db2 = torch.from_numpy(rng.standard_normal((4, 9)).astype(np.float32)), torch.from_numpy(rng.standard_normal((4, 9)).astype(np.float32))
+    backward([(g2, dg2), (b2, db2)])
+    assert np.allclose(g2.numpy(), r.numpy() * gamma.numpy(), atol=1e-6) and np.allclose(b2.numpy(), beta.numpy() + d.numpy() * gamma.numpy(), atol=1e-6)
+    assert np.allclose(gamma.grad.numpy(), r.numpy() * dg2.numpy() + d.numpy() * db2.numpy(), atol=1e-5)
+    assert np.allclose(beta.grad.numpy(), db2.numpy(), atol=1e-6)

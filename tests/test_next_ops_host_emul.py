@@ -169,3 +169,37 @@ def test_orthogonal_regularizer_rows(emul, kind, K, C):
     dW = W.astype(np.float64) @ (dG.astype(np.float64) + dG.astype(np.float64).T)
     assert np.abs(dW - gw.numpy()).max() <= 2e-4 * np.abs(gw.numpy()).max()
     assert emul.bg_ortho_reg_rows(ptr(G), ptr(dG), ptr(rowloss), ptr(loss), 0, C, scale, 2, None) != 0   # "Unknown regularization method."
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_renorm_factors_and_affine(emul, shared):
+    """ops.py:684-707: r, d, running-statistics / fade-in updates, gamma' = r gamma, beta' = beta + d gamma and its adjoint."""
+    rng = np.random.default_rng(6)
+    C, B = 150, 5
+    mean, var = rng.standard_normal(C).astype(np.float32), (rng.random(C) + 0.2).astype(np.float32)
+    rmean, rvar = rng.standard_normal(C).astype(np.float32), (rng.random(C) * 3 + 0.05).astype(np.float32)
+    w = np.array([0.7], np.float32)
+    rm0, rv0 = rmean.copy(), rvar.copy()
+    r, d, w_out = np.zeros(C, np.float32), np.zeros(C, np.float32), np.zeros(1, np.float32)
+    eps, rmin, rmax, dmax, decay, fade = 1e-5, 1 / 1.2, 1.2, 0.3, 0.8, 0.99
+    rc = emul.bg_renorm_factors(ptr(mean), ptr(var), ptr(rmean), ptr(rvar), None if shared else ptr(w), None if shared else ptr(w_out),
+                                ptr(r), ptr(d), C, eps, rmin, rmax, dmax, decay, fade, 0 if shared else 1, None)
+    assert rc == 0
+    ww = 1.0 if shared else 0.7
+    sigma, rsigma = np.sqrt(var.astype(np.float64) + eps), np.sqrt(rv0.astype(np.float64) + eps)
+    wsig, wmean = ww * rsigma + (1 - ww) * sigma, ww * rm0 + (1 - ww) * mean
+    assert np.allclose(r, np.clip(sigma / wsig, rmin, rmax), rtol=1e-5) and np.allclose(d, np.clip((mean - wmean) / wsig, -dmax, dmax), rtol=1e-4, atol=1e-6)
+    assert (r == np.float32(rmax)).any() and (d == np.float32(-dmax)).any()              # the clips are exercised
+    if shared:
+        assert np.array_equal(rmean, rm0) and np.array_equal(rvar, rv0)
+    else:
+        assert np.allclose(rmean, rm0 * decay + mean * (1 - decay), rtol=1e-6, atol=1e-7) and np.allclose(rvar, rv0 * decay + var * (1 - decay), rtol=1e-6)
+        assert abs(float(w_out[0]) - (0.7 * fade + 1 - fade)) < 1e-6
+    gamma, beta = rng.standard_normal((B, C)).astype(np.float32), rng.standard_normal((B, C)).astype(np.float32)
+    g2, b2 = np.zeros_like(gamma), np.zeros_like(beta)
+    assert emul.bg_renorm_affine_fwd(ptr(gamma), ptr(beta), ptr(r), ptr(d), ptr(g2), ptr(b2), B, C, None) == 0
+    assert np.allclose(g2, r * gamma, rtol=1e-6) and np.allclose(b2, beta + d * gamma, rtol=1e-6, atol=1e-6)
+    dg2, db2 = rng.standard_normal((B, C)).astype(np.float32), rng.standard_normal((B, C)).astype(np.float32)
+    dg = np.zeros_like(gamma)
+    assert emul.bg_renorm_affine_bwd(ptr(dg2), ptr(db2), ptr(r), ptr(d), ptr(dg), B, C, None) == 0
+    assert np.allclose(dg, r * dg2 + d * db2, rtol=1e-5, atol=1e-6)

@@ -53,9 +53,7 @@ def test_cuda_op_matches_reference_source(case, dtype):
 @UNVERIFIED
 @pytest.mark.parametrize("case", C.NEXT_OP_CASES, ids=[c["name"] for c in C.NEXT_OP_CASES])
 def test_cuda_next_row_op_matches_reference_source(case):
-    """prelu / lrelu, up- and down-sampling and g_conv variants, bn_in_d (fp32 mode)."""
-    if case["opt"].get("bn", {}).get("type") == "batch_renorm":
-        pytest.skip("conditional batch renorm: oracle pinned to the reference source, CUDA side not written yet")
+    """prelu / lrelu, up- and down-sampling and g_conv variants, bn_in_d, conditional batch renorm (fp32 mode)."""
     _cuda_op_case(case, torch.float32, "ref_ops_next.npz")
 
 
