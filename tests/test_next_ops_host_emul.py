@@ -151,8 +151,8 @@ def test_depth_to_space_and_its_adjoint(emul, dtype, shape, r):
         assert emul.bg_depth_to_space(ptr(xd), ptr(y), B, H, W, C + 1, r, 0, dtype, None) != 0
 
 
-@pytest.mark.parametrize("kind", ["ortho", "ortho_cosine"])
-@pytest.mark.parametrize("K,C", [(40, 12), (30, 70), (5, 300)])
+@pytest.mark.parametrize("kind,K,C", [("ortho", 40, 12), ("ortho", 30, 70), ("ortho", 5, 300),          # C > 256: strided row loops
+                                      ("ortho_cosine", 40, 12), ("ortho_cosine", 30, 70), ("ortho_cosine", 3, 260)])
 def test_orthogonal_regularizer_rows(emul, kind, K, C):
     """bg_ortho_reg_rows on G = W^T W: loss and, through dW = W (dG + dG^T), the gradient of utils.py:185-235."""
     rng = np.random.default_rng(5)
