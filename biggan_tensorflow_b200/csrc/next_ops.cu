@@ -123,3 +123,12 @@ extern "C" int bg_renorm_affine_bwd(const float* dgamma2, const float* dbeta2, c
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
+extern "C" int bg_image_prepare(const void* src_u8, const int* flip, void* dst, int B, int h, int w, int c, int S, int Cd, int dtype,
+                                void* stream) {
+  BG_REQUIRE(B > 0 && h > 0 && w > 0 && c > 0 && S > 0 && Cd >= c, BG_ERR_SHAPE, "image_prepare: bad shape");
+  const long n = (long)B * S * S * Cd;
+  BG_DISPATCH_DTYPE(dtype, T, BG_LAUNCH(image_prepare_kernel<T>, nx_blocks(n), 256, (cudaStream_t)stream, (const unsigned char*)src_u8, flip,
+                                        (T*)dst, h, w, c, S, Cd, n));
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}

@@ -196,3 +196,30 @@ __global__ void renorm_affine_bwd_kernel(const float* __restrict__ dgamma2, cons
     dgamma[i] = r[c] * dgamma2[i] + d[c] * dbeta2[i];
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Device half of ImageData.image_processing (utils.py:28-32): tf.image.resize_images(x, [S, S]) (TF-1 bilinear,
+// align_corners = False: source coordinate = index * in / out, neighbours floor and min(ceil, in - 1)),
+// tf.image.random_flip_left_right (the coin is an input, one int per image), cast / 127.5 - 1.
+// src uint8 [B, h, w, c] -> dst [B, S, S, Cd] (channels c..Cd-1 zero: the 16-channel image layout of the bf16 mode).
+// ------------------------------------------------------------------------------------------------------------
+template <typename T> __global__ void image_prepare_kernel(const unsigned char* __restrict__ src, const int* __restrict__ flip, T* __restrict__ dst,
+                                                           int h, int w, int c, int S, int Cd, long n) {
+  const float sy = (float)h / (float)S, sx = (float)w / (float)S;
+  NX_LOOP(i, n) {
+    const int ch = (int)(i % Cd); long t = i / Cd;
+    const int ox = (int)(t % S); t /= S;
+    const int oy = (int)(t % S); const long b = t / S;
+    if (ch >= c) { bg_st(dst, i, 0.f); continue; }
+    const int rx = (flip && flip[b]) ? S - 1 - ox : ox;          // the flip acts on the resized image
+    const float fy = oy * sy, fx = rx * sx;
+    const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    const int y1 = min((int)ceilf(fy), h - 1), x1 = min((int)ceilf(fx), w - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const unsigned char* img = src + b * (long)h * w * c + ch;
+    const float tl = img[((long)y0 * w + x0) * c], tr = img[((long)y0 * w + x1) * c];
+    const float bl = img[((long)y1 * w + x0) * c], br = img[((long)y1 * w + x1) * c];
+    const float top = tl + (tr - tl) * lx, bot = bl + (br - bl) * lx;
+    bg_st(dst, i, (top + (bot - top) * ly) / 127.5f - 1.f);
+  }
+}

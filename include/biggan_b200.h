@@ -285,6 +285,12 @@ int bg_renorm_affine_fwd(const float* gamma, const float* beta, const float* r, 
 int bg_renorm_affine_bwd(const float* dgamma2, const float* dbeta2, const float* r, const float* d, float* dgamma,
                          int B, int C, void* stream);
 
+/* device half of ImageData.image_processing (utils.py:28-32): src uint8 [B,h,w,c] -> dst [B,S,S,Cd] in `dtype`:
+ * TF-1 bilinear resize (align_corners = False), left-right flip where flip[b] != 0 (flip may be NULL), x / 127.5 - 1;
+ * channels c..Cd-1 are zero.  The PNG decode half is host code: include/biggan_io.h. */
+int bg_image_prepare(const void* src_u8, const int* flip, void* dst, int B, int h, int w, int c, int S, int Cd,
+                     int dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host utility (no device work): CRC-32C of `n` bytes continuing from `init` (0 = fresh); the 32 result bits
  * are returned in the int.  The checksum of TensorFlow's checkpoint format (checkpoint.py; saver at BigGAN.py:1018,

@@ -5,6 +5,7 @@
 // It checks index arithmetic, launch geometry and reductions of the actual kernel source when no GPU is available;
 // it says nothing about performance or about anything hardware specific.  Used by tests/test_next_ops_host_emul.py.
 #pragma once
+#include <algorithm>
 #include <barrier>
 #include <cmath>
 #include <cstdarg>
@@ -45,6 +46,8 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   return r;
 }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+using std::min;
+using std::max;
 
 template <typename F> inline void bg_emul_launch(bg_emul_dim3 grid, bg_emul_dim3 block, F&& body) {
   gridDim = grid; blockDim = block;

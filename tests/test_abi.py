@@ -42,3 +42,15 @@ def test_option_errors_match_reference_strings():
         ops.g_conv(None, 8, opt={"g_conv": "bogus"})
     with pytest.raises(ValueError, match="Invalid downsampling method"):
         ops.downconv(None, 8, opt={"downsampling_method": "bogus"})
+
+
+def test_io_library_exports_every_symbol_of_its_header():
+    """include/biggan_io.h (host-side input decoding) <-> libbiggan_io.so."""
+    import re
+    src = open(os.path.join(ROOT, "include", "biggan_io.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(bgio_\w+)\s*\(", src)
+    assert set(names) == {"bgio_last_error", "bgio_png_info", "bgio_png_decode"}
+    so = ctypes.CDLL(os.path.join(ROOT, "biggan_tensorflow_b200", "libbiggan_io.so"))
+    for n in names:
+        assert hasattr(so, n), "missing export " + n

@@ -274,3 +274,23 @@ def test_cuda_checkpoint_round_trip_in_the_reference_format(tmp_path):
     d1, g1 = tr.train_step(*args)
     d2, g2 = tr2.train_step(*args)
     assert float(d1.cpu()) == float(d2.cpu()) and float(g1.cpu()) == float(g2.cpu())
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_input_pipeline_end_to_end(tmp_path):
+    """PNG files -> HostBatches (decode on the thread pool, pinned staging) -> DevicePrefetcher (side stream, bg_image_prepare):
+    every prepared batch equals the numpy statement of resize + flip + normalise of the decoded files."""
+    from test_data_pipeline import _dataset, _tf1_resize_flip_normalise
+    from biggan_tensorflow_b200 import data as D
+    root, label_file = _dataset(tmp_path, 12, size=10)
+    paths, labels = D.load_data("toy", label_file, root=root)
+    ref = D.HostBatches(paths, labels, batch_size=4, seed=3, num_threads=2)
+    pre = D.DevicePrefetcher(D.HostBatches(paths, labels, batch_size=4, seed=3, num_threads=4), img_size=16, dtype=torch.float32,
+                             pad_channels=16, prefetch=3)
+    for _ in range(7):
+        hb, hl, hf = next(ref)
+        img, lab = next(pre)
+        assert tuple(img.shape) == (4, 16, 16, 16) and torch.equal(lab.cpu(), torch.from_numpy(hl))
+        want = _tf1_resize_flip_normalise(hb, hf, 16, 16)
+        assert np.abs(img.cpu().numpy() - want).max() < 2e-6
