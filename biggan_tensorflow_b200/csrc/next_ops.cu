@@ -102,10 +102,10 @@ extern "C" int bg_ortho_reg_rows(const float* G, float* dG, float* rowloss, floa
   return BG_OK;
 }
 extern "C" int bg_renorm_factors(const float* mean, const float* var, float* rmean, float* rvar, const float* weight, float* weight_out,
-                                 float* r, float* d, int C, float eps, float rmin, float rmax, float dmax, float decay, float fade,
-                                 int update_state, void* stream) {
+                                 float* r, float* d, int C, float eps, float rmin, float rmax, float dmax, float decay, float one_minus_decay,
+                                 float fade, float one_minus_fade, int update_state, void* stream) {
   BG_LAUNCH(renorm_factors_kernel, (unsigned)bg_cdiv(C, 128), 128, (cudaStream_t)stream, mean, var, rmean, rvar, weight, weight_out, r, d, C,
-            eps, rmin, rmax, dmax, decay, fade, update_state);
+            eps, rmin, rmax, dmax, decay, one_minus_decay, fade, one_minus_fade, update_state);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

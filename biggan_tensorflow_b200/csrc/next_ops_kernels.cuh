@@ -157,17 +157,18 @@ __global__ void ortho_sum_rows_kernel(const float* __restrict__ rowloss, int C, 
 //   sigma = sqrt(var + eps), rsigma = sqrt(rvar + eps), wsig = w rsigma + (1-w) sigma, wmean = w rmean + (1-w) mean
 //   r = clip(sigma / wsig, rmin, rmax),   d = clip((mean - wmean) / wsig, -dmax, dmax)        (constants in the backward)
 // then, unless the statistics are the shared population ones (update_state = 0), the running statistics move by
-// `decay` and the fade-in weight by `fade`.  The normalisation itself is a conditional batch norm with
+// `decay` and the fade-in weight by `fade` (the complements 1 - decay, 1 - fade are passed in: the reference forms them
+// in double precision before they become float32 constants).  The normalisation itself is a conditional batch norm with
 //   gamma' = r gamma,  beta' = beta + d gamma      (per sample and channel)
 // whose adjoint is  dgamma = r dgamma' + d dbeta',  dbeta = dbeta'.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void renorm_factors_kernel(const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ rmean,
                                       float* __restrict__ rvar, const float* __restrict__ weight, float* __restrict__ weight_out,
                                       float* __restrict__ r, float* __restrict__ d, int C, float eps, float rmin, float rmax, float dmax,
-                                      float decay, float fade, int update_state) {
+                                      float decay, float one_minus_decay, float fade, float one_minus_fade, int update_state) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const float w = weight ? weight[0] : 1.f;
-  if (c == 0 && weight_out) weight_out[0] = update_state ? w * fade + (1.f - fade) : w;
+  if (c == 0 && weight_out) weight_out[0] = update_state ? w * fade + one_minus_fade : w;
   if (c >= C) return;
   const float m = mean[c], v = var[c], rm = rmean[c], rv = rvar[c];
   const float sigma = sqrtf(v + eps), rsigma = sqrtf(rv + eps);
@@ -176,8 +177,8 @@ __global__ void renorm_factors_kernel(const float* __restrict__ mean, const floa
   r[c] = fminf(fmaxf(sigma / wsig, rmin), rmax);
   d[c] = fminf(fmaxf((m - wmean) / wsig, -dmax), dmax);
   if (update_state) {
-    rmean[c] = rm * decay + m * (1.f - decay);
-    rvar[c] = rv * decay + v * (1.f - decay);
+    rmean[c] = rm * decay + m * one_minus_decay;
+    rvar[c] = rv * decay + v * one_minus_decay;
   }
 }
 __global__ void renorm_affine_fwd_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ r,

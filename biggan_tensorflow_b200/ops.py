@@ -1102,12 +1102,12 @@ def condition_batch_renorm(x, z, opt={}, scope='batch_renorm', _act=_lib.ACT_NON
             r, d = empty([c], F32), empty([c], F32)
             if shared:       # r, d against the population statistics as they were BEFORE this step's update (:671-673)
                 call("bg_renorm_factors", mean, var, test_mean.data, test_var.data, None, None, r, d, c, 1e-05,
-                     float(renorm_clipping["rmin"]), float(renorm_clipping["rmax"]), float(renorm_clipping["dmax"]), 0.0, 0.0, 0, stream())
+                     float(renorm_clipping["rmin"]), float(renorm_clipping["rmax"]), float(renorm_clipping["dmax"]), 0.0, 0.0, 0.0, 0.0, 0, stream())
             else:
                 w_out = empty([1], F32)
                 call("bg_renorm_factors", mean, var, renorm_mean.data, renorm_var.data, renorm_weight.data, w_out, r, d, c, 1e-05,
                      float(renorm_clipping["rmin"]), float(renorm_clipping["rmax"]), float(renorm_clipping["dmax"]),
-                     float(renorm_decay), float(renorm_fadein_decay), 1, stream())
+                     float(renorm_decay), float(1 - renorm_decay), float(renorm_fadein_decay), float(1 - renorm_fadein_decay), 1, stream())
                 renorm_weight.data.copy_(w_out.reshape(renorm_weight.data.shape))
             gamma, beta = _renorm_affine(gamma, beta, r, d)
         return _bn_core(x, gamma, beta, c, test_mean, test_var, test_decay, lambda n: 1.0, opt, _act)

@@ -275,11 +275,12 @@ int bg_ortho_reg_rows(const float* G, float* dG, float* rowloss, float* loss, in
 
 /* conditional batch renorm, ops.py:645-715.  bg_renorm_factors: r, d [C] from the batch statistics (mean, var) and the
  * running ones (rmean, rvar) blended by the fade-in weight (weight NULL = 1: shared population statistics); with
- * update_state the running statistics move by `decay` in place and weight_out[0] = weight * fade + (1 - fade).
+ * update_state the running statistics move by `decay` in place and weight_out[0] = weight * fade + one_minus_fade.
  * bg_renorm_affine_fwd: gamma2 = r gamma, beta2 = beta + d gamma over [B,C]; _bwd: dgamma = r dgamma2 + d dbeta2. */
 int bg_renorm_factors(const float* mean, const float* var, float* rmean, float* rvar, const float* weight,
                       float* weight_out, float* r, float* d, int C, float eps, float rmin, float rmax, float dmax,
-                      float decay, float fade, int update_state, void* stream);
+                      float decay, float one_minus_decay, float fade, float one_minus_fade, int update_state,
+                      void* stream);
 int bg_renorm_affine_fwd(const float* gamma, const float* beta, const float* r, const float* d, float* gamma2,
                          float* beta2, int B, int C, void* stream);
 int bg_renorm_affine_bwd(const float* dgamma2, const float* dbeta2, const float* r, const float* d, float* dgamma,

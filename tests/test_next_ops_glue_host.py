@@ -142,3 +142,40 @@ def test_glue_of_the_renorm_affine_map(host_product):
     assert np.allclose(g2.numpy(), r.numpy() * gamma.numpy(), atol=1e-6) and np.allclose(b2.numpy(), beta.numpy() + d.numpy() * gamma.numpy(), atol=1e-6)
     assert np.allclose(gamma.grad.numpy(), r.numpy() * dg2.numpy() + d.numpy() * db2.numpy(), atol=1e-5)
     assert np.allclose(beta.grad.numpy(), db2.numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cbrn_fresh", "cbrn_warm", "cbrn_shared", "cbrn_inference"])
+def test_glue_of_condition_batch_renorm_matches_reference_source(host_product, monkeypatch, name):
+    """ops.condition_batch_renorm (ops.py:645-715) as shipped -- statistics pass, bg_renorm_factors, the affine map, then the
+    conditional batch-norm kernel set (loop stand-ins here) -- against the reference-generated vectors: output, d/dx, and all
+    state (pop_mean / pop_var, renorm_mean / renorm_var, renorm_weight).  The two SN projections are oracle stand-ins."""
+    import torch as _torch
+    from biggan_tensorflow_b200 import ops
+    from biggan_tensorflow_b200.tensor import Tensor, backward
+    from oracle import ref_ops as R
+    case = [c for c in C.NEXT_OP_CASES if c["name"] == name][0]
+    g = np.load(os.path.join(HERE, "golden", "ref_ops_next.npz"))
+    st = host_product
+    st.load({k: np.asarray(v, np.float32) for k, v in case["var_init"].items()})
+    for k in list(st.vars):                                            # state variables (load() guesses by name)
+        st.vars[k].trainable = st.vars[k].requires_grad = False
+    rs = R.RefStore(_torch.float64)
+
+    def fc(z, units, opt, use_bias=True, lrmul=1.0, scope='fully_0'):
+        from biggan_tensorflow_b200 import tf_shim
+        rs.scope = list(tf_shim.get_store().scope)
+        y = R.fully_connected(rs, z.data.double(), units, opt, use_bias, lrmul, scope)
+        return Tensor(y.detach().float().contiguous(), requires_grad=True)
+
+    monkeypatch.setattr(ops, "fully_connected", fc)
+    opt = C.make_opt({"relu": ops.relu}, case["opt"])
+    xs = {k: _tensor(v) for k, v in C.case_inputs(case).items()}
+    y = ops.cond_bn(xs["x"], xs["z"], opt=opt)
+    backward([(y, _torch.from_numpy(C.case_dy(case, tuple(y.shape))))])
+    C.check(g, name + "/out", y.numpy(), 2e-5)
+    C.check(g, name + "/gin/x", xs["x"].grad.numpy(), 2e-5)
+    for key in (k for k in g.files if k.startswith(name + "/state/")):
+        n = key.split("/state/")[1]
+        if n.endswith("/u"):
+            continue                                                   # the projections' spectral-norm state lives in the stand-in
+        C.check(g, key, st.vars[n].data.numpy(), 2e-5)

@@ -183,7 +183,7 @@ def test_renorm_factors_and_affine(emul, shared):
     r, d, w_out = np.zeros(C, np.float32), np.zeros(C, np.float32), np.zeros(1, np.float32)
     eps, rmin, rmax, dmax, decay, fade = 1e-5, 1 / 1.2, 1.2, 0.3, 0.8, 0.99
     rc = emul.bg_renorm_factors(ptr(mean), ptr(var), ptr(rmean), ptr(rvar), None if shared else ptr(w), None if shared else ptr(w_out),
-                                ptr(r), ptr(d), C, eps, rmin, rmax, dmax, decay, fade, 0 if shared else 1, None)
+                                ptr(r), ptr(d), C, eps, rmin, rmax, dmax, decay, 1 - decay, fade, 1 - fade, 0 if shared else 1, None)
     assert rc == 0
     ww = 1.0 if shared else 0.7
     sigma, rsigma = np.sqrt(var.astype(np.float64) + eps), np.sqrt(rv0.astype(np.float64) + eps)
