@@ -54,3 +54,20 @@ def test_io_library_exports_every_symbol_of_its_header():
     so = ctypes.CDLL(os.path.join(ROOT, "biggan_tensorflow_b200", "libbiggan_io.so"))
     for n in names:
         assert hasattr(so, n), "missing export " + n
+
+
+def test_option_errors_of_the_config_level_switches():
+    """BigGAN.py:71-84 (activation), :257-271 (regularisation), utils.py:204 (regulariser type)."""
+    import pytest
+    from biggan_tensorflow_b200 import model, utils
+    with pytest.raises(ValueError, match="Unknown activation function: swish"):
+        model._opts(model.Config(activation="swish"), True)
+    with pytest.raises(ValueError, match="Unknown regularization method: l3"):
+        model._opts(model.Config(g_regularization="l3"), True)
+    g_opt, d_opt = model._opts(model.Config(g_regularization="ortho_cosine"), is_training=False)     # sampling graph: no regulariser
+    assert g_opt["conv"]["regularizer"] is None and g_opt["fc_regularizer"] is None
+    g_opt, d_opt = model._opts(model.Config(g_regularization="ortho", activation="lrelu", bn_in_d=True, downsampling_method="pool_only"), True)
+    assert g_opt["conv"]["regularizer"].type == "ortho" and "regularizer" in g_opt["conv"] and d_opt["conv"]["regularizer"] is None
+    assert d_opt["bn_in_d"] is True and d_opt["downsampling_method"] == "pool_only" and g_opt["act"] is d_opt["act"]
+    with pytest.raises(ValueError, match="Unknown regularization method."):
+        utils.orthogonal_regularizer(1e-4, type="nope")._kind()

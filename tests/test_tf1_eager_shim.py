@@ -149,3 +149,27 @@ def test_variable_scope_naming_reuse_and_deferred_assign():
     assert v.numpy().tolist() == [0.0, 0.0]               # reads inside the run still see the old value
     E.end_run()
     assert v.numpy().tolist() == [5.0, 6.0]
+
+
+def test_more_examples_of_the_tf_docs():
+    # tf.nn.depth_to_space: [1,1,1,4] with block 2 -> [[[[1],[2]],[[3],[4]]]]; the [1,1,1,12] example -> 2x2 RGB pixels
+    x = T(np.array([[[[1., 2., 3., 4.]]]]))
+    assert E.depth_to_space(x, 2).numpy().tolist() == [[[[1.0], [2.0]], [[3.0], [4.0]]]]
+    x = T(np.arange(1., 13.).reshape(1, 1, 1, 12))
+    assert E.depth_to_space(x, 2).numpy().tolist() == [[[[1., 2., 3.], [4., 5., 6.]], [[7., 8., 9.], [10., 11., 12.]]]]
+    # tf.split with sizes, tf.meshgrid(indexing='ij'), tf.clip_by_value, tf.cast float -> int truncation, floor div / mod on ints
+    parts = E.split(T(np.arange(10.).reshape(1, 10)), [4, 6], axis=-1)
+    assert [p.shape.as_list() for p in parts] == [[1, 4], [1, 6]]
+    a, b = E.meshgrid(E.range_(2), E.range_(3), indexing="ij")
+    assert a.numpy().tolist() == [[0, 0, 0], [1, 1, 1]] and b.numpy().tolist() == [[0, 1, 2], [0, 1, 2]]
+    assert E.clip_by_value(T(np.array([-3, 0, 9])), 0, 5).numpy().tolist() == [0, 0, 5]
+    assert E.cast(T(np.array([8.5, -1.5, 16.99])), E.int32).numpy().tolist() == [8, -1, 16]
+    seven = T(np.array(7))
+    assert int(seven // 2) == 3 and int(seven % 2) == 1 and int(1 - seven % 2) == 0
+    # tf.nn.leaky_relu, tf.image.resize_nearest_neighbor, tf.reduce_mean(keepdims), tf.norm
+    assert E.leaky_relu(T(np.array([-2., 3.])), 0.2).numpy().tolist() == [-0.4, 3.0]
+    up = E.resize_nearest_neighbor(T(np.arange(4.).reshape(1, 2, 2, 1)), [4, 4]).numpy()[0, :, :, 0]
+    assert up.tolist() == [[0, 0, 1, 1], [0, 0, 1, 1], [2, 2, 3, 3], [2, 2, 3, 3]]
+    m = E.reduce_mean(T(np.arange(24.).reshape(2, 3, 4)), axis=[1, 2], keepdims=True)
+    assert m.shape.as_list() == [2, 1, 1] and m.numpy().ravel().tolist() == [5.5, 17.5]
+    assert float(E.norm(T(np.array([3., 4.]))).numpy()) == 5.0
