@@ -10,3 +10,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_referen
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-graph --quick --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1 || true
 tail -5 gpurun_out/pytest_gpu.log gpurun_out/pytest_unverified.log gpurun_out/bench_1gpu.json
+# one full-set capture of the dominant kernel (dram traffic for roofline.traffic; tensor-pipe activity)
+ncu --set full --clock-control none --import-source on -k regex:tc_fwd_kernel -s 60 -c 3 -o gpurun_out/prof_tc_fwd \
+    python bench.py --steps 1 --warmup 1 --no-graph --quick --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 || true
+ncu -i gpurun_out/prof_tc_fwd.ncu-rep --page raw --csv 2>/dev/null | head -c 200000 > gpurun_out/prof_tc_fwd_raw.csv || true
