@@ -15,7 +15,7 @@ import torch
 from . import DiffAugment_tf, _lib, ops
 from ._lib import call
 from .model import Config, discriminator, generator
-from .tensor import (BF16, F32, Tensor, accumulate_grad, backward, bg_dtype, clear_tape, empty, no_grad, record,
+from .tensor import (BF16, F32, Tensor, accumulate_grad, backward, bg_dtype, clear_tape, device, empty, no_grad, record,
                      recording, stream)
 from .tf_shim import VariableStore, set_store
 
@@ -76,9 +76,11 @@ class Trainer:
         """Create every variable (dry forward on one sample), then pack each network's trainables into
         flat arenas (params / grads / Adam m, v / EMA shadows)."""
         cfg = self.cfg
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = device()
         z = torch.zeros(2, 1, 1, cfg.z_dim, device=dev)
         cls = torch.zeros(2, max(cfg.n_labels, 1), device=dev)
+        set_store(self.store)
+        ops.set_compute_dtype(self.compute_dtype)
         self.store.begin_phase()
         self.store.sn_registry = {}                  # enumerate every spectral_norm call of both networks
         with no_grad():
@@ -121,6 +123,7 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------
     def _set_phase(self, net):
+        set_store(self.store)                        # the variable store is process-global (like TF's default graph)
         for k, v in self.store.vars.items():
             v.requires_grad = bool(v.trainable and net in k)
             v.grad = None
@@ -180,9 +183,20 @@ class Trainer:
             x.aux = aug_fake.aux
         if cfg.bn_in_d:
             # batch statistics inside D: the two instantiations (BigGAN.py:807, :857) normalise their own batch, so they
-            # cannot share one pass.  The moving statistics take the two updates in this order (TF leaves it unspecified).
+            # cannot share one pass.
+            # Both instantiations move D's moving statistics with an assign_sub whose delta is formed from the value the
+            # variable had when the run began (oracle/tf1_eager.py, session model): final = s_real + s_fake - start.
+            moving = [v for k, v in self.store.vars.items() if "discriminator" in k and "/moving_" in k]
+            start = [v.data.clone() for v in moving]
             out_r = discriminator(cfg, aug_real)
+            after_real = [v.data.clone() for v in moving]
+            for v, s0 in zip(moving, start):
+                v.data.copy_(s0)
             out_f = discriminator(cfg, aug_fake)
+            for v, s0, s1 in zip(moving, start, after_real):
+                n = v.data.numel()
+                call("bg_add", s1, v.data, s1, n, _lib.BG_F32, stream())                              # s_real + s_fake
+                call("bg_axpby", s0, s1, None, -1.0, 1.0, v.data, n, _lib.BG_F32, stream())            # - start
             real_logits, fake_logits = out_r["real"], out_f["real"]
             out = {"cls": out_r.get("cls")}
         else:
@@ -271,6 +285,7 @@ class Trainer:
             saved = ar["params"].clone()
             ar["params"].copy_(o["ema"])
         try:
+            set_store(self.store)
             self.store.begin_phase()
             clear_tape()
             self.sn_groups["generator"].forward(self.store)

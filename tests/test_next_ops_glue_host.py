@@ -25,7 +25,7 @@ STANDALONE = {"prelu", "lrelu", "upconv_nn", "downconv_pool_only"}           # c
 @pytest.fixture(scope="module")
 def host_so(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("host_lib") / "host_lib.so")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-x", "c++", "-shared", "-fPIC",
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-x", "c++", "-shared", "-fPIC",
                     os.path.join(HERE, "host_emul", "host_lib.cpp"), "-o", so], check=True)
     return so
 
