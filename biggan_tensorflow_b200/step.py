@@ -234,8 +234,8 @@ class Trainer:
         self._finish_grads("generator")
         loss = g_loss.data
         if self.reg_loss is not None:
-            loss = torch.empty_like(g_loss.data)
-            call("bg_add", g_loss.data, self.reg_loss, loss, 1, _lib.BG_F32, stream())
+            loss = torch.empty_like(g_loss.data)      # like the other terms, each rank reports its 1/world share: the sum over ranks is the loss
+            call("bg_axpby", self.reg_loss, g_loss.data, None, 1.0 / self.world, 1.0, loss, 1, _lib.BG_F32, stream())
         if apply:
             self._adam("generator", cfg.g_lr)
         return loss, {"fake": fake, "fake_logits": out["real"]}

@@ -5,9 +5,7 @@ kernel source under the emulation prelude + loop stand-ins for bg_add / bg_axpby
 run would check about the glue -- argument order into the C ABI, variable creation and naming, the tape and gradient
 accumulation -- against the reference-generated vectors.  The product package itself has no CPU path: nothing outside
 this test can select the host library."""
-import ctypes
 import os
-import subprocess
 import sys
 
 import numpy as np
@@ -17,6 +15,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 import ref_cases as C                       # noqa: E402
+sys.path.insert(0, os.path.join(HERE, "host_emul"))
+import host_env                             # noqa: E402
 
 ROOT = os.path.dirname(HERE)
 STANDALONE = {"prelu", "lrelu", "upconv_nn", "downconv_pool_only"}           # cases that need no conv kernel
@@ -24,28 +24,13 @@ STANDALONE = {"prelu", "lrelu", "upconv_nn", "downconv_pool_only"}           # c
 
 @pytest.fixture(scope="module")
 def host_so(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("host_lib") / "host_lib.so")
-    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-x", "c++", "-shared", "-fPIC",
-                    os.path.join(HERE, "host_emul", "host_lib.cpp"), "-o", so], check=True)
-    return so
+    return host_env.build(str(tmp_path_factory.mktemp("host_lib") / "host_lib.so"))
 
 
 @pytest.fixture()
 def host_product(host_so, monkeypatch):
-    from biggan_tensorflow_b200 import _lib, ops, tensor, tf_shim, utils
-    lib = ctypes.CDLL(host_so)
-    for name, (res, args) in _lib.DECLS.items():
-        if hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.restype, fn.argtypes = res, args
-    monkeypatch.setattr(_lib, "lib", lib)
-    cpu = lambda: torch.device("cpu")
-    for mod in (tensor, tf_shim):
-        monkeypatch.setattr(mod, "device", cpu)
-    for mod in (tensor, ops, utils, tf_shim):
-        monkeypatch.setattr(mod, "stream", lambda: None)
-    monkeypatch.setattr(tensor, "_ws_cache", {})
-    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    from biggan_tensorflow_b200 import ops, tensor, tf_shim
+    host_env.activate(host_so, monkeypatch.setattr)
     st = tf_shim.set_store(tf_shim.VariableStore())
     ops.set_compute_dtype(torch.float32)
     tensor.clear_tape()

@@ -9,38 +9,25 @@ import os
 import pytest
 import torch
 
-from test_next_ops_glue_host import host_so                      # noqa: F401  (fixture)
+from test_next_ops_glue_host import host_env, host_so            # noqa: F401  (fixture)
 import test_zz_reference_golden_gpu as G
 
 
 @pytest.fixture()
 def host_trainer(host_so, monkeypatch):
-    import ctypes
-    from biggan_tensorflow_b200 import DiffAugment_tf, _lib, ops, sn_group, step, tensor, tf_shim, utils
-    lib = ctypes.CDLL(host_so)
-    for name, (res, args) in _lib.DECLS.items():
-        if hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.restype, fn.argtypes = res, args
-    monkeypatch.setattr(_lib, "lib", lib)
-    for mod in (tensor, tf_shim, step, sn_group, DiffAugment_tf):
-        monkeypatch.setattr(mod, "device", lambda: torch.device("cpu"))
-    for mod in (tensor, ops, utils, tf_shim, step, sn_group, DiffAugment_tf):
-        monkeypatch.setattr(mod, "stream", lambda: None)
-    monkeypatch.setattr(tensor, "_ws_cache", {})
-    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    DiffAugment_tf._queue.clear()
+    from biggan_tensorflow_b200 import tensor, tf_shim
+    host_env.activate(host_so, monkeypatch.setattr)
     yield lambda a: torch.from_numpy(a)
     tf_shim.set_store(tf_shim.VariableStore())
     tensor.clear_tape()
 
 
-@pytest.mark.parametrize("name", ["net64", "net64cli", "net64variants"])
+@pytest.mark.parametrize("name", ["net64", "net128da", "net256", "net512", "net64cli", "net64variants"])
 def test_trainer_phases_match_reference_networks_on_the_host(host_trainer, name):
     """One D phase and one G phase (losses, every gradient norm, selected gradients, all state after each phase, variable
-    names and shapes) for the canonical 64x64 network, the fork's CLI defaults (prelu, ortho_cosine, flood, DiffAugment)
-    and the layer variants (lrelu, resize_conv, conv3, resize_conv1, bn_in_d, ortho)."""
+    names and shapes) for the canonical networks at 64, 128 (+ DiffAugment), 256 and 512 pixels (BASELINE configs 1-4 at narrow
+    width), the fork's CLI defaults (prelu, ortho_cosine, flood, DiffAugment) and the layer variants (lrelu, resize_conv,
+    conv3, resize_conv1, bn_in_d, ortho)."""
     G._cuda_net(name, dev=host_trainer)
 
 
