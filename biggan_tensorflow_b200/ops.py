@@ -339,6 +339,20 @@ def _padded_bias(bias, c_pad):
     return pb
 
 
+def _padded_param(p, c_pad, fill):
+    """Copy of a per-channel parameter [C] extended to c_pad entries with `fill` (plumbing); the gradient of the first C
+    entries flows back."""
+    C = p.shape[0]
+    pp = Tensor(torch.full((c_pad,), float(fill), dtype=F32, device=p.data.device), requires_grad=p.requires_grad)
+    pp.data[:C].copy_(p.data)
+    if recording(p):
+        def bw():
+            if pp.grad is not None:
+                accumulate_grad(p, pp.grad[:C].contiguous(), own=True)
+        record(bw)
+    return pp
+
+
 def _conv_geometry(x, channels, kernel, stride, pad, opt):
     """pad logic of ops.py:65-84."""
     B, H, W, Cin = x.shape
@@ -1122,7 +1136,24 @@ def batch_norm(x, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
         beta = get_variable("beta", [c], initializer=constant_initializer(0.0))
         mm = get_variable("moving_mean", [c], initializer=constant_initializer(0.0), trainable=False)
         mv = get_variable("moving_variance", [c], initializer=constant_initializer(1.0), trainable=False)
-        return _bn_core(x, gamma, beta, 0, mm, mv, momentum, lambda n: n / max(n - 1.0, 1.0), opt, _act)
+        vec = 4 if x.dtype == F32 else 8              # the BN kernels move 16-byte channel vectors (norm.cu)
+        if c % vec == 0:
+            return _bn_core(x, gamma, beta, 0, mm, mv, momentum, lambda n: n / max(n - 1.0, 1.0), opt, _act)
+        # narrow tensors (bn_in_d on the 3-channel image, ops.py:295): run on zero-padded channels.  A zero channel has
+        # mean 0 / variance 0 and normalises to its beta (0); its parameters and statistics are dropped again.
+        cp = round_up(c, vec)
+        xp = pad_channels(x, cp)
+        gamma_p, beta_p = _padded_param(gamma, cp, 1.0), _padded_param(beta, cp, 0.0)
+        mm_p = Tensor(torch.zeros(cp, dtype=F32, device=x.data.device))
+        mv_p = Tensor(torch.ones(cp, dtype=F32, device=x.data.device))
+        mm_p.data[:c].copy_(mm.data)
+        mv_p.data[:c].copy_(mv.data)
+        y = _bn_core(xp, gamma_p, beta_p, 0, mm_p, mv_p, momentum, lambda n: n / max(n - 1.0, 1.0), opt, _act)
+        mm.data.copy_(mm_p.data[:c])
+        mv.data.copy_(mv_p.data[:c])
+        y = slice_channels(y, c)
+        y.aux = None
+        return y
 
 
 def bn(x, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):

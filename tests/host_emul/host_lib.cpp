@@ -45,8 +45,10 @@ extern "C" int bg_bgemm(const void* A, const void* Bm, void* C, int batch, int M
 //      dgamma[b,c] = sum g xhat, dbeta[b,c] = sum g (g = dy masked by the ReLU); s = [sum_b gamma dbeta | sum_b gamma dgamma];
 //      dx = rstd (gamma g - s1/count - xhat s2/count).
 extern "C" size_t bg_bn_workspace_bytes(int, long, int) { return 256; }
+#define BN_VEC_OK(C) if ((C) % 4 != 0) { bg_set_error("bn: C=%d must be a multiple of 4", (C)); return BG_ERR_UNSUPPORTED; }   // as norm.cu
 extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, int dtype, void*, size_t, void*) {
   if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  BN_VEC_OK(C);
   for (int c = 0; c < 2 * C; ++c) sums[c] = 0.0;
   const float* p = (const float*)x;
   for (long i = 0; i < (long)B * HW; ++i)
@@ -69,6 +71,7 @@ static inline float bn_act(float v, int act) { return act == BG_ACT_RELU ? (v > 
 extern "C" int bg_bn_apply(const void* x, const float* mean, const float* var, const float* gamma, const float* beta, int gb_bstride, void* y,
                            int act, float eps, int B, long HW, int C, int dtype, void*) {
   if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  BN_VEC_OK(C);
   for (int b = 0; b < B; ++b)
     for (long r = 0; r < HW; ++r)
       for (int c = 0; c < C; ++c) {
@@ -82,6 +85,7 @@ extern "C" int bg_bn_bwd_reduce(const void* dy, const void* x, const float* mean
                                 int gb_bstride, float* dgamma, float* dbeta, int act, float eps, int B, long HW, int C, int dtype, void*,
                                 size_t, void*) {
   if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  BN_VEC_OK(C);
   for (int b = 0; b < B; ++b)
     for (int c = 0; c < C; ++c) {
       const float rs = 1.f / std::sqrt(var[c] + eps), gm = gamma[(long)b * gb_bstride + c], inv = rs * gm;
@@ -110,6 +114,7 @@ extern "C" int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean,
                                int gb_bstride, const double* s, double count, void* dx, int act, float eps, int B, long HW, int C, int dtype,
                                void*) {
   if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  BN_VEC_OK(C);
   for (int b = 0; b < B; ++b)
     for (long r = 0; r < HW; ++r)
       for (int c = 0; c < C; ++c) {
@@ -205,9 +210,11 @@ static inline long widx(const bg_conv_desc* d, int ky, int kx, int ci, int co) {
 extern "C" size_t bg_conv2d_fwd_workspace_bytes(const bg_conv_desc*, int) { return 0; }
 extern "C" size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc*, int) { return 0; }
 extern "C" size_t bg_conv2d_wgrad_workspace_bytes(const bg_conv_desc*, int) { return 16; }
+#define CONV_DESC_OK(d) if ((d)->stride < 1 || (d)->stride > 2) { bg_set_error("conv desc: stride %d unsupported", (d)->stride); return BG_ERR_UNSUPPORTED; }
 extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x_, const void* w_, const void*, const float* bias, const void* res_, void* y_,
                              int act, int dtype, void*, size_t, int, void*) {
   STANDIN_F32(dtype);
+  CONV_DESC_OK(d);
   const float *x = (const float*)x_, *w = (const float*)w_, *res = (const float*)res_;
   float* y = (float*)y_;
   const long ny = (long)d->B * d->Ho * d->Wo * d->Co;
@@ -311,6 +318,7 @@ extern "C" int bg_pad_channels(const void* src, int sdt, void* dst, int ddt, lon
 }
 extern "C" int bg_maxpool2_fwd(const void* x_, void* y_, int B, int H, int W, int C, int dtype, void*) {
   STANDIN_F32(dtype);
+  if (H % 2 || W % 2) { bg_set_error("maxpool2: odd size"); return BG_ERR_UNSUPPORTED; }
   const float* x = (const float*)x_; float* y = (float*)y_;
   for (int b = 0; b < B; ++b) for (int oy = 0; oy < H / 2; ++oy) for (int ox = 0; ox < W / 2; ++ox) for (int c = 0; c < C; ++c) {
     const long base = (((long)b * H + 2 * oy) * W + 2 * ox) * C + c;
