@@ -1,5 +1,5 @@
 """CPU execution check of the SURVEY 8(f) kernels (`csrc/next_ops.cu`): the SAME source is compiled for the host with
-`-DBG_HOST_EMULATION` (tests/host_emul/cuda_host_emul.h: blocks run in turn, the threads of a block are std::threads, so
+`-DBG_HOST_EMULATION` (tests/host_emul/cuda_host_emul.h: blocks run in turn, the threads of a block in turn or -- when the kernel synchronises -- as round-robin fibers, so
 `__syncthreads` / warp shuffles behave) and called through the same C entry points, argument for argument, against the
 oracle.  This was written when no GPU time was left in round 1: it validates index arithmetic, launch geometry and the
 fixed-order reductions of the real kernel code; the GPU parity tests (tests/test_zz_reference_golden_gpu.py, gated) still
