@@ -390,9 +390,9 @@ def save(trainer, directory, step, model_name="BigGAN"):
     variables = trainer.store.export()
     adam = {}
     for net in ("generator", "discriminator"):
-        m, v = _arena_slices(trainer, net, trainer.opt[net]["m"]), _arena_slices(trainer, net, trainer.opt[net]["v"])
+        m, v = _arena_slices(trainer, net, trainer.full_opt(net, "m")), _arena_slices(trainer, net, trainer.full_opt(net, "v"))
         adam[net] = {n: (m[n], v[n]) for n in m}
-    ema = _arena_slices(trainer, "generator", trainer.opt["generator"]["ema"])
+    ema = _arena_slices(trainer, "generator", trainer.full_ema())
     t_g = int(round(float(trainer.opt["generator"]["state"][0].cpu())))
     t_d = int(round(float(trainer.opt["discriminator"]["state"][0].cpu())))
     tensors = to_tf_tensors(variables, list(adam["generator"]), list(adam["discriminator"]), adam["generator"], adam["discriminator"],

@@ -44,11 +44,15 @@ def split_rows(t, sizes):
 
 
 class Trainer:
-    def __init__(self, cfg: Config, compute_dtype=F32, rank=0, world_size=1, process_group=None):
+    def __init__(self, cfg: Config, compute_dtype=F32, rank=0, world_size=1, process_group=None, shard_optimizer=False):
+        """shard_optimizer (off by default; SURVEY 8e "optionally optimizer-sharded"): with world_size > 1 the update phases
+        reduce-scatter the gradient arena, run Adam(+EMA) on this rank's 1/world slice and all-gather the parameters --
+        the same bytes on the wire as the all-reduce, 1/world of the optimizer's HBM traffic per rank."""
         self.cfg = cfg
         self.compute_dtype = compute_dtype
         self.rank, self.world = rank, world_size
         self.pg = process_group
+        self.shard = bool(shard_optimizer) and world_size > 1
         self.store = set_store(VariableStore())
         ops.set_compute_dtype(compute_dtype)
         assert cfg.batch_size % world_size == 0, "global batch must divide across ranks"
@@ -91,7 +95,7 @@ class Trainer:
         for k, d in snap.items():       # undo the dry run's side effects on u / BN running stats
             self.store.vars[k].data.copy_(torch.from_numpy(self._initial(k, d.shape)).to(dev))
         for net in ("generator", "discriminator"):
-            ar = self.store.pack(net)
+            ar = self.store.pack(net, multiple=4 * self.world if self.shard else 1)
             n = ar["params"].numel()
             self.opt[net] = {"m": torch.zeros(n, device=dev), "v": torch.zeros(n, device=dev),
                              "ema": ar["params"].clone() if net == "generator" else None,
@@ -134,7 +138,11 @@ class Trainer:
         for grp in self.sn_groups.values():          # every forward of a network advances its u once per phase
             grp.forward(self.store)
 
-    def _finish_grads(self, net):
+    def _shard_slice(self, net):
+        n = self.store.arenas[net]["params"].numel() // self.world
+        return slice(self.rank * n, (self.rank + 1) * n)
+
+    def _finish_grads(self, net, for_update=False):
         self.sn_groups[net].backward()
         ar = self.store.arenas[net]
         for v in ar["vars"]:
@@ -149,7 +157,13 @@ class Trainer:
                 reg.evaluate(v.data, self.reg_loss, dW=v.grad_view, grad_scale=1.0 / self.world)
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(ar["grads"], group=self.pg)          # NCCL over NVLink; sum == global-batch gradient
+            if self.shard and for_update:                        # only this rank's slice of the summed gradient is needed
+                sl = self._shard_slice(net)
+                shard = torch.empty_like(ar["grads"][sl])
+                dist.reduce_scatter_tensor(shard, ar["grads"], group=self.pg)
+                ar["grads"][sl].copy_(shard)
+            else:
+                dist.all_reduce(ar["grads"], group=self.pg)      # NCCL over NVLink; sum == global-batch gradient
         return ar
 
     def _adam(self, net, lr):
@@ -158,8 +172,30 @@ class Trainer:
         ar = self.store.arenas[net]
         o = self.opt[net]
         call("bg_adam_lr_step", o["state"], float(lr), float(cfg.beta1), float(cfg.beta2), stream())
+        if self.shard:
+            import torch.distributed as dist
+            sl = self._shard_slice(net)
+            p = ar["params"][sl]
+            call("bg_adam_ema_step", p, ar["grads"][sl], o["m"][sl], o["v"][sl], o["ema"][sl] if o["ema"] is not None else None,
+                 p.numel(), 0.0, o["state"][1:], float(cfg.beta1), float(cfg.beta2), 1e-8, float(cfg.moving_decay), 1.0, stream())
+            dist.all_gather_into_tensor(ar["params"], p.clone(), group=self.pg)
+            return
         call("bg_adam_ema_step", ar["params"], ar["grads"], o["m"], o["v"], o["ema"], ar["params"].numel(),
              0.0, o["state"][1:], float(cfg.beta1), float(cfg.beta2), 1e-8, float(cfg.moving_decay), 1.0, stream())
+
+    def full_opt(self, net, key):
+        """Optimizer state `key` ('m', 'v', 'ema') over the whole arena (with a sharded optimizer every rank maintains its
+        slice only: collective call)."""
+        t = self.opt[net][key]
+        if self.shard and t is not None:
+            import torch.distributed as dist
+            full = torch.empty_like(t)
+            dist.all_gather_into_tensor(full, t[self._shard_slice(net)].clone(), group=self.pg)
+            return full
+        return t
+
+    def full_ema(self):
+        return self.full_opt("generator", "ema")
 
     def _as_input(self, img):
         t = Tensor(img)
@@ -212,7 +248,7 @@ class Trainer:
             cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
             d_loss = d_loss + cfg.d_cls_loss_weight * cls_loss(labels, real_cls)                   # :853
         backward([(d_loss, torch.ones(1, device=real.device))])
-        self._finish_grads("discriminator")
+        self._finish_grads("discriminator", for_update=apply)
         if apply:
             self._adam("discriminator", cfg.d_lr)
         return d_loss.data, {"fake": fake, "real_logits": real_logits, "fake_logits": fake_logits}
@@ -231,7 +267,7 @@ class Trainer:
             cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
             g_loss = g_loss + cfg.g_cls_loss_weight * cls_loss(cls_z, out["cls"])                  # :894
         backward([(g_loss, torch.ones(1, device=z.device))])
-        self._finish_grads("generator")
+        self._finish_grads("generator", for_update=apply)
         loss = g_loss.data
         if self.reg_loss is not None:
             loss = torch.empty_like(g_loss.data)      # like the other terms, each rank reports its 1/world share: the sum over ranks is the loss
@@ -283,7 +319,7 @@ class Trainer:
         saved = None
         if ema and o["ema"] is not None:
             saved = ar["params"].clone()
-            ar["params"].copy_(o["ema"])
+            ar["params"].copy_(self.full_ema())
         try:
             set_store(self.store)
             self.store.begin_phase()

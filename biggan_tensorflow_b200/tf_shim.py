@@ -110,14 +110,16 @@ class VariableStore:
         torch.cuda.synchronize()
         return {k: v.data.detach().float().cpu().numpy().copy() for k, v in self.vars.items()}
 
-    def pack(self, substr):
+    def pack(self, substr, multiple=1):
         """Move the trainable variables containing `substr` into one flat fp32 arena (params, grads)
-        so that Adam/EMA and the gradient all-reduce are single launches over contiguous memory."""
+        so that Adam/EMA and the gradient all-reduce are single launches over contiguous memory.
+        `multiple`: round the arena length up to a multiple of it (equal 16-byte aligned shards per rank)."""
         vs = self.trainable_variables(substr)
         offs, total = [], 0
         for v in vs:
             offs.append(total)
             total += (v.data.numel() + 3) // 4 * 4           # keep every slice 16-byte aligned
+        total = (total + multiple - 1) // multiple * multiple
         p = torch.zeros(total, dtype=torch.float32, device=device())
         g = torch.zeros(total, dtype=torch.float32, device=device())
         for v, o in zip(vs, offs):
