@@ -1130,19 +1130,19 @@ def condition_batch_renorm(x, z, opt={}, scope='batch_renorm', _act=_lib.ACT_NON
 def batch_norm(x, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
     """ops.py:580-585 (tf.layers.batch_normalization; moving_variance takes the unbiased variance)."""
     with variable_scope(scope):
-        c = x.shape[-1]
+        c, cx = c_real(x), x.shape[-1]               # cx > c: zero-padded image tensor of the bf16 tensor-core mode
         momentum = opt.get("bn", {}).get("momentum", 0.98)
         gamma = get_variable("gamma", [c], initializer=constant_initializer(1.0))
         beta = get_variable("beta", [c], initializer=constant_initializer(0.0))
         mm = get_variable("moving_mean", [c], initializer=constant_initializer(0.0), trainable=False)
         mv = get_variable("moving_variance", [c], initializer=constant_initializer(1.0), trainable=False)
         vec = 4 if x.dtype == F32 else 8              # the BN kernels move 16-byte channel vectors (norm.cu)
-        if c % vec == 0:
+        if cx == c and c % vec == 0:
             return _bn_core(x, gamma, beta, 0, mm, mv, momentum, lambda n: n / max(n - 1.0, 1.0), opt, _act)
         # narrow tensors (bn_in_d on the 3-channel image, ops.py:295): run on zero-padded channels.  A zero channel has
         # mean 0 / variance 0 and normalises to its beta (0); its parameters and statistics are dropped again.
-        cp = round_up(c, vec)
-        xp = pad_channels(x, cp)
+        cp = cx if cx != c else round_up(c, vec)
+        xp = x if cx != c else pad_channels(x, cp)
         gamma_p, beta_p = _padded_param(gamma, cp, 1.0), _padded_param(beta, cp, 0.0)
         mm_p = Tensor(torch.zeros(cp, dtype=F32, device=x.data.device))
         mv_p = Tensor(torch.ones(cp, dtype=F32, device=x.data.device))
@@ -1151,6 +1151,9 @@ def batch_norm(x, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
         y = _bn_core(xp, gamma_p, beta_p, 0, mm_p, mv_p, momentum, lambda n: n / max(n - 1.0, 1.0), opt, _act)
         mm.data.copy_(mm_p.data[:c])
         mv.data.copy_(mv_p.data[:c])
+        if cx != c:                                   # stays in the padded image layout (pad channels: beta = 0)
+            y.aux = {"c_real": c}
+            return y
         y = slice_channels(y, c)
         y.aux = None
         return y
