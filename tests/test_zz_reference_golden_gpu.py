@@ -15,7 +15,11 @@ GPU_TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}     # north_star
 # per-case widening factors, identical to the ones tests/test_ops_gpu.py uses against the oracle on the same shapes
 TOL_SCALE = {"cbn_relu_4x4x64": (2.0, 2.0), "cbn_relu_8x8x32": (2.0, 2.0), "bn_train": (2.0, 2.0),
              "sa2_8x8x32": (2.0, 4.0), "sa2_16x16x64": (2.0, 4.0), "resblock_up_condition": (4.0, 7.5),
-             "resblock_down_rgb": (3.0, 3.0), "resblock_down_32": (3.0, 3.0), "resblock": (3.0, 3.0)}
+             "resblock_down_rgb": (3.0, 3.0), "resblock_down_32": (3.0, 3.0), "resblock": (3.0, 3.0),
+             # SURVEY 8(f) cases: the same factors as their canonical counterparts
+             "resblock_down_resize_conv1": (3.0, 3.0), "resblock_down_bn_in_d": (3.0, 3.0), "resblock_bn_in_d_prelu": (3.0, 3.0),
+             "resblock_up_condition_prelu": (4.0, 7.5), "resblock_up_condition_lrelu_subpixel3_conv5": (4.0, 7.5),
+             "cbrn_fresh": (2.0, 2.0), "cbrn_warm": (2.0, 2.0), "cbrn_shared": (2.0, 2.0), "cbrn_inference": (2.0, 2.0)}
 FP32_ONLY = {"fc_sn", "fc_dense", "cbn_inference", "sa_full_4x4x32"}     # as in tests/test_ops_gpu.py
 
 
@@ -51,10 +55,11 @@ def test_cuda_op_matches_reference_source(case, dtype):
 
 @pytest.mark.gpu
 @UNVERIFIED
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("case", C.NEXT_OP_CASES, ids=[c["name"] for c in C.NEXT_OP_CASES])
-def test_cuda_next_row_op_matches_reference_source(case):
-    """prelu / lrelu, up- and down-sampling and g_conv variants, bn_in_d, conditional batch renorm (fp32 mode)."""
-    _cuda_op_case(case, torch.float32, "ref_ops_next.npz")
+def test_cuda_next_row_op_matches_reference_source(case, dtype):
+    """prelu / lrelu, up- and down-sampling and g_conv variants, bn_in_d, conditional batch renorm."""
+    _cuda_op_case(case, dtype, "ref_ops_next.npz")
 
 
 def _cuda_op_case(case, dtype, fname):
