@@ -7,22 +7,54 @@
 
 #include "../../biggan_tensorflow_b200/csrc/host_util.cu"      // bg_crc32c: host code as shipped
 
+// Storage wrappers of the loop stand-ins: every stand-in computes on float; a bf16 buffer (BG_BF16) is widened on the
+// way in and rounded (nearest even, like the kernels) on the way out.
+struct In {
+  std::vector<float> f; const float* p = nullptr;
+  In(const void* src, long n, int dtype) {
+    if (!src) return;
+    if (dtype == BG_F32) { p = (const float*)src; return; }
+    f.resize(n);
+    for (long i = 0; i < n; ++i) f[i] = bg_emul_bf16_to_float(((const bf16*)src)[i]);
+    p = f.data();
+  }
+  operator const float*() const { return p; }
+};
+struct Out {
+  std::vector<float> f; float* p = nullptr; void* dst; long n; int dtype;
+  Out(void* dst_, long n_, int dtype_, bool preload = false) : dst(dst_), n(n_), dtype(dtype_) {
+    if (!dst) return;
+    if (dtype == BG_F32) { p = (float*)dst; return; }
+    f.resize(n);
+    if (preload) for (long i = 0; i < n; ++i) f[i] = bg_emul_bf16_to_float(((const bf16*)dst)[i]);
+    p = f.data();
+  }
+  ~Out() { if (dst && dtype == BG_BF16) for (long i = 0; i < n; ++i) ((bf16*)dst)[i] = bg_emul_float_to_bf16(f[i]); }
+  operator float*() const { return p; }
+};
+#define DTYPE_OK(dtype) if ((dtype) != BG_F32 && (dtype) != BG_BF16) { bg_set_error("bad dtype %d", (int)(dtype)); return BG_ERR_UNSUPPORTED; }
+
 extern "C" const char* bg_last_error(void) { return bg_emul_error; }
 
 extern "C" int bg_add(const void* a, const void* b, void* out, long n, int dtype, void*) {
-  if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  DTYPE_OK(dtype); In ai(a, n, dtype), bi(b, n, dtype); Out oo(out, n, dtype); a = ai.p; b = bi.p; out = oo.p;
   for (long i = 0; i < n; ++i) ((float*)out)[i] = ((const float*)a)[i] + ((const float*)b)[i];
   return BG_OK;
 }
 extern "C" int bg_axpby(const void* x, const void* y, const float* alpha_dev, float alpha, float beta, void* out, long n, int dtype, void*) {
-  if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  DTYPE_OK(dtype); In xi(x, n, dtype), yi(y, n, dtype); Out oo(out, n, dtype); x = xi.p; y = yi.p; out = oo.p;
   const float a = alpha_dev ? *alpha_dev : alpha;
   for (long i = 0; i < n; ++i) ((float*)out)[i] = a * ((const float*)x)[i] + (y ? beta * ((const float*)y)[i] : 0.f);
   return BG_OK;
 }
 extern "C" int bg_bgemm(const void* A, const void* Bm, void* C, int batch, int M, int N, int K, long a_rs, long a_cs, long a_bs,
                         long b_rs, long b_cs, long b_bs, long c_rs, long c_bs, float alpha, int accumulate, int dtype, void*) {
-  if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  DTYPE_OK(dtype);
+  // extents of the strided operands (max index + 1)
+  const long na = (long)(batch - 1) * a_bs + (long)(M - 1) * a_rs + (long)(K - 1) * a_cs + 1;
+  const long nb = (long)(batch - 1) * b_bs + (long)(K - 1) * b_rs + (long)(N - 1) * b_cs + 1;
+  const long nc = (long)(batch - 1) * c_bs + (long)(M - 1) * c_rs + N;
+  In Ai(A, na, dtype), Bi(Bm, nb, dtype); Out Co(C, nc, dtype, true); A = Ai.p; Bm = Bi.p; C = Co.p;
   std::vector<double> row(N);
   for (int b = 0; b < batch; ++b)
     for (int m = 0; m < M; ++m) {
@@ -45,9 +77,9 @@ extern "C" int bg_bgemm(const void* A, const void* Bm, void* C, int batch, int M
 //      dgamma[b,c] = sum g xhat, dbeta[b,c] = sum g (g = dy masked by the ReLU); s = [sum_b gamma dbeta | sum_b gamma dgamma];
 //      dx = rstd (gamma g - s1/count - xhat s2/count).
 extern "C" size_t bg_bn_workspace_bytes(int, long, int) { return 256; }
-#define BN_VEC_OK(C) if ((C) % 4 != 0) { bg_set_error("bn: C=%d must be a multiple of 4", (C)); return BG_ERR_UNSUPPORTED; }   // as norm.cu
+#define BN_VEC_OK(C) if ((C) % (dtype == BG_F32 ? 4 : 8) != 0) { bg_set_error("bn: C=%d must be a multiple of %d", (C), dtype == BG_F32 ? 4 : 8); return BG_ERR_UNSUPPORTED; }   // as norm.cu
 extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, int dtype, void*, size_t, void*) {
-  if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  DTYPE_OK(dtype); In xi(x, (long)B * HW * C, dtype); x = xi.p;
   BN_VEC_OK(C);
   for (int c = 0; c < 2 * C; ++c) sums[c] = 0.0;
   const float* p = (const float*)x;
@@ -70,7 +102,7 @@ extern "C" int bg_bn_finalize(const double* sums, double count, float* mean, flo
 static inline float bn_act(float v, int act) { return act == BG_ACT_RELU ? (v > 0.f ? v : 0.f) : v; }
 extern "C" int bg_bn_apply(const void* x, const float* mean, const float* var, const float* gamma, const float* beta, int gb_bstride, void* y,
                            int act, float eps, int B, long HW, int C, int dtype, void*) {
-  if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  DTYPE_OK(dtype); In xi(x, (long)B * HW * C, dtype); Out yo(y, (long)B * HW * C, dtype); x = xi.p; y = yo.p;
   BN_VEC_OK(C);
   for (int b = 0; b < B; ++b)
     for (long r = 0; r < HW; ++r)
@@ -84,7 +116,7 @@ extern "C" int bg_bn_apply(const void* x, const float* mean, const float* var, c
 extern "C" int bg_bn_bwd_reduce(const void* dy, const void* x, const float* mean, const float* var, const float* gamma, const float* beta,
                                 int gb_bstride, float* dgamma, float* dbeta, int act, float eps, int B, long HW, int C, int dtype, void*,
                                 size_t, void*) {
-  if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  DTYPE_OK(dtype); In dyi(dy, (long)B * HW * C, dtype), xi(x, (long)B * HW * C, dtype); dy = dyi.p; x = xi.p;
   BN_VEC_OK(C);
   for (int b = 0; b < B; ++b)
     for (int c = 0; c < C; ++c) {
@@ -113,7 +145,7 @@ extern "C" int bg_bn_bwd_sums(const float* dgamma, const float* dbeta, const flo
 extern "C" int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* var, const float* gamma, const float* beta,
                                int gb_bstride, const double* s, double count, void* dx, int act, float eps, int B, long HW, int C, int dtype,
                                void*) {
-  if (dtype != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
+  DTYPE_OK(dtype); In dyi(dy, (long)B * HW * C, dtype), xi(x, (long)B * HW * C, dtype); Out dxo(dx, (long)B * HW * C, dtype); dy = dyi.p; x = xi.p; dx = dxo.p;
   BN_VEC_OK(C);
   for (int b = 0; b < B; ++b)
     for (long r = 0; r < HW; ++r)
@@ -160,7 +192,9 @@ extern "C" int bg_sn_power_iter(const float* W, const float* u, float* u_out, fl
 }
 extern "C" int bg_sn_scale(const float* W, const float* sigma, void* out, void* out_t, int dtype, int taps, int rows, int C, int r_pad, int c_pad,
                            void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype);
+  const long no = (long)taps * r_pad * c_pad;
+  Out oo(out, no, dtype, true), to(out_t, no, dtype, true); out = oo.p; out_t = to.p;
   for (int t = 0; t < taps; ++t)
     for (int r = 0; r < rows; ++r)
       for (int c = 0; c < C; ++c) {
@@ -213,7 +247,9 @@ extern "C" size_t bg_conv2d_wgrad_workspace_bytes(const bg_conv_desc*, int) { re
 #define CONV_DESC_OK(d) if ((d)->stride < 1 || (d)->stride > 2) { bg_set_error("conv desc: stride %d unsupported", (d)->stride); return BG_ERR_UNSUPPORTED; }
 extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x_, const void* w_, const void*, const float* bias, const void* res_, void* y_,
                              int act, int dtype, void*, size_t, int, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype);
+  const long nxe = (long)d->B * d->Hi * d->Wi * d->Ci, nye = (long)d->B * d->Ho * d->Wo * d->Co, nwe = (long)d->kh * d->kw * d->Ci * d->Co;
+  In xi(x_, nxe, dtype), wi(w_, nwe, dtype), ri(res_, nye, dtype); Out yo(y_, nye, dtype); x_ = xi.p; w_ = wi.p; res_ = ri.p; y_ = yo.p;
   CONV_DESC_OK(d);
   const float *x = (const float*)x_, *w = (const float*)w_, *res = (const float*)res_;
   float* y = (float*)y_;
@@ -236,7 +272,9 @@ extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x_, const void* 
 }
 extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy_, const void* w_, const void*, const void* res_, void* dx_, int dtype, void*,
                                size_t, int, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype);
+  const long nxe = (long)d->B * d->Hi * d->Wi * d->Ci, nye = (long)d->B * d->Ho * d->Wo * d->Co, nwe = (long)d->kh * d->kw * d->Ci * d->Co;
+  In gi(dy_, nye, dtype), wi(w_, nwe, dtype), ri(res_, nxe, dtype); Out xo(dx_, nxe, dtype); dy_ = gi.p; w_ = wi.p; res_ = ri.p; dx_ = xo.p;
   const float *dy = (const float*)dy_, *w = (const float*)w_, *res = (const float*)res_;
   float* dx = (float*)dx_;
   const long nx = (long)d->B * d->Hi * d->Wi * d->Ci;
@@ -254,7 +292,8 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy_, const voi
   return BG_OK;
 }
 extern "C" int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x_, const void* dy_, float* dw, int dtype, void*, size_t, int, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype);
+  In xi(x_, (long)d->B * d->Hi * d->Wi * d->Ci, dtype), gi(dy_, (long)d->B * d->Ho * d->Wo * d->Co, dtype); x_ = xi.p; dy_ = gi.p;
   const float *x = (const float*)x_, *dy = (const float*)dy_;
   const long nw = (long)d->kh * d->kw * d->Ci * d->Co;
   std::vector<double> acc(nw, 0.0);
@@ -272,52 +311,64 @@ extern "C" int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x_, const void
 }
 extern "C" size_t bg_colsum_workspace_bytes(long, int) { return 16; }
 extern "C" int bg_colsum(const void* dy, float* db, long rows, int C, int dtype, void*, size_t, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In gi(dy, rows * C, dtype); dy = gi.p;
   for (int c = 0; c < C; ++c) { double a = 0; for (long r = 0; r < rows; ++r) a += ((const float*)dy)[r * C + c]; db[c] = (float)a; }
   return BG_OK;
 }
 
 // ---- small elementwise / reductions ------------------------------------------------------------------------------------
 extern "C" int bg_relu_fwd(const void* x, void* y, long n, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x, n, dtype); Out yo(y, n, dtype); x = xi.p; y = yo.p;
   for (long i = 0; i < n; ++i) ((float*)y)[i] = std::max(((const float*)x)[i], 0.f);
   return BG_OK;
 }
 extern "C" int bg_relu_bwd(const void* x, const void* dy, void* dx, long n, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x, n, dtype), gi(dy, n, dtype); Out xo(dx, n, dtype); x = xi.p; dy = gi.p; dx = xo.p;
   for (long i = 0; i < n; ++i) ((float*)dx)[i] = ((const float*)x)[i] > 0.f ? ((const float*)dy)[i] : 0.f;
   return BG_OK;
 }
 extern "C" int bg_tanh_bwd(const void* y, const void* dy, void* dx, long n, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In yi(y, n, dtype), gi(dy, n, dtype); Out xo(dx, n, dtype); y = yi.p; dy = gi.p; dx = xo.p;
   for (long i = 0; i < n; ++i) { const float t = ((const float*)y)[i]; ((float*)dx)[i] = ((const float*)dy)[i] * (1.f - t * t); }
   return BG_OK;
 }
 extern "C" int bg_cast(const void* src, int sdt, void* dst, int ddt, long n, void*) {
-  if (sdt != BG_F32 || ddt != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
-  memcpy(dst, src, (size_t)n * sizeof(float));
+  DTYPE_OK(sdt); DTYPE_OK(ddt);
+  In si(src, n, sdt); Out dout(dst, n, ddt);
+  for (long i = 0; i < n; ++i) dout.p[i] = si.p[i];
   return BG_OK;
 }
 extern "C" int bg_fill(void* p, float value, long n, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); Out po(p, n, dtype); p = po.p;
   for (long i = 0; i < n; ++i) ((float*)p)[i] = value;
   return BG_OK;
 }
 extern "C" size_t bg_dot_workspace_bytes(long) { return 16; }
 extern "C" int bg_dot(const void* a, const void* b, float* out, long n, int dtype, void*, size_t, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In ai(a, n, dtype), bi(b, n, dtype); a = ai.p; b = bi.p;
   double s = 0;
   for (long i = 0; i < n; ++i) s += (double)((const float*)a)[i] * ((const float*)b)[i];
   out[0] = (float)s;
   return BG_OK;
 }
 extern "C" int bg_pad_channels(const void* src, int sdt, void* dst, int ddt, long npix, int Cs, int Cd, void*) {
-  if (sdt != BG_F32 || ddt != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
-  for (long p = 0; p < npix; ++p) for (int c = 0; c < Cd; ++c) ((float*)dst)[p * Cd + c] = c < Cs ? ((const float*)src)[p * Cs + c] : 0.f;
+  DTYPE_OK(sdt); DTYPE_OK(ddt);
+  In si(src, npix * Cs, sdt); Out dout(dst, npix * Cd, ddt);
+  for (long p = 0; p < npix; ++p) for (int c = 0; c < Cd; ++c) dout.p[p * Cd + c] = c < Cs ? si.p[p * Cs + c] : 0.f;
+  return BG_OK;
+}
+extern "C" int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr, int dtype, void*) {
+  DTYPE_OK(dtype);
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  In xi(x, (long)B * H * W * C, dtype); Out yo(y, (long)B * Hp * Wp * C, dtype);
+  for (int b = 0; b < B; ++b) for (int i = 0; i < Hp; ++i) for (int j = 0; j < Wp; ++j) {
+    const int si = reflect_idx(i - pt, H), sj = reflect_idx(j - pl, W);
+    for (int c = 0; c < C; ++c) yo.p[(((long)b * Hp + i) * Wp + j) * C + c] = xi.p[(((long)b * H + si) * W + sj) * C + c];
+  }
   return BG_OK;
 }
 extern "C" int bg_maxpool2_fwd(const void* x_, void* y_, int B, int H, int W, int C, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x_, (long)B * H * W * C, dtype); Out yo(y_, (long)B * (H / 2) * (W / 2) * C, dtype); x_ = xi.p; y_ = yo.p;
   if (H % 2 || W % 2) { bg_set_error("maxpool2: odd size"); return BG_ERR_UNSUPPORTED; }
   const float* x = (const float*)x_; float* y = (float*)y_;
   for (int b = 0; b < B; ++b) for (int oy = 0; oy < H / 2; ++oy) for (int ox = 0; ox < W / 2; ++ox) for (int c = 0; c < C; ++c) {
@@ -327,7 +378,7 @@ extern "C" int bg_maxpool2_fwd(const void* x_, void* y_, int B, int H, int W, in
   return BG_OK;
 }
 extern "C" int bg_maxpool2_bwd(const void* x_, const void* dy_, void* dx_, int B, int H, int W, int C, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x_, (long)B * H * W * C, dtype), gi(dy_, (long)B * (H / 2) * (W / 2) * C, dtype); Out xo(dx_, (long)B * H * W * C, dtype); x_ = xi.p; dy_ = gi.p; dx_ = xo.p;
   const float *x = (const float*)x_, *dy = (const float*)dy_; float* dx = (float*)dx_;
   for (int b = 0; b < B; ++b) for (int oy = 0; oy < H / 2; ++oy) for (int ox = 0; ox < W / 2; ++ox) for (int c = 0; c < C; ++c) {
     const long base = (((long)b * H + 2 * oy) * W + 2 * ox) * C + c;
@@ -339,7 +390,7 @@ extern "C" int bg_maxpool2_bwd(const void* x_, const void* dy_, void* dx_, int B
   return BG_OK;
 }
 extern "C" int bg_sumpool_fwd(const void* x, void* y, int B, long HW, int C, int relu_first, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x, (long)B * HW * C, dtype); Out yo(y, (long)B * C, dtype); x = xi.p; y = yo.p;
   for (int b = 0; b < B; ++b) for (int c = 0; c < C; ++c) {
     double s = 0;
     for (long r = 0; r < HW; ++r) { const float v = ((const float*)x)[((long)b * HW + r) * C + c]; s += relu_first ? std::max(v, 0.f) : v; }
@@ -348,7 +399,7 @@ extern "C" int bg_sumpool_fwd(const void* x, void* y, int B, long HW, int C, int
   return BG_OK;
 }
 extern "C" int bg_sumpool_bwd(const void* x, const void* dy, void* dx, int B, long HW, int C, int relu_first, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x, (long)B * HW * C, dtype), gi(dy, (long)B * C, dtype); Out xo(dx, (long)B * HW * C, dtype); x = xi.p; dy = gi.p; dx = xo.p;
   for (int b = 0; b < B; ++b) for (long r = 0; r < HW; ++r) for (int c = 0; c < C; ++c) {
     const long i = ((long)b * HW + r) * C + c;
     ((float*)dx)[i] = (!relu_first || ((const float*)x)[i] > 0.f) ? ((const float*)dy)[(long)b * C + c] : 0.f;
@@ -356,7 +407,7 @@ extern "C" int bg_sumpool_bwd(const void* x, const void* dy, void* dx, int B, lo
   return BG_OK;
 }
 extern "C" int bg_softmax_fwd(const void* x, void* y, long rows, int n, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x, rows * n, dtype); Out yo(y, rows * n, dtype); x = xi.p; y = yo.p;
   for (long r = 0; r < rows; ++r) {
     const float* xr = (const float*)x + r * n; float* yr = (float*)y + r * n;
     float m = xr[0];
@@ -368,7 +419,7 @@ extern "C" int bg_softmax_fwd(const void* x, void* y, long rows, int n, int dtyp
   return BG_OK;
 }
 extern "C" int bg_softmax_bwd(const void* y, const void* dy, void* dx, long rows, int n, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In yi(y, rows * n, dtype), gi(dy, rows * n, dtype); Out xo(dx, rows * n, dtype); y = yi.p; dy = gi.p; dx = xo.p;
   for (long r = 0; r < rows; ++r) {
     const float *yr = (const float*)y + r * n, *dr = (const float*)dy + r * n;
     double s = 0;
@@ -410,7 +461,7 @@ static inline float flood_of(float L, float flood, float* sgn) {
 }
 extern "C" int bg_hinge_d_fwd_bwd(const void* real_, const void* fake_, int n_real, int n_fake, float inv_count, float flood, float* loss,
                                   void* dreal, void* dfake, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In ri(real_, n_real, dtype), fi(fake_, n_fake, dtype); Out dro(dreal, n_real, dtype), dfo(dfake, n_fake, dtype); real_ = ri.p; fake_ = fi.p; dreal = dro.p; dfake = dfo.p;
   const float *real = (const float*)real_, *fake = (const float*)fake_;
   double s = 0;
   for (int i = 0; i < n_real; ++i) s += std::max(1.f - real[i], 0.f);
@@ -422,7 +473,7 @@ extern "C" int bg_hinge_d_fwd_bwd(const void* real_, const void* fake_, int n_re
   return BG_OK;
 }
 extern "C" int bg_hinge_g_fwd_bwd(const void* fake_, int n, float inv_count, float flood, float* loss, void* dfake, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In fi(fake_, n, dtype); Out dfo(dfake, n, dtype); fake_ = fi.p; dfake = dfo.p;
   double s = 0;
   for (int i = 0; i < n; ++i) s += ((const float*)fake_)[i];
   float sgn;
@@ -432,7 +483,7 @@ extern "C" int bg_hinge_g_fwd_bwd(const void* fake_, int n, float inv_count, flo
 }
 extern "C" int bg_logistic_cls_fwd_bwd(const void* logits_, const float* labels, const float* cls_w, int B, int n_labels, float weight,
                                        float inv_count, float* loss, void* dlogits, int accumulate_loss, int dtype, void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In li(logits_, (long)B * n_labels, dtype); Out dlo(dlogits, (long)B * n_labels, dtype); logits_ = li.p; dlogits = dlo.p;
   const float* logits = (const float*)logits_;
   double s = 0;
   for (long i = 0; i < (long)B * n_labels; ++i) {
@@ -470,7 +521,7 @@ static inline bool da_cut_host(int i, int j, int ox, int oy, int H, int W) {
 }
 extern "C" int bg_diffaug_fwd(const void* x_, void* y_, const float* rnd_f, const int* rnd_i, int flags, int B, int H, int W, int C, float*, int dtype,
                               void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In xi(x_, (long)B * H * W * C, dtype); Out yo(y_, (long)B * H * W * C, dtype); x_ = xi.p; y_ = yo.p;
   const float* x = (const float*)x_; float* y = (float*)y_;
   const long n = (long)H * W * C;
   for (int b = 0; b < B; ++b) {
@@ -497,7 +548,7 @@ extern "C" int bg_diffaug_fwd(const void* x_, void* y_, const float* rnd_f, cons
 }
 extern "C" int bg_diffaug_bwd(const void* dy_, void* dx_, const float* rnd_f, const int* rnd_i, int flags, int B, int H, int W, int C, float*, int dtype,
                               void*) {
-  STANDIN_F32(dtype);
+  DTYPE_OK(dtype); In gi(dy_, (long)B * H * W * C, dtype); Out xo(dx_, (long)B * H * W * C, dtype); dy_ = gi.p; dx_ = xo.p;
   const float* dy = (const float*)dy_; float* dx = (float*)dx_;
   const long n = (long)H * W * C;
   std::vector<float> g3(n);
