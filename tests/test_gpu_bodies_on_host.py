@@ -1,6 +1,6 @@
-"""The fp32 bodies of the GPU tests of the training step (tests/test_step_gpu.py, tests/test_golden.py: one full D + G
+"""The bodies of the GPU tests of the training step (tests/test_step_gpu.py, tests/test_golden.py: one full D + G
 iteration with Adam / EMA applied, with and without DiffAugment, against the oracle and against the oracle-generated
-golden step) executed on the test-only host implementation of the C ABI.  Purpose: a CPU-side regression guard for the
+golden step; fp32 and bf16 storage mode) executed on the test-only host implementation of the C ABI.  Purpose: a CPU-side regression guard for the
 Python layer of the canonical path, and a cross-check of the host library itself against tests that are known to pass
 on hardware."""
 import pytest
@@ -21,9 +21,10 @@ def host_all(host_so, monkeypatch):
     tensor.clear_tape()
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("da_policy", ["", "color,translation,cutout"])
-def test_train_step_matches_oracle_on_the_host(host_all, da_policy):
-    S.test_train_step_matches_oracle(torch.float32, da_policy)
+def test_train_step_matches_oracle_on_the_host(host_all, da_policy, dtype):
+    S.test_train_step_matches_oracle(dtype, da_policy)
 
 
 def test_parameters_after_update_on_the_host(host_all):
