@@ -169,7 +169,9 @@ extern "C" int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean,
 // =====================================================================================================================
 #define STANDIN_F32(dtype) if ((dtype) != BG_F32) { bg_set_error("host stand-in: fp32 only"); return BG_ERR_UNSUPPORTED; }
 extern "C" int bg_abi_version(void) { return 1; }
-extern "C" int bg_has_tensor_core_path(void) { return 0; }
+// BG_HOST_TC=1 makes the Python layer take its tensor-core-mode glue (16-channel image layout, per-tap transposed weight
+// copies, padded narrow projections, im2col of the RGB convs, fused attention entry points) on top of the same loops.
+extern "C" int bg_has_tensor_core_path(void) { const char* e = getenv("BG_HOST_TC"); return e && e[0] == '1'; }
 extern "C" int bg_debug_counters(int* a, int* b) { *a = 0; *b = 0; return BG_OK; }
 
 // ---- spectral norm ---------------------------------------------------------------------------------------------------
@@ -572,5 +574,73 @@ extern "C" int bg_diffaug_bwd(const void* dy_, void* dx_, const float* rnd_f, co
       for (int c = 0; c < C; ++c) dst[c] = sat * (con * g3[p * C + c] + (1.f - con) * (float)gm) + (1.f - sat) * mc;
     }
   }
+  return BG_OK;
+}
+
+// ---- tensor-core-mode entry points (bf16): im2col of the 3 real image channels, fused attention core ----------------------
+extern "C" int bg_im2col_rgb(const void* x, void* z, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int stride, int pad_t, int pad_l,
+                             int pad_mode, int Cz, void*) {
+  if (Cx < 3 || Cz < kh * kw * 3) { bg_set_error("im2col_rgb: bad shape"); return BG_ERR_SHAPE; }
+  In xi(x, (long)B * H * W * Cx, BG_BF16); Out zo(z, (long)B * Ho * Wo * Cz, BG_BF16);
+  for (long i = 0; i < (long)B * Ho * Wo * Cz; ++i) zo.p[i] = 0.f;
+  for (int b = 0; b < B; ++b) for (int oy = 0; oy < Ho; ++oy) for (int ox = 0; ox < Wo; ++ox) for (int ky = 0; ky < kh; ++ky) for (int kx = 0; kx < kw; ++kx) {
+    int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
+    if (pad_mode == BG_PAD_REFLECT) { iy = reflect_idx(iy, H); ix = reflect_idx(ix, W); }
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    for (int c = 0; c < 3; ++c) zo.p[(((long)b * Ho + oy) * Wo + ox) * Cz + (ky * kw + kx) * 3 + c] = xi.p[(((long)b * H + iy) * W + ix) * Cx + c];
+  }
+  return BG_OK;
+}
+extern "C" int bg_col2im_rgb(const void* dz, void* dx, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int stride, int pad_t, int pad_l,
+                             int, int, int pad_mode, int Cz, void*) {
+  In zi(dz, (long)B * Ho * Wo * Cz, BG_BF16); Out xo(dx, (long)B * H * W * Cx, BG_BF16);
+  std::vector<double> acc((size_t)B * H * W * 3, 0.0);
+  for (int b = 0; b < B; ++b) for (int oy = 0; oy < Ho; ++oy) for (int ox = 0; ox < Wo; ++ox) for (int ky = 0; ky < kh; ++ky) for (int kx = 0; kx < kw; ++kx) {
+    int iy = oy * stride + ky - pad_t, ix = ox * stride + kx - pad_l;
+    if (pad_mode == BG_PAD_REFLECT) { iy = reflect_idx(iy, H); ix = reflect_idx(ix, W); }
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    for (int c = 0; c < 3; ++c) acc[(((size_t)b * H + iy) * W + ix) * 3 + c] += zi.p[(((long)b * Ho + oy) * Wo + ox) * Cz + (ky * kw + kx) * 3 + c];
+  }
+  for (long p = 0; p < (long)B * H * W; ++p) for (int c = 0; c < Cx; ++c) xo.p[p * Cx + c] = c < 3 ? (float)acc[p * 3 + c] : 0.f;
+  return BG_OK;
+}
+// o = softmax(q k^T) v, lse = log sum exp of the scores; backward recomputes the probabilities from lse
+extern "C" int bg_attn2_fwd(const void* q_, const void* k_, const void* v_, void* o_, float* lse, int B, int Nq, int Nk, int dq, int dv, void*) {
+  In q(q_, (long)B * Nq * dq, BG_BF16), k(k_, (long)B * Nk * dq, BG_BF16), v(v_, (long)B * Nk * dv, BG_BF16); Out o(o_, (long)B * Nq * dv, BG_BF16);
+  std::vector<double> s(Nk);
+  for (int b = 0; b < B; ++b) for (int i = 0; i < Nq; ++i) {
+    double m = -1e300;
+    for (int j = 0; j < Nk; ++j) { double a = 0; for (int c = 0; c < dq; ++c) a += (double)q.p[((long)b * Nq + i) * dq + c] * k.p[((long)b * Nk + j) * dq + c]; s[j] = a; m = std::max(m, a); }
+    double z = 0;
+    for (int j = 0; j < Nk; ++j) { s[j] = std::exp(s[j] - m); z += s[j]; }
+    lse[(long)b * Nq + i] = (float)(m + std::log(z));
+    for (int c = 0; c < dv; ++c) { double a = 0; for (int j = 0; j < Nk; ++j) a += s[j] * v.p[((long)b * Nk + j) * dv + c]; o.p[((long)b * Nq + i) * dv + c] = (float)(a / z); }
+  }
+  return BG_OK;
+}
+extern "C" int bg_attn2_bwd(const void* q_, const void* k_, const void* v_, const void* o_, const void* do_, const float* lse, float* delta, void* dq_,
+                            void* dk_, void* dv_, int B, int Nq, int Nk, int dq, int dv, void*) {
+  In q(q_, (long)B * Nq * dq, BG_BF16), k(k_, (long)B * Nk * dq, BG_BF16), v(v_, (long)B * Nk * dv, BG_BF16), o(o_, (long)B * Nq * dv, BG_BF16),
+     go(do_, (long)B * Nq * dv, BG_BF16);
+  Out gq(dq_, (long)B * Nq * dq, BG_BF16), gk(dk_, (long)B * Nk * dq, BG_BF16), gv(dv_, (long)B * Nk * dv, BG_BF16);
+  std::vector<double> aq((size_t)B * Nq * dq, 0.0), ak((size_t)B * Nk * dq, 0.0), av((size_t)B * Nk * dv, 0.0);
+  for (int b = 0; b < B; ++b) for (int i = 0; i < Nq; ++i) {
+    const long qi = (long)b * Nq + i;
+    double dl = 0;
+    for (int c = 0; c < dv; ++c) dl += (double)go.p[qi * dv + c] * o.p[qi * dv + c];
+    delta[qi] = (float)dl;
+    for (int j = 0; j < Nk; ++j) {
+      const long kj = (long)b * Nk + j;
+      double sc = 0, dp = 0;
+      for (int c = 0; c < dq; ++c) sc += (double)q.p[qi * dq + c] * k.p[kj * dq + c];
+      const double pr = std::exp(sc - lse[qi]);
+      for (int c = 0; c < dv; ++c) { dp += (double)go.p[qi * dv + c] * v.p[kj * dv + c]; av[kj * dv + c] += pr * go.p[qi * dv + c]; }
+      const double ds = pr * (dp - dl);
+      for (int c = 0; c < dq; ++c) { aq[qi * dq + c] += ds * k.p[kj * dq + c]; ak[kj * dq + c] += ds * q.p[qi * dq + c]; }
+    }
+  }
+  for (size_t i = 0; i < aq.size(); ++i) gq.p[i] = (float)aq[i];
+  for (size_t i = 0; i < ak.size(); ++i) gk.p[i] = (float)ak[i];
+  for (size_t i = 0; i < av.size(); ++i) gv.p[i] = (float)av[i];
   return BG_OK;
 }

@@ -21,10 +21,18 @@ def host_all(host_so, monkeypatch):
     tensor.clear_tape()
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16-tcglue"])
 @pytest.mark.parametrize("da_policy", ["", "color,translation,cutout"])
-def test_train_step_matches_oracle_on_the_host(host_all, da_policy, dtype):
-    S.test_train_step_matches_oracle(dtype, da_policy)
+def test_train_step_matches_oracle_on_the_host(host_all, monkeypatch, da_policy, mode):
+    """bf16-tcglue: the host library reports a tensor-core path (BG_HOST_TC=1), so the Python layer takes its tensor-core-mode
+    glue -- 16-channel image layout, im2col of the RGB convs, per-tap transposed weight copies, zero-padded narrow
+    projections, the fused attention entry points -- over the same loop stand-ins."""
+    if mode == "bf16-tcglue":
+        from biggan_tensorflow_b200 import ops
+        monkeypatch.setenv("BG_HOST_TC", "1")
+        ops.set_compute_dtype(torch.bfloat16)
+        assert ops.rgb_pad() == 16
+    S.test_train_step_matches_oracle(torch.float32 if mode == "fp32" else torch.bfloat16, da_policy)
 
 
 def test_parameters_after_update_on_the_host(host_all):

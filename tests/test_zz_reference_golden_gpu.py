@@ -147,7 +147,7 @@ def _to_cuda(a):
     return torch.from_numpy(a).cuda()
 
 
-def _cuda_net(name, dtype=torch.float32, stol=2e-4, dev=_to_cuda):
+def _cuda_net(name, dtype=torch.float32, stol=2e-4, dev=_to_cuda, tol=1e-4, gtol=3e-4, l2=False, skip=()):
     from biggan_tensorflow_b200 import DiffAugment_tf as D
     from biggan_tensorflow_b200.model import Config
     from biggan_tensorflow_b200.step import Trainer
@@ -167,7 +167,7 @@ def _cuda_net(name, dtype=torch.float32, stol=2e-4, dev=_to_cuda):
     state_g = tr.store.export()
     ref_shapes = {str(n): tuple(int(s) for s in str(sh).split(",") if s) for n, sh in zip(g["all_names"], g["all_shapes"])}
     assert {k: tuple(v.shape) for k, v in state_g.items()} == ref_shapes
-    check_net64(g, float(d_loss.cpu()), gd, None, state_d, float(g_loss.cpu()), gg, None, state_g, tol=1e-4, gtol=3e-4, stol=stol)
+    check_net64(g, float(d_loss.cpu()), gd, None, state_d, float(g_loss.cpu()), gg, None, state_g, tol=tol, gtol=gtol, stol=stol, l2=l2, skip=skip)
 
 
 @pytest.mark.gpu
