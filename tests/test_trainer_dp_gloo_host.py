@@ -47,7 +47,7 @@ def _run(kw, rank, world, pg):
     return dict(dl=float(dl), gl=float(gl), gd=gd, gg=gg, state_d=state_d, state_g=tr.store.export())
 
 
-def _train(kw, rank, world, pg, shard, steps=2):
+def _train(kw, rank, world, pg, shard, steps=2, ckpt_dir=None):
     """`steps` full iterations (D update + G update with Adam / EMA applied) -> parameters and optimizer state."""
     from biggan_tensorflow_b200.model import Config
     from biggan_tensorflow_b200.step import Trainer
@@ -64,6 +64,9 @@ def _train(kw, rank, world, pg, shard, steps=2):
         for key in ("m", "v") + (("ema",) if net == "generator" else ()):
             out[net + "/" + key] = tr.full_opt(net, key).clone().numpy()
         out[net + "/numel"] = n
+    if ckpt_dir:                                       # collective with a sharded optimizer: every rank gathers the slots
+        from biggan_tensorflow_b200 import checkpoint as ck
+        out["ckpt"] = ck.read_bundle(ck.save(tr, os.path.join(ckpt_dir, "rank%d" % rank), step=steps))
     return out
 
 
@@ -72,7 +75,7 @@ def _worker_train(rank, world, port, so, kw, shard, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     host_env.activate(so)
-    torch.save(_train(kw, rank, world, dist.group.WORLD, shard), out % rank)
+    torch.save(_train(kw, rank, world, dist.group.WORLD, shard, ckpt_dir=os.path.dirname(out)), out % rank)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -96,6 +99,9 @@ def test_sharded_optimizer_equals_replicated_optimizer(tmp_path, so):
             n = a[net + "/numel"]
             for key in ("m", "v") + (("ema",) if net == "generator" else ()):
                 assert np.array_equal(a[net + "/" + key][:n], b[net + "/" + key][:n]), (net, key)
+        assert sorted(a["ckpt"]) == sorted(b["ckpt"])                           # the checkpoint a sharded run writes is the same file content
+        for k in a["ckpt"]:
+            assert np.array_equal(a["ckpt"][k], b["ckpt"][k]), k
     for k in res[True][0]["vars"]:                                              # replicas agree
         assert np.array_equal(res[True][0]["vars"][k], res[True][1]["vars"][k]), k
 
