@@ -20,3 +20,11 @@ def _built_library():
         import __graft_entry__
         __graft_entry__.build()
     yield
+
+
+@pytest.fixture(scope="session")
+def host_so(tmp_path_factory):
+    """The test-only host implementation of the C ABI (tests/host_emul/host_lib.cpp), compiled once per session."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host_emul"))
+    import host_env
+    return host_env.build(str(tmp_path_factory.mktemp("host_lib") / "host_lib.so"))

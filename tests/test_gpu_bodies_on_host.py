@@ -6,7 +6,7 @@ on hardware."""
 import pytest
 import torch
 
-from test_next_ops_glue_host import host_env, host_so           # noqa: F401  (fixture)
+from test_next_ops_glue_host import host_env                    # noqa: F401
 import test_golden as TG
 import test_step_gpu as S
 
@@ -21,8 +21,8 @@ def host_all(host_so, monkeypatch):
     tensor.clear_tape()
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16-tcglue"])
-@pytest.mark.parametrize("da_policy", ["", "color,translation,cutout"])
+@pytest.mark.parametrize("mode,da_policy", [("fp32", ""), ("bf16", "color,translation,cutout"), ("bf16-tcglue", ""),
+                                            ("bf16-tcglue", "color,translation,cutout")])
 def test_train_step_matches_oracle_on_the_host(host_all, monkeypatch, da_policy, mode):
     """bf16-tcglue: the host library reports a tensor-core path (BG_HOST_TC=1), so the Python layer takes its tensor-core-mode
     glue -- 16-channel image layout, im2col of the RGB convs, per-tap transposed weight copies, zero-padded narrow

@@ -22,11 +22,6 @@ ROOT = os.path.dirname(HERE)
 STANDALONE = {"prelu", "lrelu", "upconv_nn", "downconv_pool_only"}           # cases that need no conv kernel
 
 
-@pytest.fixture(scope="module")
-def host_so(tmp_path_factory):
-    return host_env.build(str(tmp_path_factory.mktemp("host_lib") / "host_lib.so"))
-
-
 @pytest.fixture()
 def host_product(host_so, monkeypatch):
     from biggan_tensorflow_b200 import ops, tensor, tf_shim
