@@ -11,7 +11,12 @@ import zlib
 import numpy as np
 import pytest
 
-from biggan_tensorflow_b200 import data as D
+try:
+    from biggan_tensorflow_b200 import data as D
+except RuntimeError:                       # libbiggan_io.so not built yet (fresh checkout): build, then import
+    import __graft_entry__
+    __graft_entry__.build()
+    from biggan_tensorflow_b200 import data as D
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
