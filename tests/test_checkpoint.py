@@ -8,7 +8,12 @@ import struct
 import numpy as np
 import pytest
 
-from biggan_tensorflow_b200 import checkpoint as ck
+try:
+    from biggan_tensorflow_b200 import checkpoint as ck
+except RuntimeError:                       # libbiggan_b200.so not built yet (fresh checkout): build, then import
+    import __graft_entry__
+    __graft_entry__.build()
+    from biggan_tensorflow_b200 import checkpoint as ck
 
 
 def test_crc32c_known_answers_and_mask():
