@@ -309,10 +309,45 @@ def read_bundle(prefix, verify=True, names=None):
     return out
 
 
-def write_checkpoint_state(directory, prefix_basename):
-    """The text `checkpoint` file tf.train.get_checkpoint_state reads (BigGAN.py:1279)."""
-    with open(os.path.join(directory, "checkpoint"), "w") as f:
-        f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (prefix_basename, prefix_basename))
+def read_checkpoint_state(directory):
+    """-> (model_checkpoint_path, [all_model_checkpoint_paths]) of the text `checkpoint` file, or (None, [])."""
+    path = os.path.join(directory, "checkpoint")
+    latest, history = None, []
+    if os.path.exists(path):
+        for line in open(path):
+            key, _, val = line.partition(":")
+            val = val.strip().strip('"')
+            if key.strip() == "model_checkpoint_path":
+                latest = val
+            elif key.strip() == "all_model_checkpoint_paths":
+                history.append(val)
+    return latest, history
+
+
+def write_checkpoint_state(directory, prefix_basename, max_to_keep=0):
+    """The text `checkpoint` file tf.train.get_checkpoint_state reads (BigGAN.py:1279).  Like tf.train.Saver it keeps the
+    history of saved prefixes in `all_model_checkpoint_paths`; with max_to_keep > 0 (the reference passes
+    --keep_checkpoints, BigGAN.py:1018) the oldest prefixes beyond that count are dropped from the list and their files
+    deleted.  The state file is replaced atomically."""
+    _, history = read_checkpoint_state(directory)
+    history = [h for h in history if h != prefix_basename] + [prefix_basename]
+    if max_to_keep and max_to_keep > 0:
+        for old in history[:-max_to_keep]:
+            base = old if os.path.isabs(old) else os.path.join(directory, old)
+            for fn in _bundle_files(base):
+                if os.path.exists(fn):
+                    os.remove(fn)
+        history = history[-max_to_keep:]
+    tmp = os.path.join(directory, "checkpoint.tmp.%d" % os.getpid())
+    with open(tmp, "w") as f:
+        f.write('model_checkpoint_path: "%s"\n' % prefix_basename)
+        for h in history:
+            f.write('all_model_checkpoint_paths: "%s"\n' % h)
+    os.replace(tmp, os.path.join(directory, "checkpoint"))
+
+
+def _bundle_files(prefix):
+    return [prefix + ".index", prefix + ".data-00000-of-00001"]
 
 
 def latest_checkpoint(directory):
@@ -347,14 +382,41 @@ def to_tf_tensors(variables, g_trainable, d_trainable, g_adam, d_adam, ema, t_g,
     out["beta2_power"] = np.array(beta2 ** (t_g + 1), dtype=np.float32)
     out["beta1_power_1"] = np.array(beta1 ** (t_d + 1), dtype=np.float32)
     out["beta2_power_1"] = np.array(beta2 ** (t_d + 1), dtype=np.float32)
+    # the float32 beta2_power underflows (denormal near t = 830, exactly 0 from t = 1000 at beta2 = 0.9), so the exact
+    # optimizer step counts travel as two extra tensors; TF's restore only reads the names its graph asks for.
+    out[STEP_G] = np.array(t_g, dtype=np.int64)
+    out[STEP_D] = np.array(t_d, dtype=np.int64)
     return out
 
 
-def from_tf_tensors(tensors, beta2):
-    """Inverse of to_tf_tensors -> dict(variables, g_adam, d_adam, ema, t_g, t_d).  The step counts are recovered from
-    beta2_power (beta1 may be 0)."""
+STEP_G = "biggan_b200/adam_step_generator"
+STEP_D = "biggan_b200/adam_step_discriminator"
+
+
+def counter_from_prefix(prefix):
+    """BigGAN.load_checkpoint (BigGAN.py:1267): the iteration counter is the '-<step>' suffix of the checkpoint name."""
+    try:
+        return int(os.path.basename(prefix).split('-')[-1])
+    except ValueError:
+        return None
+
+
+def steps_from_beta_power(p, beta2):
+    """t from beta2_power = beta2^(t+1), or None where the float32 value no longer determines t (outside (0, 1),
+    or denormal / close to it: below 1e-30 one ulp spans several steps)."""
+    p = float(p)
+    if not (1e-30 < p < 1.0) or not (0.0 < beta2 < 1.0):
+        return None
+    return max(int(round(np.log(p) / np.log(beta2))) - 1, 0)
+
+
+def from_tf_tensors(tensors, beta2, counter=None):
+    """Inverse of to_tf_tensors -> dict(variables, g_adam, d_adam, ema, t_g, t_d).  Optimizer step counts, in order of
+    preference: the exact counters this package writes; beta2_power while it still determines t (cross-checked against
+    nothing else -- a checkpoint written by TensorFlow has only this); the iteration counter of the file name
+    (BigGAN.py:1267; one D and one G step per iteration at n_critic = 1), which is what the reference resumes from."""
     skip_suffix = ("/Adam", "/Adam_1", "/ExponentialMovingAverage")
-    special = {"beta1_power", "beta2_power", "beta1_power_1", "beta2_power_1"}
+    special = {"beta1_power", "beta2_power", "beta1_power_1", "beta2_power_1", STEP_G, STEP_D}
     variables = {n: a for n, a in tensors.items() if not n.endswith(skip_suffix) and n not in special}
     ema, g_adam, d_adam = {}, {}, {}
     for n in list(variables):
@@ -364,14 +426,16 @@ def from_tf_tensors(tensors, beta2):
         if n + "/Adam" in tensors:
             (g_adam if "generator" in n else d_adam)[n] = (tensors[n + "/Adam"], tensors[n + "/Adam_1"])
 
-    def steps(key):
-        if key not in tensors:
-            return 0
-        p = float(tensors[key])
-        return max(int(round(np.log(p) / np.log(beta2))) - 1, 0) if 0 < p < 1 else 0
+    def steps(own, key):
+        if own in tensors:
+            return int(tensors[own])
+        t = steps_from_beta_power(tensors[key], beta2) if key in tensors else None
+        if t is not None:
+            return t
+        return int(counter) if counter is not None else 0
 
     return {"variables": variables, "g_adam": g_adam, "d_adam": d_adam, "ema": ema,
-            "t_g": steps("beta2_power"), "t_d": steps("beta2_power_1")}
+            "t_g": steps(STEP_G, "beta2_power"), "t_d": steps(STEP_D, "beta2_power_1")}
 
 
 def _arena_slices(trainer, net, flat):
@@ -380,36 +444,53 @@ def _arena_slices(trainer, net, flat):
     return {v.name: host[o:o + v.data.numel()].reshape(tuple(v.data.shape)).copy() for v, o in zip(ar["vars"], ar["offsets"])}
 
 
-def save(trainer, directory, step, model_name="BigGAN"):
-    """BigGAN.save (BigGAN.py:1255-1261): <directory>/<model_name>.model-<step>.{index,data-00000-of-00001} + `checkpoint`."""
+def save(trainer, directory, step, model_name="BigGAN", max_to_keep=0):
+    """BigGAN.save (BigGAN.py:1255-1261): <directory>/<model_name>.model-<step>.{index,data-00000-of-00001} + `checkpoint`
+    (history pruned to max_to_keep prefixes when > 0, the reference's --keep_checkpoints).
+
+    Data parallel: COLLECTIVE -- every rank must call it (with a sharded optimizer the Adam / EMA slices are all-gathered).
+    Replicas are identical, so rank 0 alone writes; files are written under a temporary name and renamed into place, and
+    all ranks leave through a barrier so that no rank reads a half-written checkpoint."""
     import torch
     if not trainer._built:
         trainer.build()
     torch.cuda.synchronize()
     cfg = trainer.cfg
-    variables = trainer.store.export()
-    adam = {}
-    for net in ("generator", "discriminator"):
-        m, v = _arena_slices(trainer, net, trainer.full_opt(net, "m")), _arena_slices(trainer, net, trainer.full_opt(net, "v"))
-        adam[net] = {n: (m[n], v[n]) for n in m}
-    ema = _arena_slices(trainer, "generator", trainer.full_ema())
-    t_g = int(round(float(trainer.opt["generator"]["state"][0].cpu())))
-    t_d = int(round(float(trainer.opt["discriminator"]["state"][0].cpu())))
-    tensors = to_tf_tensors(variables, list(adam["generator"]), list(adam["discriminator"]), adam["generator"], adam["discriminator"],
-                            ema, t_g, t_d, cfg.beta1, cfg.beta2)
+    full = {(net, key): trainer.full_opt(net, key) for net in ("generator", "discriminator") for key in ("m", "v")}   # collective
+    full_ema = trainer.full_ema()                                                                                       # collective
     base = "%s.model-%d" % (model_name, step)
-    write_bundle(os.path.join(directory, base), tensors)
-    write_checkpoint_state(directory, base)
+    if trainer.rank == 0:
+        variables = trainer.store.export()
+        adam = {}
+        for net in ("generator", "discriminator"):
+            m, v = _arena_slices(trainer, net, full[(net, "m")]), _arena_slices(trainer, net, full[(net, "v")])
+            adam[net] = {n: (m[n], v[n]) for n in m}
+        ema = _arena_slices(trainer, "generator", full_ema)
+        t_g = int(round(float(trainer.opt["generator"]["state"][0].cpu())))
+        t_d = int(round(float(trainer.opt["discriminator"]["state"][0].cpu())))
+        tensors = to_tf_tensors(variables, list(adam["generator"]), list(adam["discriminator"]), adam["generator"],
+                                adam["discriminator"], ema, t_g, t_d, cfg.beta1, cfg.beta2)
+        os.makedirs(directory, exist_ok=True)
+        tmp = os.path.join(directory, ".tmp-%d-%s" % (os.getpid(), base))
+        write_bundle(tmp, tensors)
+        for src, dst in zip(_bundle_files(tmp), _bundle_files(os.path.join(directory, base))):
+            os.replace(src, dst)
+        write_checkpoint_state(directory, base, max_to_keep=max_to_keep)
+    if trainer.world > 1:
+        import torch.distributed as dist
+        dist.barrier(group=trainer.pg)
     return os.path.join(directory, base)
 
 
 def load(trainer, prefix):
-    """BigGAN.load_checkpoint (BigGAN.py:1264-1270): restore weights, state, Adam slots, EMA shadows and step counts."""
+    """BigGAN.load_checkpoint (BigGAN.py:1264-1270): restore weights, state, Adam slots, EMA shadows and step counts.
+    Returns the iteration counter to resume from: the '-<step>' suffix of the checkpoint name, as the reference does."""
     import torch
     if not trainer._built:
         trainer.build()
     cfg = trainer.cfg
-    st = from_tf_tensors(read_bundle(prefix), cfg.beta2)
+    counter = counter_from_prefix(prefix)
+    st = from_tf_tensors(read_bundle(prefix), cfg.beta2, counter=counter)
     missing = sorted(set(trainer.store.vars) - set(st["variables"]))
     if missing:
         raise KeyError("checkpoint %s lacks %d variables, e.g. %s" % (prefix, len(missing), missing[:3]))
@@ -426,4 +507,5 @@ def load(trainer, prefix):
         lr = cfg.g_lr if net == "generator" else cfg.d_lr
         lr_t = lr * np.sqrt(1 - cfg.beta2 ** t) / (1 - cfg.beta1 ** t) if t > 0 else 0.0
         o["state"].copy_(torch.tensor([float(t), float(lr_t)]))
-    return st["t_g"]
+    trainer.t_g, trainer.t_d = st["t_g"], st["t_d"]
+    return counter if counter is not None else st["t_g"]

@@ -83,6 +83,10 @@ extern "C" int bgio_png_decode(const void* data, size_t n, void* out_v, size_t o
   PngParts p;
   if (walk((const uint8_t*)data, n, &p, false)) return -1;
   const PngHeader& h = p.hdr;
+  // header dimensions come from the file: bound them before any size arithmetic (a crafted IHDR near 2^31 would wrap the
+  // products below, and zlib's 32-bit avail_in / avail_out would truncate a > 4 GiB scanline buffer)
+  const int kMaxSide = 1 << 16;
+  if (h.w <= 0 || h.h <= 0 || h.w > kMaxSide || h.h > kMaxSide) return fail("PNG dimensions %d x %d are out of range (1..%d)", h.w, h.h, kMaxSide);
   if (h.interlace) return fail("interlaced PNG is not supported");
   const bool pal = h.color == 3;
   if (pal ? (h.depth != 1 && h.depth != 2 && h.depth != 4 && h.depth != 8) : h.depth != 8)
@@ -95,7 +99,10 @@ extern "C" int bgio_png_decode(const void* data, size_t n, void* out_v, size_t o
   if (out_bytes < (size_t)h.w * h.h * oc) return fail("output buffer too small");
   const size_t row_bytes = pal ? ((size_t)h.w * h.depth + 7) / 8 : (size_t)h.w * stored;
   const int bpp = pal ? 1 : stored;                              // filter distance in bytes (>= 1)
-  std::vector<uint8_t> raw((row_bytes + 1) * h.h);
+  // (row_bytes + 1) <= 4 * 65536 + 1 and h <= 65536: the product fits size_t; it must also fit zlib's 32-bit counters
+  const size_t raw_bytes = (row_bytes + 1) * (size_t)h.h;
+  if (raw_bytes > 0xFFFFFFFFull || p.idat.size() > 0xFFFFFFFFull) return fail("PNG image data exceeds 4 GiB");
+  std::vector<uint8_t> raw(raw_bytes);
   z_stream zs;
   memset(&zs, 0, sizeof(zs));
   if (inflateInit(&zs) != Z_OK) return fail("zlib init failed");
@@ -104,7 +111,7 @@ extern "C" int bgio_png_decode(const void* data, size_t n, void* out_v, size_t o
   const int zr = inflate(&zs, Z_FINISH);
   const size_t got = raw.size() - zs.avail_out;
   inflateEnd(&zs);
-  if ((zr != Z_STREAM_END && zr != Z_OK && zr != Z_BUF_ERROR) || got != raw.size()) return fail("PNG image data: inflate failed or short (%zu of %zu bytes)", got, raw.size());
+  if (zr != Z_STREAM_END || got != raw.size()) return fail("PNG image data: inflate failed, short or overlong (%zu of %zu bytes, zlib %d)", got, raw.size(), zr);
   // unfilter in place
   std::vector<uint8_t> zero(row_bytes, 0);
   for (int y = 0; y < h.h; ++y) {

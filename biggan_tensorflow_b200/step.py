@@ -312,7 +312,9 @@ class Trainer:
     def sample(self, z, cls_z, ema=True):
         """Generator in inference mode (is_training=False: population BN statistics, BigGAN.py:771-787) with the EMA
         shadow weights swapped in (MovingAverageOptimizer.swapping_saver semantics) when ema=True.  Returns the image
-        tensor [B, S, S, 3(+pad)].  Spectral norm still advances `u` (ops.py:743 has no training switch)."""
+        tensor [B, S, S, 3(+pad)].  Spectral norm still advances `u` (ops.py:743 has no training switch).
+        With a sharded optimizer and ema=True this is a COLLECTIVE call (the EMA shadow slices are all-gathered):
+        every rank must make it."""
         if not self._built:
             self.build()
         ar, o = self.store.arenas["generator"], self.opt["generator"]

@@ -133,3 +133,41 @@ def test_swapping_saver_naming_round_trip():
     assert s["t_g"] == 5 and s["t_d"] == 6
     assert sorted(s["variables"]) == sorted(variables) and all(np.array_equal(s["variables"][n], variables[n]) for n in variables)
     assert all(np.array_equal(s["ema"][n], ema[n]) for n in g_names) and sorted(s["g_adam"]) == sorted(g_names) and sorted(s["d_adam"]) == d_names
+
+
+def test_step_counts_survive_beta2_power_underflow():
+    """beta2_power = 0.9^(t+1) is denormal near t = 830 and exactly 0.0 from t = 1000 in float32: the step counts must not
+    come from it there.  Order of preference: the exact counters this package writes, beta2_power while it determines t,
+    the '-<step>' suffix of the checkpoint name (BigGAN.py:1267)."""
+    v = {"generator/G_logit/kernel": np.zeros((1, 2), np.float32), "discriminator/D_logit/kernel": np.zeros((1, 2), np.float32)}
+    adam = {n: (np.zeros((1, 2), np.float32), np.zeros((1, 2), np.float32)) for n in v}
+    for t in (2, 500, 979, 1000, 2500, 100000):
+        tt = ck.to_tf_tensors(v, ["generator/G_logit/kernel"], ["discriminator/D_logit/kernel"], adam, adam,
+                              {"generator/G_logit/kernel": v["generator/G_logit/kernel"]}, t_g=t, t_d=t + 1, beta1=0.0, beta2=0.9)
+        s = ck.from_tf_tensors(tt, beta2=0.9, counter=t)
+        assert (s["t_g"], s["t_d"]) == (t, t + 1)
+        # a checkpoint written by TensorFlow has no exact counters
+        tf_only = {k: a for k, a in tt.items() if k not in (ck.STEP_G, ck.STEP_D)}
+        s = ck.from_tf_tensors(tf_only, beta2=0.9, counter=t)
+        assert s["t_g"] == t, (t, s["t_g"])
+        assert s["t_d"] == (t + 1 if t + 1 < 600 else t), (t, s["t_d"])     # past the float32 range: the file-name counter
+        assert ck.STEP_G not in s["variables"] and "beta2_power" not in s["variables"]
+    assert ck.steps_from_beta_power(0.0, 0.9) is None and ck.steps_from_beta_power(1e-38, 0.9) is None
+    assert ck.steps_from_beta_power(0.9 ** 6, 0.9) == 5
+    assert ck.counter_from_prefix("/a/b/BigGAN.model-2500") == 2500 and ck.counter_from_prefix("/a/b/weights") is None
+
+
+def test_checkpoint_state_history_and_pruning(tmp_path):
+    """tf.train.Saver(max_to_keep=k) semantics (BigGAN.py:1018): `all_model_checkpoint_paths` keeps the last k prefixes,
+    older bundles are deleted; max_to_keep = 0 keeps everything."""
+    d = str(tmp_path)
+    for step in (10, 20, 30):
+        ck.write_bundle(os.path.join(d, "BigGAN.model-%d" % step), {"x": np.array(step, np.int64)})
+        ck.write_checkpoint_state(d, "BigGAN.model-%d" % step, max_to_keep=2)
+    latest, hist = ck.read_checkpoint_state(d)
+    assert latest == "BigGAN.model-30" and hist == ["BigGAN.model-20", "BigGAN.model-30"]
+    assert not os.path.exists(os.path.join(d, "BigGAN.model-10.index")) and os.path.exists(os.path.join(d, "BigGAN.model-20.index"))
+    assert ck.latest_checkpoint(d) == os.path.join(d, "BigGAN.model-30")
+    ck.write_checkpoint_state(d, "BigGAN.model-20", max_to_keep=0)          # re-saving an old step moves it to the end, no duplicates
+    assert ck.read_checkpoint_state(d) == ("BigGAN.model-20", ["BigGAN.model-30", "BigGAN.model-20"])
+    assert not [f for f in os.listdir(d) if "tmp" in f]

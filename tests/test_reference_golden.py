@@ -179,8 +179,11 @@ def _oracle_net(name):
     return g, rs, d_loss, gd, d_aux, state_d, g_loss, gg, g_aux, state_g
 
 
-def check_net64(g, d_loss, gd, d_aux, state_d, g_loss, gg, g_aux, state_g, tol, gtol, stol, l2=False, skip=()):
-    """Shared by the CPU (oracle) and GPU (CUDA path) tests.  gd / gg: name -> gradient array."""
+def check_net64(g, d_loss, gd, d_aux, state_d, g_loss, gg, g_aux, state_g, tol, gtol, stol, l2=False, skip=(), g_gtol=None,
+                g_norm_tol=None):
+    """Shared by the CPU (oracle) and GPU (CUDA path) tests.  gd / gg: name -> gradient array.  g_gtol / g_norm_tol:
+    tolerance of the G-PHASE gradients (elements / norms) when it differs from gtol (fp32 CUDA path: the end-to-end
+    comparison through D(G(z)) is limited by ReLU / max-pool ties, see tests/test_zz_reference_golden_gpu.py)."""
     C.check(g, "d_loss", np.reshape(d_loss, ()), tol)
     C.check(g, "g_loss", np.reshape(g_loss, ()), tol)
     if d_aux is not None:
@@ -195,12 +198,14 @@ def check_net64(g, d_loss, gd, d_aux, state_d, g_loss, gg, g_aux, state_g, tol, 
         ref = g[which + "_grad_norms"]
         norms = np.array([float(np.linalg.norm(np.asarray(grads[n], dtype=np.float64))) for n in names])
         ok = ref > 1e-3 * ref.max()                      # analytically-zero gradients (f_conv bias) hold only noise
-        np.testing.assert_allclose(norms[ok], ref[ok], rtol=gtol, err_msg=which + " gradient norms")
+        etol = g_gtol if (which == "G" and g_gtol is not None) else gtol
+        ntol = g_norm_tol if (which == "G" and g_norm_tol is not None) else gtol
+        np.testing.assert_allclose(norms[ok], ref[ok], rtol=ntol, err_msg=which + " gradient norms")
         for k in sorted(set(f.split("#")[0] for f in g.files if f.startswith(which + "_grad/"))):
             n = k[len(which) + 6:]
             if n.endswith("f_conv/bias") or n.endswith(tuple(skip)):
                 continue
-            C.check(g, k, grads[n], gtol, l2=l2)
+            C.check(g, k, grads[n], etol, l2=l2)
     for tag, st in (("state_after_D/", state_d), ("state_after_G/", state_g)):
         for k in sorted(set(f.split("#")[0] for f in g.files if f.startswith(tag))):
             C.check(g, k, st[k[len(tag):]], stol, l2=l2)

@@ -60,9 +60,12 @@ def _train(kw, rank, world, pg, shard, steps=2, ckpt_dir=None):
         for key in ("m", "v") + (("ema",) if net == "generator" else ()):
             out[net + "/" + key] = tr.full_opt(net, key).clone().numpy()
         out[net + "/numel"] = n
-    if ckpt_dir:                                       # collective with a sharded optimizer: every rank gathers the slots
+    if ckpt_dir:           # collective: every rank calls save (the slots are gathered), rank 0 alone writes, all leave by a barrier
         from biggan_tensorflow_b200 import checkpoint as ck
-        out["ckpt"] = ck.read_bundle(ck.save(tr, os.path.join(ckpt_dir, "rank%d" % rank), step=steps))
+        d = os.path.join(ckpt_dir, "ckpt_shard%d" % int(shard))
+        prefix = ck.save(tr, d, step=steps)
+        assert sorted(os.listdir(d)) == ["BigGAN.model-%d.data-00000-of-00001" % steps, "BigGAN.model-%d.index" % steps, "checkpoint"]
+        out["ckpt"] = ck.read_bundle(prefix)
     return out
 
 

@@ -28,7 +28,7 @@ def test_trainer_phases_match_reference_networks_on_the_host(host_trainer, name)
     names and shapes) for the canonical networks at 64, 128 (+ DiffAugment), 256 and 512 pixels (BASELINE configs 1-4 at narrow
     width), the fork's CLI defaults (prelu, ortho_cosine, flood, DiffAugment) and the layer variants (lrelu, resize_conv,
     conv3, resize_conv1, bn_in_d, ortho)."""
-    G._cuda_net(name, dev=host_trainer)
+    G._cuda_net(name, dev=host_trainer, split=(name == "net64"))     # the float64 split check once is enough on the host
 
 
 def test_virtual_batches_and_ema_sampling_on_the_host(host_trainer):

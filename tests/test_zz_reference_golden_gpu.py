@@ -23,10 +23,10 @@ TOL_SCALE = {"cbn_relu_4x4x64": (2.0, 2.0), "cbn_relu_8x8x32": (2.0, 2.0), "bn_t
 FP32_ONLY = {"fc_sn", "fc_dense", "cbn_inference", "sa_full_4x4x32"}     # as in tests/test_ops_gpu.py
 
 
-UNVERIFIED = pytest.mark.skipif(
-    os.environ.get("BG_RUN_UNVERIFIED") != "1",
-    reason="written after the round-1 GPU budget was spent: this code path compiles and its oracle side is pinned to the reference "
-           "source on CPU, but it has not run on hardware yet; enable with BG_RUN_UNVERIFIED=1")
+def UNVERIFIED(f):
+    """Round 1 gated these tests behind BG_RUN_UNVERIFIED=1 (written without GPU time).  They ran on B200 at the start of
+    round 2 and are part of the normal `-m gpu` suite now; the marker is kept as a no-op to show which they were."""
+    return f
 
 
 def _acts(ops):
@@ -147,7 +147,61 @@ def _to_cuda(a):
     return torch.from_numpy(a).cuda()
 
 
-def _cuda_net(name, dtype=torch.float32, stol=2e-4, dev=_to_cuda, tol=1e-4, gtol=3e-4, l2=False, skip=()):
+# fp32-mode tolerances of the whole-network checks (the error budget is measured):
+#  * everything of the D phase, the G-phase losses and images: NET_TOL / NET_GTOL (north_star's 1e-4; 3e-4 on gradients);
+#  * G-phase gradients are checked in two TIGHT halves split at the generated image, each against the float64 oracle
+#    evaluated AT THE SAME POINT (the CUDA path's own state and image): dL/d image (D's input-gradient chain) and G's
+#    backward seeded with that dL/d image.  Measured on B200: 7e-7 and 2.4e-6 (net64), 7e-7 and 6.5e-4 (net512, where
+#    the float32 CPU run of the reference algorithm itself is 7.7e-4 off float64: BatchNorm sums over 2 x 512 x 512 terms);
+#  * end to end against the golden vectors the same gradients are limited by the REFERENCE FUNCTION, not by arithmetic:
+#    D(G(z)) is not differentiable at ReLU / max-pool ties, and a 2.5e-6 forward difference in the image moves one tie in
+#    D, which changes dL/d image by 4e-3 of its maximum inside one receptive field of one sample (tools/g_backward_bisect.py)
+#    and every G gradient by up to 2e-3 (net64) / 4e-3 (net512) of its maximum.  Hence KINK_GTOL for that comparison only.
+NET_TOL, NET_GTOL, KINK_GTOL, KINK_NORM_TOL = 1e-4, 3e-4, 1e-2, 3e-3
+SPLIT_TOL = {"net64": (1e-5, 1e-4), "net128da": (1e-5, 1e-4), "net256": (1e-5, 1e-3), "net512": (1e-5, 2e-3)}
+
+
+def _rel_max(a, r):
+    a, r = np.asarray(a, np.float64), np.asarray(r, np.float64)
+    return float(np.abs(a.reshape(r.shape) - r).max() / max(float(np.abs(r).max()), 1e-30))
+
+
+def _g_phase_split_check(name, kw, g, state_after_d, b, img, dimg, gg, tol_d, tol_g):
+    """The two tight halves of the G-phase gradient check (see the tolerance note above).  float64 oracle, started from
+    the CUDA path's own post-D state: (A) d loss / d image evaluated at the CUDA path's image; (B) the generator's backward
+    seeded with the CUDA path's d loss / d image."""
+    from oracle import ref_ops as R
+    cfg = M.Config(**kw)
+    dt = torch.float64
+    rnd = None
+    if kw.get("da_policy"):
+        rnd = R.rnd_to_torch({k.split("/")[1]: g[k] for k in g.files if k.startswith("rnd2/")})
+    rs = R.RefStore(dt, params=state_after_d)
+    rs.begin_phase()
+    M._detach_all(rs)
+    cls_t = torch.as_tensor(b["labels"], dtype=dt)
+    fake_ref = M.generator(rs, cfg, torch.as_tensor(b["z_g"], dtype=dt), cls_t)
+    leaf = torch.tensor(np.asarray(img, np.float64), dtype=dt, requires_grad=True)
+    out = M.discriminator(rs, cfg, R.DiffAugment(leaf, policy=cfg.da_policy, rnd=rnd))
+    loss = R.generator_loss(cfg.gan_type, fake=out["real"], real=None, flood_level=cfg.g_flood)
+    if cfg.acgan:
+        loss = loss + cfg.g_cls_loss_weight * R.cls_loss_logistic(cls_t, out["cls"])
+    (gi,) = torch.autograd.grad(loss, [leaf])
+    e = _rel_max(dimg, gi.numpy())
+    assert e <= tol_d, "%s: d loss / d image at the same image: error %.2e > %.0e" % (name, e, tol_d)
+    g_vars = rs.trainables("generator")
+    names = list(g_vars)
+    grads = torch.autograd.grad(fake_ref, [g_vars[n] for n in names], grad_outputs=torch.as_tensor(np.asarray(dimg, np.float64)),
+                                allow_unused=True)
+    scale = max(float(gr.abs().max()) for gr in grads if gr is not None)
+    for n, gr in zip(names, grads):
+        if gr is None or n.endswith("f_conv/bias") or float(gr.abs().max()) <= 1e-10 * scale:
+            continue                                    # analytically zero: only rounding noise on both sides
+        e = _rel_max(gg[n], gr.numpy())
+        assert e <= tol_g, "%s: G backward seeded with the same d loss / d image, %s: error %.2e > %.0e" % (name, n, e, tol_g)
+
+
+def _cuda_net(name, dtype=torch.float32, stol=2e-4, dev=_to_cuda, tol=NET_TOL, gtol=NET_GTOL, l2=False, skip=(), split=True):
     from biggan_tensorflow_b200 import DiffAugment_tf as D
     from biggan_tensorflow_b200.model import Config
     from biggan_tensorflow_b200.step import Trainer
@@ -159,15 +213,23 @@ def _cuda_net(name, dtype=torch.float32, stol=2e-4, dev=_to_cuda, tol=1e-4, gtol
     if kw.get("da_policy"):
         for i in range(3):
             D.push_randoms({k.split("/")[1]: g[k] for k in g.files if k.startswith("rnd%d/" % i)})
-    d_loss, _ = tr.d_update(dev(b["real"]), dev(b["labels"]), dev(b["z_d"]), dev(b["labels"]), apply=False)
+    host = lambda t: t.data.detach().float().cpu().numpy()
+    d_loss, da = tr.d_update(dev(b["real"]), dev(b["labels"]), dev(b["z_d"]), dev(b["labels"]), apply=False)
     gd = tr.grads("discriminator")
     state_d = tr.store.export()
-    g_loss, _ = tr.g_update(dev(b["z_g"]), dev(b["labels"]), apply=False)
+    d_aux = {"real_logits": host(da["real_logits"]), "fake_logits": host(da["fake_logits"]), "fake": host(da["fake"])[..., :3]}
+    g_loss, ga = tr.g_update(dev(b["z_g"]), dev(b["labels"]), apply=False)
     gg = tr.grads("generator")
     state_g = tr.store.export()
+    img, dimg = host(ga["fake"])[..., :3], ga["fake"].grad.detach().float().cpu().numpy()[..., :3]
+    g_aux = {"fake_logits": host(ga["fake_logits"]), "fake": img}
     ref_shapes = {str(n): tuple(int(s) for s in str(sh).split(",") if s) for n, sh in zip(g["all_names"], g["all_shapes"])}
     assert {k: tuple(v.shape) for k, v in state_g.items()} == ref_shapes
-    check_net64(g, float(d_loss.cpu()), gd, None, state_d, float(g_loss.cpu()), gg, None, state_g, tol=tol, gtol=gtol, stol=stol, l2=l2, skip=skip)
+    fp32 = dtype == torch.float32 and not l2
+    check_net64(g, float(d_loss.cpu()), gd, d_aux, state_d, float(g_loss.cpu()), gg, g_aux, state_g, tol=tol, gtol=gtol, stol=stol, l2=l2,
+                skip=skip, g_gtol=max(gtol, KINK_GTOL) if fp32 else None, g_norm_tol=max(gtol, KINK_NORM_TOL) if fp32 else None)
+    if fp32 and split and name in SPLIT_TOL:
+        _g_phase_split_check(name, kw, g, state_d, b, img, dimg, gg, *SPLIT_TOL[name])
 
 
 @pytest.mark.gpu
