@@ -20,6 +20,8 @@ extern "C" const char* bgio_last_error(void) { return g_err; }
 
 static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
+// header dimensions come from the file: callers size buffers from them, so they are bounded where they are parsed
+static const int kMaxSide = 1 << 16;
 struct PngHeader { int w, h, depth, color, interlace, channels; };
 struct PngParts { PngHeader hdr; std::vector<uint8_t> idat; uint8_t palette[256][3]; int n_palette = 0; };
 
@@ -41,6 +43,7 @@ static int walk(const uint8_t* d, size_t n, PngParts* parts, bool header_only) {
       PngHeader& h = parts->hdr;
       h.w = (int)be32(body); h.h = (int)be32(body + 4); h.depth = body[8]; h.color = body[9]; h.interlace = body[12];
       if (h.w <= 0 || h.h <= 0 || body[10] != 0 || body[11] != 0) return fail("unsupported PNG header");
+      if (h.w > kMaxSide || h.h > kMaxSide) return fail("PNG dimensions %d x %d are out of range (1..%d)", h.w, h.h, kMaxSide);
       switch (h.color) {
         case 0: h.channels = 1; break;
         case 2: h.channels = 3; break;
@@ -85,7 +88,6 @@ extern "C" int bgio_png_decode(const void* data, size_t n, void* out_v, size_t o
   const PngHeader& h = p.hdr;
   // header dimensions come from the file: bound them before any size arithmetic (a crafted IHDR near 2^31 would wrap the
   // products below, and zlib's 32-bit avail_in / avail_out would truncate a > 4 GiB scanline buffer)
-  const int kMaxSide = 1 << 16;
   if (h.w <= 0 || h.h <= 0 || h.w > kMaxSide || h.h > kMaxSide) return fail("PNG dimensions %d x %d are out of range (1..%d)", h.w, h.h, kMaxSide);
   if (h.interlace) return fail("interlaced PNG is not supported");
   const bool pal = h.color == 3;

@@ -134,6 +134,15 @@ def test_png_decoder_rejects_bad_input():
         D.decode_png(interlaced)
     with pytest.raises(ValueError, match="`out`"):
         D.decode_png(bytes(png), out=np.zeros((4, 4, 4), np.uint8))
+    # crafted header: dimensions near 2^31 would wrap the size arithmetic -> rejected before any allocation
+    for w, h in ((0x7FFFFFFF, 0x7FFFFFFF), (0x7FFFFFFF, 1), (1, 0x7FFFFFFF), (0, 4), (70000, 2)):
+        huge = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + _chunk(b"IDAT", zlib.compress(bytes(14))) + _chunk(b"IEND", b"")
+        with pytest.raises(ValueError, match="out of range|unsupported PNG header"):
+            D.decode_png(huge)
+    # a stream longer than the image needs (trailing scanline data) is rejected, not silently truncated
+    over = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 2, 0, 0, 0)) + _chunk(b"IDAT", zlib.compress(bytes(14 + 7))) + _chunk(b"IEND", b"")
+    with pytest.raises(ValueError, match="inflate"):
+        D.decode_png(over)
 
 
 def _dataset(tmp_path, n, size=6):
