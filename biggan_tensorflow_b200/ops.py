@@ -147,6 +147,12 @@ def spectral_norm(w, iteration=1, _out_dtype=None, _taps=1, _want_t=False, _pad_
     hit = store.sn_cache.get(key)
     if hit is not None:
         return hit
+    grouped = getattr(store, "sn_grouped", {}).get(u.name)
+    if grouped is not None:
+        # the grouped pass (sn_group.SnGroup.forward) has advanced this u for the phase; evaluating the weight again in
+        # another layout would advance it a second time (the reference updates u once per run, ops.py:743)
+        raise RuntimeError("spectral_norm(%s): layout %r was not part of the grouped pass built for this network (it holds %r); "
+                           "rebuild the Trainer with the options in use" % (u.name, key[1:], grouped[1:]))
     reg = getattr(store, "sn_registry", None)
     if reg is not None and key not in reg:       # the Trainer is enumerating the network's spectral norms
         reg[key] = {"w": w, "u": u, "taps": _taps, "rows": rows, "r_pad": r_pad, "c_pad": c_pad, "out_dtype": out_dtype,

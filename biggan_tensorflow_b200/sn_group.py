@@ -26,6 +26,11 @@ class SnGroup:
         """entries: registry records of ops.spectral_norm (dicts with w, u, taps, rows, r_pad, c_pad, out_dtype, want_t, key)."""
         self.entries = entries
         n = len(entries)
+        # one record per weight: two records sharing a `u` (the same weight requested in two layouts) would both advance u and
+        # both write dW within one launch
+        names = [e["u"].name for e in entries]
+        assert len(set(names)) == len(names), "spectral_norm registry holds two layouts of one weight: %s" % sorted(
+            n_ for n_ in set(names) if names.count(n_) > 1)
         self.items = (SnItem * n)()
         dev = device()
         for i, e in enumerate(entries):
@@ -59,6 +64,7 @@ class SnGroup:
         self.live = []
         for e in self.entries:
             w = e["w"]
+            store.sn_grouped[e["u"].name] = e["key"]     # a later call asking for another layout of this weight must not re-run the power iteration
             wn = Tensor(e["out"], requires_grad=w.requires_grad)
             wn.aux = {"w_t": e["out_t"], "sigma": e["sigma"], "v_hat": e["v"], "u_hat": e["u"].data}
             if w.requires_grad:

@@ -65,6 +65,7 @@ class VariableStore:
         self.vars = {}
         self.scope = []
         self.sn_cache = {}       # per update-phase cache: one spectral_norm evaluation per variable
+        self.sn_grouped = {}     # u name -> cache key of the weights a grouped spectral norm already advanced this phase
         self.arenas = {}
         self.regularizers = {}   # full variable name -> regularizer (tf REGULARIZATION_LOSSES: one entry per variable)
         self.default_names = {}  # parent scope -> {base: count} for variable_scope(None, default_name=...)
@@ -92,6 +93,7 @@ class VariableStore:
 
     def begin_phase(self):
         self.sn_cache = {}
+        self.sn_grouped = {}
 
     def trainable_variables(self, substr):
         return [v for k, v in sorted(self.vars.items()) if v.trainable and substr in k]
