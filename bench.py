@@ -157,9 +157,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-entry-point timing breakdown here")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the captured CUDA graph")
-    ap.add_argument("--shard-optimizer", action="store_true",
-                    help="N > 1: reduce-scatter gradients, Adam on 1/N of the arena per rank, all-gather parameters (off by default: "
-                         "not yet measured on hardware)")
+    ap.add_argument("--no-shard-optimizer", action="store_true",
+                    help="N > 1: all-reduce + replicated Adam instead of reduce-scatter, Adam on 1/N of the arena per rank, all-gather")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: keep the D update's collective + Adam on the compute stream")
     ap.add_argument("--quick", action="store_true", help="warm-up + timed steps only (for ncu captures): no e2e / breakdown pass")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -196,7 +196,7 @@ def main():
         kw["batch_size"] = args.batch
     cfg = Config(**kw)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    tr = Trainer(cfg, compute_dtype=dtype, rank=rank, world_size=world, process_group=pg, shard_optimizer=args.shard_optimizer)
+    tr = Trainer(cfg, compute_dtype=dtype, rank=rank, world_size=world, process_group=pg, shard_optimizer=not args.no_shard_optimizer, overlap=not args.no_overlap)
     tr.build()
     B, Bl = cfg.batch_size, cfg.batch_size // world
     sb = synthetic_batch(RConfig(**kw), B=B)           # same synthetic tensors on every rank; each takes its shard

@@ -112,6 +112,26 @@ def profile_end():
     return out
 
 
+class timed:
+    """with timed("nccl_allreduce_grads"): ...  -- CUDA-event record of a non-C-ABI region (collectives) while profiling."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if _prof is not None:
+            import torch
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            self.e1.record()
+            _prof.append((self.tag, self.e0, self.e1, 0.0))
+        return False
+
+
 def call(name, *args, flops=0.0, tag=None):
     """Invoke a status-returning entry point; raise with bg_last_error() on failure."""
     global launch_count

@@ -412,7 +412,15 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
-  for (int i = 0; i < nchunk; ++i) s += part[(long)i * C + c];
+  int i = 0;
+  for (; i + 8 <= nchunk; i += 8) {          // 8 independent loads in flight, added in the same fixed order
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(part + (long)(i + k) * C + c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+  }
+  for (; i < nchunk; ++i) s += part[(long)i * C + c];
   out[c] = s;
 }
 

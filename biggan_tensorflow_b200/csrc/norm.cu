@@ -110,8 +110,22 @@ __global__ void __launch_bounds__(1024) bn_stats_final_kernel(const float* __res
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   double a = 0.0, q = 0.0;
-  if (c < C)
-    for (int i = ty; i < nrow; i += 32) { a += (double)part[((long)i * 2) * C + c]; q += (double)part[((long)i * 2 + 1) * C + c]; }
+  if (c < C) {
+    // the partial rows are L2 hits whose latency dominated this kernel (one dependent load pair per iteration): issue 8
+    // row pairs at once, then add them in the same fixed order
+    int i = ty;
+    for (; i + 7 * 32 < nrow; i += 8 * 32) {
+      float va[8], vq[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        va[k] = __ldg(part + ((long)(i + k * 32) * 2) * C + c);
+        vq[k] = __ldg(part + ((long)(i + k * 32) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a += (double)va[k]; q += (double)vq[k]; }
+    }
+    for (; i < nrow; i += 32) { a += (double)part[((long)i * 2) * C + c]; q += (double)part[((long)i * 2 + 1) * C + c]; }
+  }
   sa[ty][tx] = a; sq[ty][tx] = q;
   __syncthreads();
   if (ty == 0 && c < C) {

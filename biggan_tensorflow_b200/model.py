@@ -9,8 +9,8 @@ import torch
 
 from . import _lib
 from .ops import (bn, cast, compute_dtype, rgb_pad, constant_initializer, conv, fully_connected, get_variable,
-                  global_sum_pooling, lrelu, prelu, relu, reshape, resblock, resblock_down, resblock_up_condition,
-                  round_up, self_attention_2, variable_scope)
+                  global_sum_pooling, lrelu, precompute_cbn_projections, prelu, relu, reshape, resblock, resblock_down,
+                  resblock_up_condition, round_up, self_attention_2, variable_scope)
 from .utils import orthogonal_regularizer, orthogonal_regularizer_fc
 from .tensor import F32, Tensor
 
@@ -159,6 +159,18 @@ def generator(cfg, z, cls_z, is_training=True):
                 x = fully_connected(x, units=4 * 4 * ch, scope='dense2', opt=opt)
         x = reshape(x, [-1, 4, 4, ch])                                          # :446
         x = cast(x, compute_dtype())
+        # every conditional-BN gamma / beta projection of the pass in one grouped launch (same names, same math; ops.py)
+        hoist, zi, cin, ch_h, mul_h = [], 1, ch, ch, ch_mul
+        for bi_h, block_count in enumerate(block_info["counts"]):
+            scope = 'resblock_up_' + str(mul_h)
+            for sb_i in range(block_count):
+                if block_count > 1:
+                    scope = scope + '_' + str(sb_i)
+                hoist += [(scope + '/res1/batch_norm', z_split[zi], cin), (scope + '/res2/batch_norm', z_split[zi], ch_h)]
+                zi, cin = zi + 1, ch_h
+            ch_h = round_up(int(cfg.ch * 2.0 ** (n_blocks - bi_h - 2)), 8)
+            mul_h //= 2
+        precompute_cbn_projections(hoist, opt)
         zi = 1
         b_i = 0
         for block_count in block_info["counts"]:

@@ -9,6 +9,9 @@ Precision modes (north_star): `set_compute_dtype(F32)` = parity mode (fp32 SIMT 
 `set_compute_dtype(BF16)` = performance mode (bf16 activations, fp32 accumulate, tcgen05 kernels
 where the shape is eligible).  Fully-connected layers always run in fp32 (they are tiny).
 """
+import contextlib
+import ctypes
+
 import torch
 
 from . import _lib
@@ -1042,6 +1045,79 @@ def _bn_core(x, gamma, beta, gb_bstride, run_mean, run_var, momentum, var_correc
     return y
 
 
+class FcGroupItem(ctypes.Structure):
+    """mirror of bg_fc_group_item"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("x", "w", "bias", "y")] + [(n, ctypes.c_int) for n in ("K", "N", "ldw", "reserved")]
+
+
+def precompute_cbn_projections(items, opt):
+    """Hoists the gamma / beta projections of conditional batch norm (ops.py:623-627) out of the blocks: their inputs (z chunk
+    + class vector) exist before the first block runs, so all of them are computed by ONE grouped launch here and their weight
+    / bias gradients by ONE launch at the end of the backward pass (csrc/fc_group.cu) instead of ~18 launches per CBN layer.
+    items: [(scope path of the batch-norm scope relative to the current scope, z Tensor [B, K] fp32, channels)].
+    The results wait in the store's phase cache until `condition_batch_norm` asks for them under that scope name; the
+    variables are created under exactly the names fully_connected would give them.  Returns False (nothing done) when the
+    configuration does not fit the grouped kernels; the blocks then compute their own projections."""
+    store = get_store()
+    bn_type = opt.get("bn", {}).get("type", "bn")
+    if not (_state["compute_dtype"] == BF16 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1
+            and opt.get("conv", {}).get("sn", True) and bn_type in ("bn", "batch_norm") and 0 < 2 * len(items) <= 32):
+        return False
+    for _, z, c in items:
+        K = z.numel() // z.shape[0]
+        if z.requires_grad or z.dtype != F32 or K % 4 != 0 or c % 4 != 0:       # 16-byte vector loads of the grouped kernels
+            return False
+    recs, arr = [], (FcGroupItem * (2 * len(items)))()
+    B = items[0][1].shape[0]
+    for path, z, c in items:
+        K = z.numel() // B
+        with contextlib.ExitStack() as es:
+            for part in path.split("/"):
+                es.enter_context(variable_scope(part))
+            key = current_scope_name()
+            pair = []
+            for name in ("beta", "gamma"):                 # creation order of ops.py:623-627
+                with variable_scope(name):
+                    reg = opt.get("fc_regularizer", None) if 'generator' in current_scope_name() else None
+                    w = get_variable_with_custom_lr("kernel", shape=[K, c], regularizer=reg, lrmul=1.0)
+                    bias = get_variable("bias", [c], initializer=constant_initializer(0.0))
+                    wn = _sn_weight(w, 1, True, BF16)
+                y = Tensor(empty([B, c], F32), requires_grad=wn.requires_grad or bias.requires_grad)
+                it = arr[len(recs)]
+                it.x, it.w, it.bias, it.y = z.data.data_ptr(), wn.aux["w_t"].data_ptr(), bias.data.data_ptr(), y.data.data_ptr()
+                it.K, it.N, it.ldw = K, c, K          # w_t is the [c][K] (K-major) copy, whatever shape its handle carries
+                recs.append((z, wn, bias, y))
+                pair.append(y)
+            store.cbn_cache[key] = (pair[1], pair[0])      # (gamma, beta)
+    call("bg_fc_group_fwd", arr, len(recs), B, _lib.BG_BF16, stream(), tag="fc_group_fwd")
+    if recording(*[t for r in recs for t in (r[1], r[2])]):
+        def bw():
+            live, fins = [], []
+            for z, wn, bias, y in recs:
+                if y.grad is None:
+                    continue
+                dw, fin_w = grad_target(wn, dtype=F32) if wn.requires_grad else (None, None)
+                db, fin_b = grad_target(bias) if bias.requires_grad else (None, None)
+                live.append((z, y, dw, db))
+                fins += [f for f in (fin_w, fin_b) if f]
+            if not live:
+                return
+            arr2 = (FcGroupItem * len(live))()
+            scratch = []
+            for it, (z, y, dw, db) in zip(arr2, live):
+                g = y.grad.contiguous()
+                if dw is None:                              # bias-only gradient: the kernel still needs a destination
+                    dw = empty([z.numel() // B, y.shape[1]], F32)
+                scratch.append((g, dw))
+                it.x, it.w, it.bias, it.y = z.data.data_ptr(), dw.data_ptr(), (db.data_ptr() if db is not None else None), g.data_ptr()
+                it.K, it.N, it.ldw = z.numel() // B, y.shape[1], dw.shape[-1]
+            call("bg_fc_group_bwd", arr2, len(live), B, stream(), tag="fc_group_bwd")
+            for f in fins:
+                f()
+        record(bw)
+    return True
+
+
 def condition_batch_norm(x, z, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
     """ops.py:611-643."""
     with variable_scope(scope):
@@ -1049,6 +1125,10 @@ def condition_batch_norm(x, z, opt={}, scope='batch_norm', _act=_lib.ACT_NONE):
         decay = opt.get("bn", {}).get("momentum", 0.98)
         test_mean = get_variable("pop_mean", shape=[c], initializer=constant_initializer(0.0), trainable=False)
         test_var = get_variable("pop_var", shape=[c], initializer=constant_initializer(1.0), trainable=False)
+        hoisted = get_store().cbn_cache.pop(current_scope_name(), None)
+        if hoisted is not None:                  # projections computed up front by precompute_cbn_projections
+            gamma, beta = hoisted
+            return _bn_core(x, gamma, beta, c, test_mean, test_var, decay, lambda n: 1.0, opt, _act)
         if (_state["compute_dtype"] == BF16 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1
                 and z.numel() // z.shape[0] % 8 == 0 and c % 16 == 0 and opt.get("conv", {}).get("sn", True)):
             z = cast(flatten(z), BF16)           # both projections take the tensor-core path: cast the condition once

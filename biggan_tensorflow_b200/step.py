@@ -9,6 +9,7 @@ small all-reduces inside ops._bn_core; losses are scaled by 1/global batch so su
 the single-device gradient of the global-batch mean.
 """
 import math
+import os
 
 import torch
 
@@ -44,15 +45,23 @@ def split_rows(t, sizes):
 
 
 class Trainer:
-    def __init__(self, cfg: Config, compute_dtype=F32, rank=0, world_size=1, process_group=None, shard_optimizer=False):
-        """shard_optimizer (off by default; SURVEY 8e "optionally optimizer-sharded"): with world_size > 1 the update phases
+    def __init__(self, cfg: Config, compute_dtype=F32, rank=0, world_size=1, process_group=None, shard_optimizer=None, overlap=True):
+        """shard_optimizer (default: on when world_size > 1; SURVEY 8e "optionally optimizer-sharded"): the update phases
         reduce-scatter the gradient arena, run Adam(+EMA) on this rank's 1/world slice and all-gather the parameters --
-        the same bytes on the wire as the all-reduce, 1/world of the optimizer's HBM traffic per rank."""
+        the same bytes on the wire as the all-reduce, 1/world of the optimizer's HBM traffic per rank.
+        overlap (world_size > 1, CUDA): the D update's collective + Adam run on a side stream underneath the G phase's
+        generator forward (which does not touch D); the BN-statistics all-reduces then use their own communicator so
+        that they do not queue behind the gradient collective."""
         self.cfg = cfg
         self.compute_dtype = compute_dtype
         self.rank, self.world = rank, world_size
         self.pg = process_group
-        self.shard = bool(shard_optimizer) and world_size > 1
+        self.pg_small = process_group
+        self.shard = (world_size > 1) if shard_optimizer is None else (bool(shard_optimizer) and world_size > 1)
+        self.overlap = bool(overlap) and world_size > 1
+        self.comm_stream = None          # created in build() on a CUDA device
+        self.peer = None                 # comm.PeerComm (NVLink peer-memory all-reduce of the BN statistics)
+        self._pending = False            # D-update collective / Adam in flight on the side stream
         self.store = set_store(VariableStore())
         ops.set_compute_dtype(compute_dtype)
         assert cfg.batch_size % world_size == 0, "global batch must divide across ranks"
@@ -62,7 +71,8 @@ class Trainer:
             import torch.distributed as dist
 
             def allreduce(buf):
-                dist.all_reduce(buf, group=self.pg)
+                with _lib.timed("nccl_allreduce_bn_stats"):
+                    dist.all_reduce(buf, group=self.pg_small)
                 return buf
             ops.dist.all_reduce_sum = allreduce
         else:
@@ -81,6 +91,21 @@ class Trainer:
         flat arenas (params / grads / Adam m, v / EMA shadows)."""
         cfg = self.cfg
         dev = device()
+        if self.overlap and dev.type == "cuda" and self.comm_stream is None:
+            import torch.distributed as dist
+            self.comm_stream = torch.cuda.Stream()
+            self.pg_small = dist.new_group(ranks=list(range(self.world)))      # own communicator for the BN statistics
+        if self.world > 1 and dev.type == "cuda" and self.peer is None and os.environ.get("BG_BN_SYNC", "p2p") == "p2p":
+            # cross-replica BN statistics: one-shot all-reduce over NVLink peer memory (csrc/comm.cu) instead of NCCL
+            from .comm import MAX_DOUBLES, PeerComm
+            self.peer = PeerComm(self.rank, self.world, self.pg)
+            nccl_sum = ops.dist.all_reduce_sum
+
+            def peer_sum(buf):
+                if buf.dtype == torch.float64 and buf.numel() <= MAX_DOUBLES:
+                    return self.peer.all_reduce_sum(buf)
+                return nccl_sum(buf)
+            ops.dist.all_reduce_sum = peer_sum
         z = torch.zeros(2, 1, 1, cfg.z_dim, device=dev)
         cls = torch.zeros(2, max(cfg.n_labels, 1), device=dev)
         set_store(self.store)
@@ -99,7 +124,10 @@ class Trainer:
             n = ar["params"].numel()
             self.opt[net] = {"m": torch.zeros(n, device=dev), "v": torch.zeros(n, device=dev),
                              "ema": ar["params"].clone() if net == "generator" else None,
-                             "state": torch.zeros(2, device=dev)}          # [t, lr_t]
+                             "state": torch.zeros(2, device=dev),          # [t, lr_t]
+                             # sharded optimizer: persistent landing buffers of the reduce-scatter / source of the all-gather
+                             "gshard": torch.zeros(n // self.world, device=dev) if self.shard else None,
+                             "pshard": torch.zeros(n // self.world, device=dev) if self.shard else None}
         from .sn_group import SnGroup
         self.sn_groups = {net: SnGroup([e for e in registry.values() if net in e["u"].name])
                           for net in ("generator", "discriminator")}
@@ -135,19 +163,60 @@ class Trainer:
             v.grad_owned = True
         self.store.begin_phase()
         clear_tape()
-        for grp in self.sn_groups.values():          # every forward of a network advances its u once per phase
-            grp.forward(self.store)
+        # every forward of a network advances its u once per phase.  In the G phase D's spectral norm waits until the
+        # generator forward is issued (`_sn_forward_discriminator`): D's parameters may still be in the D update's
+        # collective / Adam on the side stream
+        self.sn_groups["generator"].forward(self.store)
+        if net == "discriminator":
+            self._sn_forward_discriminator()
+
+    def _sn_forward_discriminator(self):
+        self._join_side()
+        self.sn_groups["discriminator"].forward(self.store)
+
+    def _join_side(self):
+        """Main stream waits for the side stream's D update (no-op when nothing is in flight)."""
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self._pending = False
 
     def _shard_slice(self, net):
         n = self.store.arenas[net]["params"].numel() // self.world
         return slice(self.rank * n, (self.rank + 1) * n)
 
-    def _finish_grads(self, net, for_update=False):
+    def _update(self, net, lr, apply):
+        """Gradient collective (+ optimizer step when `apply`).  The D update of an overlapped trainer runs on the side
+        stream; whoever needs D's parameters next joins it (`_join_side`)."""
         self.sn_groups[net].backward()
         ar = self.store.arenas[net]
         for v in ar["vars"]:
             if not v.grad_set:
                 v.grad_view.zero_()
+        self._regularizer_grads(net, ar)
+        side = apply and net == "discriminator" and self.comm_stream is not None
+        if side:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self._reduce_grads(net, ar, for_update=True)
+                self._adam(net, lr)
+            self._pending = True
+            return
+        self._reduce_grads(net, ar, for_update=apply)
+        if apply:
+            self._adam(net, lr)
+
+    def _finish_grads(self, net, for_update=False):
+        """(kept for callers that only want the summed gradients)"""
+        self.sn_groups[net].backward()
+        ar = self.store.arenas[net]
+        for v in ar["vars"]:
+            if not v.grad_set:
+                v.grad_view.zero_()
+        self._regularizer_grads(net, ar)
+        self._reduce_grads(net, ar, for_update)
+        return ar
+
+    def _regularizer_grads(self, net, ar):
         self.reg_loss = None
         if net == "generator" and self.regs:
             # g_loss += sum of the regularisation losses (BigGAN.py:897-898).  Every rank holds the same weights and the
@@ -155,16 +224,16 @@ class Trainer:
             self.reg_loss = torch.zeros(1, dtype=torch.float32, device=ar["grads"].device)
             for v, reg in self.regs:
                 reg.evaluate(v.data, self.reg_loss, dW=v.grad_view, grad_scale=1.0 / self.world)
+
+    def _reduce_grads(self, net, ar, for_update):
         if self.world > 1:
             import torch.distributed as dist
             if self.shard and for_update:                        # only this rank's slice of the summed gradient is needed
-                sl = self._shard_slice(net)
-                shard = torch.empty_like(ar["grads"][sl])
-                dist.reduce_scatter_tensor(shard, ar["grads"], group=self.pg)
-                ar["grads"][sl].copy_(shard)
+                with _lib.timed("nccl_reduce_scatter_grads"):
+                    dist.reduce_scatter_tensor(self.opt[net]["gshard"], ar["grads"], group=self.pg)
             else:
-                dist.all_reduce(ar["grads"], group=self.pg)      # NCCL over NVLink; sum == global-batch gradient
-        return ar
+                with _lib.timed("nccl_allreduce_grads"):
+                    dist.all_reduce(ar["grads"], group=self.pg)      # NCCL over NVLink; sum == global-batch gradient
 
     def _adam(self, net, lr):
         """Adam(+EMA) over the network's flat arena; the step counter and lr_t live on the device (graph-replayable)."""
@@ -175,10 +244,12 @@ class Trainer:
         if self.shard:
             import torch.distributed as dist
             sl = self._shard_slice(net)
-            p = ar["params"][sl]
-            call("bg_adam_ema_step", p, ar["grads"][sl], o["m"][sl], o["v"][sl], o["ema"][sl] if o["ema"] is not None else None,
+            p = o["pshard"]
+            p.copy_(ar["params"][sl])
+            call("bg_adam_ema_step", p, o["gshard"], o["m"][sl], o["v"][sl], o["ema"][sl] if o["ema"] is not None else None,
                  p.numel(), 0.0, o["state"][1:], float(cfg.beta1), float(cfg.beta2), 1e-8, float(cfg.moving_decay), 1.0, stream())
-            dist.all_gather_into_tensor(ar["params"], p.clone(), group=self.pg)
+            with _lib.timed("nccl_allgather_params"):
+                dist.all_gather_into_tensor(ar["params"], p, group=self.pg)
             return
         call("bg_adam_ema_step", ar["params"], ar["grads"], o["m"], o["v"], o["ema"], ar["params"].numel(),
              0.0, o["state"][1:], float(cfg.beta1), float(cfg.beta2), 1e-8, float(cfg.moving_decay), 1.0, stream())
@@ -186,6 +257,7 @@ class Trainer:
     def full_opt(self, net, key):
         """Optimizer state `key` ('m', 'v', 'ema') over the whole arena (with a sharded optimizer every rank maintains its
         slice only: collective call)."""
+        self._join_side()
         t = self.opt[net][key]
         if self.shard and t is not None:
             import torch.distributed as dist
@@ -248,9 +320,7 @@ class Trainer:
             cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
             d_loss = d_loss + cfg.d_cls_loss_weight * cls_loss(labels, real_cls)                   # :853
         backward([(d_loss, torch.ones(1, device=real.device))])
-        self._finish_grads("discriminator", for_update=apply)
-        if apply:
-            self._adam("discriminator", cfg.d_lr)
+        self._update("discriminator", cfg.d_lr, apply)
         return d_loss.data, {"fake": fake, "real_logits": real_logits, "fake_logits": fake_logits}
 
     def g_update(self, z, cls_z, apply=True):
@@ -261,19 +331,18 @@ class Trainer:
         self._set_phase("generator")
         fake = generator(cfg, z, cls_z)
         aug = DiffAugment_tf.DiffAugment(fake, policy=cfg.da_policy)
+        self._sn_forward_discriminator()                   # joins the D update running underneath the generator forward
         out = discriminator(cfg, aug)
         g_loss = ops.generator_loss(cfg.gan_type, fake=out["real"], real=None, flood_level=cfg.g_flood)   # :896
         if cfg.acgan:
             cls_loss = ops.cls_loss_fn('logistic', self.cls_weights)
             g_loss = g_loss + cfg.g_cls_loss_weight * cls_loss(cls_z, out["cls"])                  # :894
         backward([(g_loss, torch.ones(1, device=z.device))])
-        self._finish_grads("generator", for_update=apply)
+        self._update("generator", cfg.g_lr, apply)
         loss = g_loss.data
         if self.reg_loss is not None:
             loss = torch.empty_like(g_loss.data)      # like the other terms, each rank reports its 1/world share: the sum over ranks is the loss
             call("bg_axpby", self.reg_loss, g_loss.data, None, 1.0 / self.world, 1.0, loss, 1, _lib.BG_F32, stream())
-        if apply:
-            self._adam("generator", cfg.g_lr)
         return loss, {"fake": fake, "fake_logits": out["real"]}
 
     def train_step(self, real, labels, z_d, z_g, cls_z):
@@ -298,6 +367,8 @@ class Trainer:
             losses.append(loss)
             call("bg_add", acc, ar["grads"], acc, n, _lib.BG_F32, stream())
         call("bg_axpby", acc, None, None, 1.0 / k, 0.0, ar["grads"], n, _lib.BG_F32, stream())
+        if self.shard:                                # the accumulated gradients are full sums (all-reduced per virtual batch)
+            self.opt[net]["gshard"].copy_(ar["grads"][self._shard_slice(net)])
         self._adam(net, lr)
         return losses
 
@@ -317,6 +388,7 @@ class Trainer:
         every rank must make it."""
         if not self._built:
             self.build()
+        self._join_side()
         ar, o = self.store.arenas["generator"], self.opt["generator"]
         saved = None
         if ema and o["ema"] is not None:
@@ -336,5 +408,6 @@ class Trainer:
 
     def grads(self, net):
         ar = self.store.arenas[net]
+        self._join_side()
         torch.cuda.synchronize()
         return {v.name: v.grad_view.detach().cpu().numpy().copy() for v in ar["vars"]}

@@ -66,6 +66,7 @@ class VariableStore:
         self.scope = []
         self.sn_cache = {}       # per update-phase cache: one spectral_norm evaluation per variable
         self.sn_grouped = {}     # u name -> cache key of the weights a grouped spectral norm already advanced this phase
+        self.cbn_cache = {}      # batch-norm scope name -> (gamma, beta) computed up front (ops.precompute_cbn_projections)
         self.arenas = {}
         self.regularizers = {}   # full variable name -> regularizer (tf REGULARIZATION_LOSSES: one entry per variable)
         self.default_names = {}  # parent scope -> {base: count} for variable_scope(None, default_name=...)
@@ -94,6 +95,7 @@ class VariableStore:
     def begin_phase(self):
         self.sn_cache = {}
         self.sn_grouped = {}
+        self.cbn_cache = {}
 
     def trainable_variables(self, substr):
         return [v for k, v in sorted(self.vars.items()) if v.trainable and substr in k]

@@ -293,6 +293,37 @@ int bg_image_prepare(const void* src_u8, const int* flip, void* dst, int B, int 
                      int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Grouped fully-connected layers (fc_group.cu) -- ops.py:148-175 as called by condition_batch_norm (ops.py:623-627):
+ * all gamma / beta projections of one generator pass in ONE launch (their inputs, z chunk + class vector, exist before
+ * the first block), and all their weight / bias gradients in ONE launch at the end of the backward pass.
+ *   forward : y_i[M, N_i] (fp32) = x_i[M, K_i] (fp32) . w_i[N_i, ldw_i]^T + bias_i;  w = K-major normalised weights
+ *             (the transposed copy bg_sn_scale writes), w_dtype BG_BF16 or BG_F32; K_i, ldw_i multiples of 4.
+ *   backward: w_i[K_i, ldw_i] (fp32, OUT) = x_i^T . y_i  (y_i = d loss / d y_i, fp32 [M, N_i]);  bias_i[N_i] (OUT, may be
+ *             NULL) = column sums of y_i.  Fixed summation order.  At most 32 problems per call.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const void* x; void* w; void* bias; void* y; int K, N, ldw, reserved; } bg_fc_group_item;
+int bg_fc_group_fwd(const bg_fc_group_item* items, int n, int M, int w_dtype, void* stream);
+int bg_fc_group_bwd(const bg_fc_group_item* items, int n, int M, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel small exchanges (comm.cu; SURVEY 8e collective C2 -- new design, the reference is single-device):
+ * one-shot all-reduce over NVLink peer memory for the cross-replica BatchNorm statistics (2C doubles per BN layer,
+ * forward and backward; the sums ops.py:630 takes over the local batch become sums over the global batch).
+ *   bg_comm_local_alloc: allocates this rank's exchange buffer on the current device (the one exception to "the library
+ *     allocates nothing": the buffer must be a whole cudaMalloc allocation to be exportable) and returns its 64-byte
+ *     CUDA IPC handle in handle64_out (host memory).  The caller exchanges the handles of all ranks (host side).
+ *   bg_comm_open: handles = world x 64 bytes in rank order (host memory) -> opaque communicator in *comm_out.
+ *   bg_comm_allreduce_f64: out[i] = sum over ranks of in[i], n <= 4096 doubles, out may alias in; one kernel on `stream`,
+ *     graph-capturable, result bit-identical on every rank (fixed rank order).  Every rank must issue the same
+ *     sequence of calls.
+ * ------------------------------------------------------------------------------------------- */
+size_t bg_comm_buffer_bytes(void);
+int bg_comm_local_alloc(void** local_out, void* handle64_out);
+int bg_comm_open(int rank, int world, const void* handles, void* local, void** comm_out);
+int bg_comm_allreduce_f64(void* comm, const double* in, double* out, int n, void* stream);
+int bg_comm_destroy(void* comm);
+
+/* ---------------------------------------------------------------------------------------------
  * Host utility (no device work): CRC-32C of `n` bytes continuing from `init` (0 = fresh); the 32 result bits
  * are returned in the int.  The checksum of TensorFlow's checkpoint format (checkpoint.py; saver at BigGAN.py:1018,
  * :1255-1284).

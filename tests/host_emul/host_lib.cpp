@@ -644,3 +644,34 @@ extern "C" int bg_attn2_bwd(const void* q_, const void* k_, const void* v_, cons
   for (size_t i = 0; i < av.size(); ++i) gv.p[i] = (float)av[i];
   return BG_OK;
 }
+
+// grouped fully-connected layers (csrc/fc_group.cu): loop stand-ins written from the header
+extern "C" int bg_fc_group_fwd(const bg_fc_group_item* items, int n, int M, int w_dtype, void*) {
+  DTYPE_OK(w_dtype);
+  for (int i = 0; i < n; ++i) {
+    const bg_fc_group_item& s = items[i];
+    if (s.K % 4 != 0 || s.ldw % 4 != 0) { bg_set_error("bg_fc_group_fwd: K = %d, ldw = %d must be multiples of 4", s.K, s.ldw); return BG_ERR_UNSUPPORTED; }
+    In w(s.w, (long)s.N * s.ldw, w_dtype);
+    const float* x = (const float*)s.x; const float* bias = (const float*)s.bias; float* y = (float*)s.y;
+    for (int m = 0; m < M; ++m) for (int c = 0; c < s.N; ++c) {
+      double a = bias ? bias[c] : 0.0;
+      for (int k = 0; k < s.K; ++k) a += (double)x[(long)m * s.K + k] * w.p[(long)c * s.ldw + k];
+      y[(long)m * s.N + c] = (float)a;
+    }
+  }
+  return BG_OK;
+}
+extern "C" int bg_fc_group_bwd(const bg_fc_group_item* items, int n, int M, void*) {
+  for (int i = 0; i < n; ++i) {
+    const bg_fc_group_item& s = items[i];
+    if (s.K % 4 != 0 || s.N % 4 != 0 || s.ldw < s.N) { bg_set_error("bg_fc_group_bwd: K = %d, N = %d must be multiples of 4", s.K, s.N); return BG_ERR_UNSUPPORTED; }
+    const float* x = (const float*)s.x; const float* g = (const float*)s.y; float* dw = (float*)s.w; float* db = (float*)s.bias;
+    for (int k = 0; k < s.K; ++k) for (int c = 0; c < s.N; ++c) {
+      double a = 0;
+      for (int m = 0; m < M; ++m) a += (double)x[(long)m * s.K + k] * g[(long)m * s.N + c];
+      dw[(long)k * s.ldw + c] = (float)a;
+    }
+    if (db) for (int c = 0; c < s.N; ++c) { double a = 0; for (int m = 0; m < M; ++m) a += g[(long)m * s.N + c]; db[c] = (float)a; }
+  }
+  return BG_OK;
+}
