@@ -384,6 +384,41 @@ extern "C" int bg_pad_channels(const void* src, int src_dtype, void* dst, int ds
   return BG_OK;
 }
 
+// channel-slice copy between NHWC tensors of different widths: dst[p * ld_dst + c] = src[p * ld_src + c], c < width
+// (the fused f / g / h attention projection, ops.py:473-479, produces one wide tensor; its slices feed max-pool / attention).
+// 16-byte vectors when width, both strides and both base addresses allow it.
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ src, long ld_src, T* __restrict__ dst, long ld_dst, long npix, int width) {
+  const long n = npix * width;
+  EW_LOOP(i, n) {
+    const long p = i / width;
+    const int c = (int)(i - p * width);
+    dst[p * ld_dst + c] = src[p * ld_src + c];
+  }
+}
+__global__ void copy_channels_vec_kernel(const uint4* __restrict__ src, long ld_src, uint4* __restrict__ dst, long ld_dst, long npix, int width) {
+  const long n = npix * width;                       // everything in 16-byte units
+  EW_LOOP(i, n) {
+    const long p = i / width;
+    const int c = (int)(i - p * width);
+    dst[p * ld_dst + c] = __ldg(src + p * ld_src + c);
+  }
+}
+extern "C" int bg_copy_channels(const void* src, long ld_src, void* dst, long ld_dst, long npix, int width, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int es = dtype == BG_F32 ? 4 : 2, per = 16 / es;
+  if (npix <= 0 || width <= 0) return BG_OK;
+  if (width % per == 0 && ld_src % per == 0 && ld_dst % per == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const long n = npix * (width / per);
+    copy_channels_vec_kernel<<<ew_blocks(n), 256, 0, st>>>((const uint4*)src, ld_src / per, (uint4*)dst, ld_dst / per, npix, width / per);
+  } else {
+    const long n = npix * width;
+    BG_DISPATCH_DTYPE(dtype, T, copy_channels_kernel<T><<<ew_blocks(n), 256, 0, st>>>((const T*)src, ld_src, (T*)dst, ld_dst, npix, width));
+  }
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // im2col of the 3-channel image tensors (bf16, stored zero-padded to Cx channels): the first D convs
 // (ops.py:49-113 with Cin = 3) become a 1x1 tensor-core GEMM with K = kh*kw*3 (padded to Cz) instead

@@ -11,6 +11,7 @@ where the shape is eligible).  Fully-connected layers always run in fp32 (they a
 """
 import contextlib
 import ctypes
+import os
 
 import torch
 
@@ -775,6 +776,85 @@ def _attn2_fused(q, k, v):
     return o
 
 
+def _split_channels(y, widths):
+    """[.., sum(widths)] -> one contiguous tensor per slice (bg_copy_channels); ONE backward entry reassembles the gradient."""
+    Nt = y.shape[-1]
+    npix = y.numel() // Nt
+    dt = bg_dtype(y)
+    outs, c0 = [], 0
+    for w in widths:
+        o = Tensor(empty(list(y.shape[:-1]) + [w], y.dtype), requires_grad=y.requires_grad)
+        call("bg_copy_channels", y.data.view(-1)[c0:], Nt, o.data, w, npix, w, dt, stream())
+        outs.append(o)
+        c0 += w
+    if recording(y):
+        def bw():
+            if all(o.grad is None for o in outs):
+                return
+            g = torch.empty_like(y.data)
+            c1 = 0
+            for o, w in zip(outs, widths):
+                dst = g.view(-1)[c1:]
+                if o.grad is None:
+                    zero = torch.zeros_like(o.data)
+                    call("bg_copy_channels", zero, w, dst, Nt, npix, w, dt, stream())
+                else:
+                    call("bg_copy_channels", o.grad.contiguous(), w, dst, Nt, npix, w, dt, stream())
+                c1 += w
+            accumulate_grad(y, g, own=True)
+        record(bw)
+    return outs
+
+
+def _qkv_projection(x, channels, opt, use_bias):
+    """The f / g / h 1x1 projections of self_attention_2 (ops.py:473-479) as ONE GEMM: the three spectrally normalised weight
+    matrices (separate variables, separate `u`, exactly as conv() creates them) are stacked along the output-channel axis
+    (f and g zero-padded to 16 channels for the tensor cores), x is read once, and the backward pass is one dgrad and one
+    wgrad.  Returns (f, g, h) as contiguous tensors."""
+    cin_x = x.shape[-1]
+    c8, c2 = channels // 8, channels // 2
+    parts = []                                      # (normalised weight, bias or None, real width, padded width)
+    for scope, width, wpad in (('f_conv', c8, round_up(c8, 16)), ('g_conv', c8, round_up(c8, 16)), ('h_conv', c2, c2)):
+        with variable_scope(scope):
+            reg = opt.get("conv", {}).get("regularizer", None) if 'generator' in current_scope_name() else None
+            w = get_variable("kernel", shape=[1, 1, cin_x, width], initializer=weight_init, regularizer=reg)
+            wn = _sn_weight(w, 1, True, x.dtype, pad_c=wpad)
+            bias = get_variable("bias", [width], initializer=constant_initializer(0.0)) if use_bias else None
+        parts.append((wn, bias, width, wpad))
+    Nt = sum(p[3] for p in parts)
+    dev = x.data.device
+    # stacked operands (plumbing: a few KB per phase): native [cin, Nt] for the dgrad, K-major [Nt, cin] for the forward
+    w_nat = torch.cat([wn.data.reshape(cin_x, wp) for wn, _, _, wp in parts], dim=1).reshape(1, 1, cin_x, Nt)
+    w_t = torch.cat([wn.aux["w_t"].reshape(-1).view(wp, cin_x) for wn, _, _, wp in parts], dim=0)
+    wn_all = Tensor(w_nat, requires_grad=any(wn.requires_grad for wn, _, _, _ in parts))
+    wn_all.aux = {"w_t": w_t}
+    bias_all = None
+    if use_bias:
+        bias_all = Tensor(torch.zeros(Nt, dtype=F32, device=dev), requires_grad=any(b.requires_grad for _, b, _, _ in parts))
+        c0 = 0
+        for _, b, width, wp in parts:
+            bias_all.data[c0:c0 + width].copy_(b.data)
+            c0 += wp
+    if recording(wn_all, bias_all):
+        def bw():                                    # un-stack the gradients (runs after the conv's own backward entry)
+            c1 = 0
+            for wn, b, width, wp in parts:
+                if wn.requires_grad and wn_all.grad is not None:
+                    accumulate_grad(wn, wn_all.grad.reshape(cin_x, Nt)[:, c1:c1 + wp].contiguous(), own=True)
+                if b is not None and b.requires_grad and bias_all.grad is not None:
+                    accumulate_grad(b, bias_all.grad[c1:c1 + width].contiguous(), own=True)
+                c1 += wp
+        record(bw)
+    B, H, W, _ = x.shape
+    desc = ConvDesc(B, H, W, cin_x, H, W, Nt, 1, 1, 1, 0, 0, 0, 0, _lib.PAD_ZERO, 0)
+    y = _conv_op(x, wn_all, bias_all, desc)
+    f, g, h = _split_channels(y, [p[3] for p in parts])
+    if parts[0][3] != c8:
+        f.aux = {"c_real": c8}
+        g.aux = {"c_real": c8}
+    return f, g, h
+
+
 def self_attention_2(x, channels, opt, scope='self_attention'):
     """ops.py:467-492 (the live block: 2x2 max-pooled keys/values, C/8 q/k, C/2 v, 1x1 out conv)."""
     with variable_scope(scope):
@@ -782,10 +862,13 @@ def self_attention_2(x, channels, opt, scope='self_attention'):
         fused = (x.dtype == BF16 and not _state["force_simt"] and _lib.lib.bg_has_tensor_core_path() == 1
                  and (channels // 2) % 16 == 0 and channels // 2 <= 128 and channels // 8 <= 64)
         pad = 16 if fused else 0      # q/k channels zero-padded to a multiple of 16 for the tensor cores
-        f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias, _pad_cout_to=pad)
+        if fused and c_real(x) == x.shape[-1] and os.environ.get("BG_NO_QKV_FUSION") != "1":
+            f, g, h = _qkv_projection(x, channels, opt, use_bias)
+        else:
+            f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias, _pad_cout_to=pad)
+            g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias, _pad_cout_to=pad)
+            h = conv(x, channels // 2, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
         f = max_pooling(f)
-        g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias, _pad_cout_to=pad)
-        h = conv(x, channels // 2, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
         h = max_pooling(h)
         if fused:
             o = _attn2_fused(hw_flatten(g), hw_flatten(f), hw_flatten(h))           # [bs, N, C/2]

@@ -194,6 +194,9 @@ int bg_sumpool_fwd(const void* x, void* y, int B, long HW, int C, int relu_first
 int bg_sumpool_bwd(const void* x, const void* dy, void* dx, int B, long HW, int C, int relu_first,
                    int dtype, void* stream);
 int bg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long n, void* stream);
+/* channel-slice copy between NHWC tensors: dst[p*ld_dst + c] = src[p*ld_src + c] for p < npix, c < width (strides in
+ * elements; the pointers already point at the first channel of the slice) */
+int bg_copy_channels(const void* src, long ld_src, void* dst, long ld_dst, long npix, int width, int dtype, void* stream);
 /* [npix, Cs] -> [npix, Cd]: copies min(Cs, Cd) channels, zero-fills the rest (channel pad / slice + cast) */
 int bg_pad_channels(const void* src, int src_dtype, void* dst, int dst_dtype, long npix, int Cs, int Cd,
                     void* stream);

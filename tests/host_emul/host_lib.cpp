@@ -675,3 +675,10 @@ extern "C" int bg_fc_group_bwd(const bg_fc_group_item* items, int n, int M, void
   }
   return BG_OK;
 }
+
+extern "C" int bg_copy_channels(const void* src, long ld_src, void* dst, long ld_dst, long npix, int width, int dtype, void*) {
+  DTYPE_OK(dtype);
+  const size_t es = dtype == BG_F32 ? 4 : 2;
+  for (long p = 0; p < npix; ++p) memcpy((char*)dst + (size_t)p * ld_dst * es, (const char*)src + (size_t)p * ld_src * es, (size_t)width * es);
+  return BG_OK;
+}
