@@ -48,12 +48,21 @@ struct TcFwdParams {
   // halo mode (tc_fwd_halo_kernel): taps that differ only in dx share ONE activation box widened by their dx span
   int ngroups, halo_w;       // tap groups; box width in pixels (128 + span)
   TcGroup groups[TC_MAX_GROUPS];
+  // TMA-store epilogue (layers whose main loop is short): the bf16 tile is staged in shared memory as 16-channel slabs
+  // [128 pixels][32 B] and written with cp.async.bulk.tensor -- full 32-byte sectors in a few bulk requests instead of one
+  // 16-byte store per thread and slab, which saturated the SM's L1 -> crossbar request port (ncu: l1tex__m_l1tex2xbar_req
+  // 65 % busy at 33 % tensor-pipe activity on the 96-channel 3x3 layers)
+  int tma_store;             // 0 = direct stores
+  uint32_t ostage_off;       // staging area, bytes from the 1024-aligned dynamic shared memory base
+  uint32_t ostage_half;      // bytes per epilogue half and set
+  int ostage_sets;           // 1, or 2 when the ring can spare the memory (tile i's bulk stores overlap the staging of tile i + 1)
+  CUtensorMap omap[4];       // per phase: the output sampled with step `ostep` from (oy0, ox0); box (16, bw, bh, bb), no swizzle
 };
 
 // Epilogue warps (8): drain the double-buffered TMEM accumulator of every tile this CTA owns:
 // tcgen05.ld -> bias / residual / activation -> bf16 -> global.  Shared by the plain and the halo kernel.
 __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                int warp, int lane, int ntiles, int ntn, int tiles_pp) {
+                                                int warp, int lane, int ntiles, int ntn, int tiles_pp, uint32_t smem_base) {
     const int ew = warp - 2;                      // 0..7
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = ew >> 2;                     // which half of the BN columns
@@ -107,6 +116,17 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         continue;
       }
       const bool use_res = (p.residual != nullptr) && valid && res_ok;
+      const bool tstore = p.tma_store != 0;
+      // staging slabs are double-buffered per half: tile lt writes set lt & 1 while the bulk stores of tile lt - 1 still read
+      // the other set; the stores of tile lt - 2 (same set) must have finished reading
+      const uint32_t hset = smem_base + p.ostage_off + (uint32_t)(p.ostage_sets * half + (p.ostage_sets == 2 ? (lt & 1) : 0)) * p.ostage_half;
+      const uint32_t hb = hset + (uint32_t)row * 32u;
+      if (tstore) {
+        if ((ew & 3) == 0 && elect_one_sync()) {                            // same elected lane as the one issuing the stores
+          if (p.ostage_sets == 2) tma_store_wait_read1(); else tma_store_wait_read0();
+        }
+        named_bar_sync(1u + (uint32_t)half, 128u);
+      }
       uint4 rb[2][4][2];
       auto load_group = [&](int g, int cg) {
 #pragma unroll
@@ -129,7 +149,7 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
           if (c0 >= cend) break;
           uint32_t r[16];
           tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), r);
-          if (valid) {
+          if (valid || tstore) {
             float v[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
@@ -162,16 +182,32 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
               q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
               q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
             }
-            uint4* op = reinterpret_cast<uint4*>(outb + obase + c0);
-            op[0] = o0;
-            op[1] = o1;
+            if (tstore) {
+              const uint32_t a = hb + (uint32_t)((c0 - cbeg) >> 4) * 4096u;
+              st_shared_v4(a, o0);
+              st_shared_v4(a + 16u, o1);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(outb + obase + c0);
+              op[0] = o0;
+              op[1] = o1;
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+      if (tstore) {
+        fence_proxy_async_smem();
+        named_bar_sync(1u + (uint32_t)half, 128u);
+        if ((ew & 3) == 0 && elect_one_sync()) {
+          uint32_t src = hset;
+          for (int c0 = cbeg; c0 < cend; c0 += 16, src += 4096u) tma_store_4d(&p.omap[phase], src, n0 + c0, j0, i0, b0);
+          tma_store_commit();
+        }
+      }
     }
+    if (p.tma_store && (ew & 3) == 0 && elect_one_sync()) tma_store_wait_all();     // shared memory must outlive the last bulk store
 }
 
 // Persistent: one CTA per SM walks the tile list (n-tile fastest, so concurrently running CTAs share the
@@ -276,7 +312,7 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
       }
     }
   } else {
-    tc_fwd_epilogue(p, tmem_base, tfull_bar, tempty_bar, warp, lane, ntiles, ntn, tiles_pp);
+    tc_fwd_epilogue(p, tmem_base, tfull_bar, tempty_bar, warp, lane, ntiles, ntn, tiles_pp, smem_base);
   }
   tc_fence_before();
   __syncthreads();
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_halo_kernel(const __grid_consta
       }
     }
   } else {
-    tc_fwd_epilogue(p, tmem_base, tfull_bar, tempty_bar, warp, lane, ntiles, ntn, tiles_pp);
+    tc_fwd_epilogue(p, tmem_base, tfull_bar, tempty_bar, warp, lane, ntiles, ntn, tiles_pp, smem_base);
   }
   tc_fence_before();
   __syncthreads();
@@ -432,18 +468,19 @@ static bool tc_device_ok() {
 extern "C" int bg_has_tensor_core_path(void) { return tc_device_ok() ? 1 : 0; }
 
 // activation map [B,H,W,C] bf16 sampled with step s starting at parity (pa,pb); box (64, bw, bh, bb)
-static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int s, int pa, int pb, int bw, int bh, int bb) {
+static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int s, int pa, int pb, int bw, int bh, int bb,
+                        int box_c = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   const int Hs = (H - pa + s - 1) / s, Ws = (W - pb + s - 1) / s;
   if (Hs <= 0 || Ws <= 0) { memset(m, 0, sizeof(*m)); return BG_OK; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)s * C * 2, (cuuint64_t)s * W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
   cuuint32_t es[4] = {1, 1, 1, 1};
   const char* ptr = (const char*)base + ((long)pa * W + pb) * C * 2;
   static int promo = -1;                          // tuning knob: L2 promotion of the activation maps (default 256 B)
   if (promo < 0) { const char* e = getenv("BG_TC_PROMO"); promo = e ? atoi(e) : 3; if (promo < 0 || promo > 3) promo = 3; }
   CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            swz, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { bg_set_error("cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d B=%d s=%d)", (int)r, C, Ws, Hs, B, s); return BG_ERR_CUDA; }
   return BG_OK;
 }
@@ -598,7 +635,29 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   P.ktail = (int)bg_cdiv(g.Ci - (P.nkb - 1) * 64, 16);
   P.BN = BN; P.act = act;
   const int stage_bytes = 16384 + BN * 128;
-  int stages = (200 * 1024) / stage_bytes;       // one persistent CTA per SM: a deep ring that never drains
+  // TMA-store epilogue for layers with a short main loop (see TcFwdParams): the staging slabs come out of the ring's budget
+  int ring_budget = 200 * 1024;
+  {
+    static int ts_env = -1;                       // A/B knob: 0 = never, 1 = automatic (default), 2 = whenever possible
+    if (ts_env < 0) { const char* e = getenv("BG_TC_TMA_STORE"); ts_env = e ? atoi(e) : 1; }
+    int min_taps2 = 1 << 30;
+    for (int ph = 0; ph < g.nphase; ++ph) min_taps2 = min(min_taps2, g.ph[ph].ntaps);
+    const long mma_cycles = (long)min_taps2 * bg_cdiv(g.Ci, 16) * (BN <= 128 ? 60 : BN / 2);   // issue-rate model of one tile
+    const int half_bytes = ((BN / 16 + 1) / 2) * 4096;
+    if (ts_env > 0 && !fold && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < 3L * 16 * BN) &&
+        (ring_budget - 2 * half_bytes) / stage_bytes >= 3) {
+      P.tma_store = 1;
+      P.ostage_half = (uint32_t)half_bytes;
+      P.ostage_sets = (ring_budget - 4 * half_bytes) / stage_bytes >= 4 ? 2 : 1;
+      ring_budget -= 2 * P.ostage_sets * half_bytes;
+      for (int ph = 0; ph < g.nphase; ++ph)
+        if ((rc = make_act_map(&P.omap[ph], out, g.B, g.Ho, g.Wo, g.Co, g.ostep, g.ph[ph].oy0, g.ph[ph].ox0, bw, bh, bb, 16,
+                               CU_TENSOR_MAP_SWIZZLE_NONE)))
+          return rc;
+      for (int ph = g.nphase; ph < 4; ++ph) P.omap[ph] = P.omap[0];
+    }
+  }
+  int stages = ring_budget / stage_bytes;        // one persistent CTA per SM: a deep ring that never drains
   if (stages > 8) stages = 8;
   {
     static int st_env = -1;                       // tuning knob (tools/layer_bench.py)
@@ -633,7 +692,15 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     const char* he = getenv("BG_TC_HALO");        // tuning / A-B knob, read per call
     const int halo_env = he ? atoi(he) : 1;
     const int hstage = TC_HALO_ABYTES + 3 * BN * 128;
-    int hstages = (200 * 1024) / hstage;
+    int hstages = ring_budget / hstage;
+    if (P.tma_store && P.ostage_sets == 2 && hstages < 4 && halo_env) {   // halo stages are larger: give the second set back
+      ring_budget += 2 * (int)P.ostage_half;
+      P.ostage_sets = 1;
+      hstages = ring_budget / hstage;
+      stages = ring_budget / stage_bytes;
+      if (stages > 8) stages = 8;
+      P.stages = stages;
+    }
     if (hstages > 8) hstages = 8;
     if (halo_env && P.ksplit == 1 && g.nphase == 1 && s == 1 && bw == 128 && bh == 1 && bb == 1 && hstages >= 3) {
       TcTap srt[TC_MAX_TAPS];
@@ -659,7 +726,8 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
       if (ok && shared > 0) {
         P.ngroups = ng; P.halo_w = 128 + span; P.stages = hstages;
         if ((rc = make_act_map(&P.amap[0], in, g.B, in_H, in_W, g.Ci, 1, 0, 0, P.halo_w, 1, 1))) return rc;
-        const size_t hsmem = (size_t)hstages * hstage + 1024;
+        P.ostage_off = (uint32_t)(hstages * hstage);
+        const size_t hsmem = (size_t)hstages * hstage + 1024 + (P.tma_store ? 2 * P.ostage_sets * P.ostage_half : 0);
 #define TC_LAUNCH_H(COLS)                                                                                        \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
@@ -683,7 +751,8 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
       }
     }
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  P.ostage_off = (uint32_t)(stages * stage_bytes);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + (P.tma_store ? 2 * P.ostage_sets * P.ostage_half : 0);
 #define TC_LAUNCH(COLS)                                                                                          \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
