@@ -644,6 +644,7 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     for (int ph = 0; ph < g.nphase; ++ph) min_taps2 = min(min_taps2, g.ph[ph].ntaps);
     const long mma_cycles = (long)min_taps2 * bg_cdiv(g.Ci, 16) * (BN <= 128 ? 60 : BN / 2);   // issue-rate model of one tile
     const int half_bytes = ((BN / 16 + 1) / 2) * 4096;
+    // (not in fold mode: boxes starting at negative coordinates are fine for TMA loads but fault on stores -- measured)
     if (ts_env > 0 && !fold && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < 3L * 16 * BN) &&
         (ring_budget - 2 * half_bytes) / stage_bytes >= 3) {
       P.tma_store = 1;
