@@ -249,6 +249,78 @@ extern "C" int bg_maxpool2_bwd(const void* x, const void* dy, void* dx, int B, i
   return BG_OK;
 }
 
+// the same pooling on a CHANNEL SLICE of a wider NHWC tensor (the f / h thirds of the fused attention projection):
+// x points at the first channel of the slice, pixels are ldx elements apart; y is contiguous [B, H/2, W/2, C].
+// backward: dx is a slice too (pixel stride ld_dx); every position of the slice is written.  8 channels (16 B) per thread.
+__global__ void maxpool2_slice_fwd_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ y, int H, int W, int C8, long n) {
+  const int Ho = H / 2, Wo = W / 2;
+  EW_LOOP(i, n) {
+    const int c = (int)(i % C8); long r = i / C8;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho); const long b = r / Ho;
+    const long p00 = (b * H + 2 * oy) * W + 2 * ox;
+    const long off[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      Vec<bf16>::ld(x, off[k] * ldx + (long)c * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = k == 0 ? v[e] : fmaxf(m[e], v[e]);
+    }
+    Vec<bf16>::st(y, i * 8, m);
+  }
+}
+__global__ void maxpool2_slice_bwd_kernel(const bf16* __restrict__ x, long ldx, const bf16* __restrict__ dy, bf16* __restrict__ dx, long ld_dx,
+                                          int H, int W, int C8, long n) {
+  const int Ho = H / 2, Wo = W / 2;
+  EW_LOOP(i, n) {
+    const int c = (int)(i % C8); long r = i / C8;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho); const long b = r / Ho;
+    const long p00 = (b * H + 2 * oy) * W + 2 * ox;
+    const long off[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    float v[4][8], g[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Vec<bf16>::ld(x, off[k] * ldx + (long)c * 8, v[k]);
+    Vec<bf16>::ld(dy, i * 8, g);
+    int best[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {                    // first maximum wins (same tie rule as maxpool2_bwd_kernel)
+      best[e] = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) if (v[k][e] > v[best[e]][e]) best[e] = k;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = best[e] == k ? g[e] : 0.f;
+      Vec<bf16>::st(dx, off[k] * ld_dx + (long)c * 8, o);
+    }
+  }
+}
+static bool slice_vec_ok(const void* p, long ld, int C) { return C % 8 == 0 && ld % 8 == 0 && (((uintptr_t)p) & 15) == 0; }
+extern "C" int bg_maxpool2_slice_fwd(const void* x, long ldx, void* y, int B, int H, int W, int C, int dtype, void* stream) {
+  BG_REQUIRE(H % 2 == 0 && W % 2 == 0, BG_ERR_UNSUPPORTED, "maxpool2: odd size");
+  BG_REQUIRE(dtype == BG_BF16 && slice_vec_ok(x, ldx, C) && slice_vec_ok(y, C, C), BG_ERR_UNSUPPORTED,
+             "maxpool2_slice: bf16, C and strides multiples of 8, 16-byte aligned slices");
+  const long n = (long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_slice_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, H, W, C / 8, n);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+extern "C" int bg_maxpool2_slice_bwd(const void* x, long ldx, const void* dy, void* dx, long ld_dx, int B, int H, int W, int C, int dtype,
+                                     void* stream) {
+  BG_REQUIRE(H % 2 == 0 && W % 2 == 0, BG_ERR_UNSUPPORTED, "maxpool2: odd size");
+  BG_REQUIRE(dtype == BG_BF16 && slice_vec_ok(x, ldx, C) && slice_vec_ok(dx, ld_dx, C) && slice_vec_ok(dy, C, C), BG_ERR_UNSUPPORTED,
+             "maxpool2_slice: bf16, C and strides multiples of 8, 16-byte aligned slices");
+  const long n = (long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_slice_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)dy, (bf16*)dx, ld_dx, H, W, C / 8, n);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
 // softmax over the last axis: one warp per row (n up to a few thousand)
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long rows, int n) {

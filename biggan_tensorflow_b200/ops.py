@@ -776,41 +776,42 @@ def _attn2_fused(q, k, v):
     return o
 
 
-def _split_channels(y, widths):
-    """[.., sum(widths)] -> one contiguous tensor per slice (bg_copy_channels); ONE backward entry reassembles the gradient."""
-    Nt = y.shape[-1]
-    npix = y.numel() // Nt
+def _split_qkv_pooled(y, widths):
+    """y [B,H,W, wf+wg+wh] (the stacked f / g / h projection) -> (maxpool2(f), g, maxpool2(h)) as contiguous tensors: the two
+    pooled thirds are read straight out of y (bg_maxpool2_slice_fwd), g is a channel-slice copy.  ONE backward entry
+    assembles d loss / d y: the pooling backward writes its slice in place, g's gradient is copied into its slice."""
+    B, H, W, Nt = y.shape
+    wf, wg, wh = widths
+    npix = B * H * W
     dt = bg_dtype(y)
-    outs, c0 = [], 0
-    for w in widths:
-        o = Tensor(empty(list(y.shape[:-1]) + [w], y.dtype), requires_grad=y.requires_grad)
-        call("bg_copy_channels", y.data.view(-1)[c0:], Nt, o.data, w, npix, w, dt, stream())
-        outs.append(o)
-        c0 += w
+    flat = y.data.view(-1)
+    f = Tensor(empty([B, H // 2, W // 2, wf], y.dtype), requires_grad=y.requires_grad)
+    g = Tensor(empty([B, H, W, wg], y.dtype), requires_grad=y.requires_grad)
+    h = Tensor(empty([B, H // 2, W // 2, wh], y.dtype), requires_grad=y.requires_grad)
+    call("bg_maxpool2_slice_fwd", flat, Nt, f.data, B, H, W, wf, dt, stream())
+    call("bg_copy_channels", flat[wf:], Nt, g.data, wg, npix, wg, dt, stream())
+    call("bg_maxpool2_slice_fwd", flat[wf + wg:], Nt, h.data, B, H, W, wh, dt, stream())
     if recording(y):
         def bw():
-            if all(o.grad is None for o in outs):
+            if f.grad is None and g.grad is None and h.grad is None:
                 return
-            g = torch.empty_like(y.data)
-            c1 = 0
-            for o, w in zip(outs, widths):
-                dst = g.view(-1)[c1:]
-                if o.grad is None:
-                    zero = torch.zeros_like(o.data)
-                    call("bg_copy_channels", zero, w, dst, Nt, npix, w, dt, stream())
-                else:
-                    call("bg_copy_channels", o.grad.contiguous(), w, dst, Nt, npix, w, dt, stream())
-                c1 += w
-            accumulate_grad(y, g, own=True)
+            gy = torch.empty_like(y.data)
+            gflat = gy.view(-1)
+            for t, c0, w in ((f, 0, wf), (h, wf + wg, wh)):
+                dy = t.grad.contiguous() if t.grad is not None else torch.zeros_like(t.data)
+                call("bg_maxpool2_slice_bwd", flat[c0:], Nt, dy, gflat[c0:], Nt, B, H, W, w, dt, stream())
+            dg = g.grad.contiguous() if g.grad is not None else torch.zeros_like(g.data)
+            call("bg_copy_channels", dg, wg, gflat[wf:], Nt, npix, wg, dt, stream())
+            accumulate_grad(y, gy, own=True)
         record(bw)
-    return outs
+    return f, g, h
 
 
 def _qkv_projection(x, channels, opt, use_bias):
     """The f / g / h 1x1 projections of self_attention_2 (ops.py:473-479) as ONE GEMM: the three spectrally normalised weight
     matrices (separate variables, separate `u`, exactly as conv() creates them) are stacked along the output-channel axis
     (f and g zero-padded to 16 channels for the tensor cores), x is read once, and the backward pass is one dgrad and one
-    wgrad.  Returns (f, g, h) as contiguous tensors."""
+    wgrad.  Returns (maxpool2(f), g, maxpool2(h)) (ops.py:473, :478) as contiguous tensors."""
     cin_x = x.shape[-1]
     c8, c2 = channels // 8, channels // 2
     parts = []                                      # (normalised weight, bias or None, real width, padded width)
@@ -848,7 +849,7 @@ def _qkv_projection(x, channels, opt, use_bias):
     B, H, W, _ = x.shape
     desc = ConvDesc(B, H, W, cin_x, H, W, Nt, 1, 1, 1, 0, 0, 0, 0, _lib.PAD_ZERO, 0)
     y = _conv_op(x, wn_all, bias_all, desc)
-    f, g, h = _split_channels(y, [p[3] for p in parts])
+    f, g, h = _split_qkv_pooled(y, [p[3] for p in parts])
     if parts[0][3] != c8:
         f.aux = {"c_real": c8}
         g.aux = {"c_real": c8}
@@ -863,13 +864,13 @@ def self_attention_2(x, channels, opt, scope='self_attention'):
                  and (channels // 2) % 16 == 0 and channels // 2 <= 128 and channels // 8 <= 64)
         pad = 16 if fused else 0      # q/k channels zero-padded to a multiple of 16 for the tensor cores
         if fused and c_real(x) == x.shape[-1] and os.environ.get("BG_NO_QKV_FUSION") != "1":
-            f, g, h = _qkv_projection(x, channels, opt, use_bias)
+            f, g, h = _qkv_projection(x, channels, opt, use_bias)          # f, h already max-pooled
         else:
             f = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='f_conv', use_bias=use_bias, _pad_cout_to=pad)
             g = conv(x, channels // 8, kernel=1, stride=1, opt=opt, scope='g_conv', use_bias=use_bias, _pad_cout_to=pad)
             h = conv(x, channels // 2, kernel=1, stride=1, opt=opt, scope='h_conv', use_bias=use_bias)
-        f = max_pooling(f)
-        h = max_pooling(h)
+            f = max_pooling(f)
+            h = max_pooling(h)
         if fused:
             o = _attn2_fused(hw_flatten(g), hw_flatten(f), hw_flatten(h))           # [bs, N, C/2]
             o = reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2])
@@ -881,8 +882,63 @@ def self_attention_2(x, channels, opt, scope='self_attention'):
             o = matmul(beta, cast(hw_flatten(h), F32))                      # [bs, N, C/2]
             o = cast(reshape(o, [x.shape[0], x.shape[1], x.shape[2], channels // 2]), x.dtype)
         gamma = get_variable("gamma", [1], initializer=constant_initializer(0.0))
+        if fused and os.environ.get("BG_NO_GAMMA_FOLD") != "1":
+            return _attn_out_gamma_folded(o, x, gamma, channels, opt, use_bias)
         o = conv(o, channels, kernel=1, stride=1, opt=opt, scope='attn_conv', use_bias=use_bias)
         return _gamma_residual(gamma, o, x)
+
+
+def _attn_out_gamma_folded(o, x, gamma, channels, opt, use_bias):
+    """x + gamma * attn_conv(o) (ops.py:486-490) as ONE conv: the scalar gamma is folded into the (tiny) normalised 1x1 weight
+    and bias, x rides in the conv epilogue as the residual.  The three elementwise passes of `gamma * o + x`, the two of its
+    backward and the full-size dot product for d gamma disappear; d gamma = <d(gamma W), W> + <d(gamma b), b> is taken on the
+    C/2 x C weight instead."""
+    cin = o.shape[-1]
+    with variable_scope('attn_conv'):
+        reg = opt.get("conv", {}).get("regularizer", None) if 'generator' in current_scope_name() else None
+        w = get_variable("kernel", shape=[1, 1, cin, channels], initializer=weight_init, regularizer=reg)
+        wn = _sn_weight(w, 1, True, o.dtype)
+        bias = get_variable("bias", [channels], initializer=constant_initializer(0.0)) if use_bias else None
+    dtw = bg_dtype(wn)
+    nW = wn.numel()
+    ws = Tensor(torch.empty_like(wn.data), requires_grad=wn.requires_grad or gamma.requires_grad)
+    ws_t = torch.empty_like(wn.aux["w_t"])
+    call("bg_axpby", wn.data, None, gamma.data, 0.0, 0.0, ws.data, nW, dtw, stream())
+    call("bg_axpby", wn.aux["w_t"], None, gamma.data, 0.0, 0.0, ws_t, nW, dtw, stream())
+    ws.aux = {"w_t": ws_t}
+    bs = None
+    if bias is not None:
+        bs = Tensor(empty([channels], F32), requires_grad=bias.requires_grad or gamma.requires_grad)
+        call("bg_axpby", bias.data, None, gamma.data, 0.0, 0.0, bs.data, channels, _lib.BG_F32, stream())
+    if recording(ws, bs):
+        def bw():                                    # runs after the conv's backward entry: un-fold gamma
+            dws = ws.grad                            # fp32, d loss / d (gamma W)
+            dbs = bs.grad if bs is not None else None
+            if gamma.requires_grad:
+                dg = torch.zeros(1, dtype=F32, device=gamma.data.device)
+                for d, v, n in ((dws, wn.data, nW), (dbs, bias.data if bias is not None else None, channels)):
+                    if d is None or v is None:
+                        continue
+                    v32 = v if v.dtype == F32 else empty(list(v.shape), F32)
+                    if v.dtype != F32:
+                        call("bg_cast", v, bg_dtype(v), v32, _lib.BG_F32, n, stream())
+                    part = empty([1], F32)
+                    wsd = workspace(query("bg_dot_workspace_bytes", n))
+                    call("bg_dot", d, v32, part, n, _lib.BG_F32, wsd, wsd.numel(), stream())
+                    call("bg_add", dg, part, dg, 1, _lib.BG_F32, stream())
+                accumulate_grad(gamma, dg, own=True)
+            if wn.requires_grad and dws is not None:
+                g = torch.empty_like(dws)
+                call("bg_axpby", dws, None, gamma.data, 0.0, 0.0, g, nW, _lib.BG_F32, stream())
+                accumulate_grad(wn, g, own=True)
+            if bias is not None and bias.requires_grad and dbs is not None:
+                g = torch.empty_like(dbs)
+                call("bg_axpby", dbs, None, gamma.data, 0.0, 0.0, g, channels, _lib.BG_F32, stream())
+                accumulate_grad(bias, g, own=True)
+        record(bw)
+    B, H, W, _ = o.shape
+    desc = ConvDesc(B, H, W, cin, H, W, channels, 1, 1, 1, 0, 0, 0, 0, _lib.PAD_ZERO, 0)
+    return _conv_op(o, ws, bs, desc, residual=x)
 
 
 ##################################################################################

@@ -194,6 +194,12 @@ int bg_sumpool_fwd(const void* x, void* y, int B, long HW, int C, int relu_first
 int bg_sumpool_bwd(const void* x, const void* dy, void* dx, int B, long HW, int C, int relu_first,
                    int dtype, void* stream);
 int bg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long n, void* stream);
+/* 2x2/2 max pooling (ops.py:508-510) of a CHANNEL SLICE of a wider NHWC tensor: x points at the slice's first channel,
+ * pixels are ldx elements apart; y / dy are contiguous [B,H/2,W/2,C]; dx is a slice with pixel stride ld_dx, every position
+ * of which is written.  bf16, C and strides multiples of 8. */
+int bg_maxpool2_slice_fwd(const void* x, long ldx, void* y, int B, int H, int W, int C, int dtype, void* stream);
+int bg_maxpool2_slice_bwd(const void* x, long ldx, const void* dy, void* dx, long ld_dx, int B, int H, int W, int C,
+                          int dtype, void* stream);
 /* channel-slice copy between NHWC tensors: dst[p*ld_dst + c] = src[p*ld_src + c] for p < npix, c < width (strides in
  * elements; the pointers already point at the first channel of the slice) */
 int bg_copy_channels(const void* src, long ld_src, void* dst, long ld_dst, long npix, int width, int dtype, void* stream);

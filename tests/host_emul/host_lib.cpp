@@ -682,3 +682,33 @@ extern "C" int bg_copy_channels(const void* src, long ld_src, void* dst, long ld
   for (long p = 0; p < npix; ++p) memcpy((char*)dst + (size_t)p * ld_dst * es, (const char*)src + (size_t)p * ld_src * es, (size_t)width * es);
   return BG_OK;
 }
+
+// max pooling on a channel slice of a wider NHWC tensor (bf16 only, as the kernels)
+extern "C" int bg_maxpool2_slice_fwd(const void* x_, long ldx, void* y_, int B, int H, int W, int C, int dtype, void*) {
+  if (dtype != BG_BF16 || C % 8 || ldx % 8 || H % 2 || W % 2) { bg_set_error("maxpool2_slice: unsupported"); return BG_ERR_UNSUPPORTED; }
+  const bf16* x = (const bf16*)x_; bf16* y = (bf16*)y_;
+  const int Ho = H / 2, Wo = W / 2;
+  for (int b = 0; b < B; ++b) for (int oy = 0; oy < Ho; ++oy) for (int ox = 0; ox < Wo; ++ox) for (int c = 0; c < C; ++c) {
+    const long p00 = ((long)b * H + 2 * oy) * W + 2 * ox;
+    const long off[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    float m = bg_emul_bf16_to_float(x[off[0] * ldx + c]);
+    for (int k = 1; k < 4; ++k) { const float v = bg_emul_bf16_to_float(x[off[k] * ldx + c]); if (v > m) m = v; }
+    y[(((long)b * Ho + oy) * Wo + ox) * C + c] = bg_emul_float_to_bf16(m);
+  }
+  return BG_OK;
+}
+extern "C" int bg_maxpool2_slice_bwd(const void* x_, long ldx, const void* dy_, void* dx_, long ld_dx, int B, int H, int W, int C, int dtype, void*) {
+  if (dtype != BG_BF16 || C % 8 || ldx % 8 || ld_dx % 8 || H % 2 || W % 2) { bg_set_error("maxpool2_slice: unsupported"); return BG_ERR_UNSUPPORTED; }
+  const bf16* x = (const bf16*)x_; const bf16* dy = (const bf16*)dy_; bf16* dx = (bf16*)dx_;
+  const int Ho = H / 2, Wo = W / 2;
+  for (int b = 0; b < B; ++b) for (int oy = 0; oy < Ho; ++oy) for (int ox = 0; ox < Wo; ++ox) for (int c = 0; c < C; ++c) {
+    const long p00 = ((long)b * H + 2 * oy) * W + 2 * ox;
+    const long off[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    int best = 0;
+    for (int k = 1; k < 4; ++k)
+      if (bg_emul_bf16_to_float(x[off[k] * ldx + c]) > bg_emul_bf16_to_float(x[off[best] * ldx + c])) best = k;
+    const bf16 g = dy[(((long)b * Ho + oy) * Wo + ox) * C + c];
+    for (int k = 0; k < 4; ++k) dx[off[k] * ld_dx + c] = k == best ? g : bg_emul_float_to_bf16(0.f);
+  }
+  return BG_OK;
+}
