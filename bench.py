@@ -140,7 +140,10 @@ def workload_config(args, world):
                         "da_policy='%s' (BASELINE config %d)" % (c["img_size"], c["ch"], args.batch or c["batch_size"], c["n_labels"],
                                                                  c.get("da_policy", ""), args.config),
             "global_batch": args.batch or c["batch_size"], "per_gpu_batch": (args.batch or c["batch_size"]) // world,
-            "parallelism": "dp%d" % world,
+            "parallelism": "dp%d" % world + ("" if world == 1 else " (%s, %s, BN statistics %s)" % (
+                "all-reduce + replicated Adam" if args.no_shard_optimizer else "reduce-scatter + sharded Adam + all-gather",
+                "no overlap" if args.no_overlap else "D update overlapped with the G-phase generator forward",
+                "over NCCL" if os.environ.get("BG_BN_SYNC", "p2p") != "p2p" else "over NVLink peer memory")),
             "l2": "no explicit flush: every step streams several GB of activations/weights, far larger than the 126 MB L2"}
 
 
@@ -287,8 +290,14 @@ def main():
     ach = c_fl / (c_ms * 1e-3) / 1e12 if c_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"] if dtype == torch.bfloat16 else 75.0
     step_flops = {0: 0.87e9, 1: 212.7e9, 2: 212.7e9, 3: 714.0e9, 4: 603.6e9}[args.config] * B
-    roof = {"bound": "tensor", "kernel": "tc_fwd_kernel/tc_wgrad_kernel (conv, deconv, dgrad, wgrad implicit GEMMs)",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
+    if os.path.exists(tp) and args.config == 1 and dtype == torch.bfloat16 and world == 1 and not args.batch:
+        t = json.load(open(tp))      # dram__bytes_read.sum + dram__bytes_write.sum of the same kernels, per launch, one ncu capture
+        traffic, traffic_src = t["dram_bytes_per_launch"], "%s (ncu, %d launches of one iteration)" % (t["source"], t["launches_per_step"])
+    roof = {"bound": "tensor", "kernel": "tc_fwd_kernel/tc_fwd_halo_kernel/tc_wgrad_kernel (conv, deconv, dgrad, wgrad implicit GEMMs)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch (DRAM)",
+            "traffic_source": traffic_src,
             "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
             "launches_per_step": c_calls, "avg_launch_ms": c_ms / max(c_calls, 1), "share_of_step": c_ms / max(tot_ms, 1e-9),
             "how": "CUDA events around every conv C-ABI call of one extra step on the launch stream; achieved = sum of "
