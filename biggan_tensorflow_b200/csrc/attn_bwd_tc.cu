@@ -2,7 +2,10 @@
 // P = exp(S - lse) tile by tile (nothing of size [N, N/4] is ever stored), with
 //   dP = dO V^T,  dS = P o (dP - delta),  delta_i = dO_i . O_i,
 //   dV = P^T dO,  dK = dS^T Q   (kernel attn_bwd_dkdv: one CTA per (image, 128 keys), loop over query tiles)
-//   dQ = dS K                   (kernel attn_bwd_dq:   one CTA per (image, 128 queries), loop over key blocks)
+//   dQ = dS K                   round 2: the SAME kernel also forms this key block's contribution dS K for every query tile
+//                               (one more MMA group on the dS tile it already holds; fp32 partial [key block][B, Nq, dq] in the
+//                               workspace) and attn_dq_reduce_kernel sums the <= 8 partials in fixed order -- the second kernel
+//                               that recomputed S, P and dP for dQ (attn_bwd_dq, kept for callers without workspace) is not run.
 // Every operand transposition is done by the UMMA descriptors: the same 128B-swizzled shared-memory tile
 // [rows][64 ch] is read K-major (contract over channels) or MN-major (contract over rows).
 // Deterministic: no atomics; each output element is produced by exactly one CTA.
@@ -19,6 +22,7 @@ struct AttnBwdParams {
   bf16* dq_out;
   bf16* dk_out;
   bf16* dv_out;
+  float* dq_part;            // [nkb][B][Nq][dq] fp32 partial dQ (NULL: the dkdv kernel does not form dQ)
 };
 
 // p / ds for 16 consecutive keys of one query row -> bf16 K-major SWIZZLE_128B tiles
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tS = tmem, tdP = tmem + 128u, tdV = tmem + 256u, tdK = tmem + 384u;
+  const uint32_t tS = tmem, tdP = tmem + 128u, tdV = tmem + 256u, tdK = tmem + 384u, tdQ = tmem + 448u;   // dq <= 64 columns each
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -98,6 +102,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
     if (elect_one_sync()) {
       const uint32_t idesc_dv = umma_idesc_bf16(128, p.dv, 1, 1);
       const uint32_t idesc_dk = umma_idesc_bf16(128, p.dq, 1, 1);
+      const uint32_t idesc_dq = umma_idesc_bf16(128, p.dq, 0, 1);
+      const bool want_dq = p.dq_part != nullptr;
       mbar_wait(smem_u32(&kv_full), 0);
       for (int i = 0; i <= p.nqt; ++i) {
         if (i < p.nqt) {
@@ -122,6 +128,14 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
             const uint64_t bQ = umma_desc_mnmajor_sw128(Qs + (uint32_t)s * 16384u + (uint32_t)k * 2048u, 16384u, 1024u);
             umma_bf16(tdK, adS, bQ, idesc_dk, (pi | k) != 0 ? 1u : 0u);
           }
+          if (want_dq) {
+#pragma unroll
+            for (int k = 0; k < AB_T / 16; ++k) {    // dQ(tile pi) contribution of this key block: contract over its 128 keys
+              const uint64_t adS = umma_desc_kmajor_sw128(dSs + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
+              const uint64_t bK = umma_desc_mnmajor_sw128(Ks + (uint32_t)k * 2048u, 16384u, 1024u);
+              umma_bf16(tdQ, adS, bK, idesc_dq, k != 0 ? 1u : 0u);
+            }
+          }
           umma_commit(smem_u32(&pds_empty));
           umma_commit(smem_u32(&qd_empty[s]));
         }
@@ -143,6 +157,22 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
       mbar_wait(smem_u32(&s_full), (uint32_t)(i & 1));
       tc_fence_after();
       mbar_wait(smem_u32(&pds_empty), (uint32_t)((i & 1) ^ 1));
+      if (p.dq_part != nullptr && i > 0) {           // the MMAs of tile i - 1 are complete: its dQ partial leaves TMEM before
+        tc_fence_after();                            // tile i's dS (and with it the next dQ MMA group) is released
+        const int qp = (i - 1) * AB_T + row;
+        const int qsplit = ((p.dq / 16 + 1) / 2) * 16;
+        for (int c0 = half ? qsplit : 0; c0 < (half ? p.dq : qsplit); c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(tdQ + lane_base + (uint32_t)c0, r);
+          if (qp < p.Nq) {
+            float4* o = reinterpret_cast<float4*>(p.dq_part + (((long)j * p.B + b) * p.Nq + qp) * p.dq + c0);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+          }
+        }
+        tc_fence_before();
+      }
       for (int cc = 0; cc < 64; cc += 16) {
         const int c0 = half * 64 + cc;
         uint32_t rs[16], rp[16], pk[8], dk[8];
@@ -172,6 +202,20 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
     }
     mbar_wait(smem_u32(&acc_full), 0);
     tc_fence_after();
+    if (p.dq_part != nullptr) {                      // dQ partial of the last query tile
+      const int qp = (p.nqt - 1) * AB_T + row;
+      const int qsplit = ((p.dq / 16 + 1) / 2) * 16;
+      for (int c0 = half ? qsplit : 0; c0 < (half ? p.dq : qsplit); c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(tdQ + lane_base + (uint32_t)c0, r);
+        if (qp < p.Nq) {
+          float4* o = reinterpret_cast<float4*>(p.dq_part + (((long)j * p.B + b) * p.Nq + qp) * p.dq + c0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+        }
+      }
+    }
     const int key = j * AB_T + row;          // accumulator rows are keys
     const int vsplit = ((p.dv / 16 + 1) / 2) * 16, ksplit = ((p.dq / 16 + 1) / 2) * 16;
     for (int c0 = half ? vsplit : 0; c0 < (half ? p.dv : vsplit); c0 += 16) {
@@ -313,6 +357,21 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dq_kernel(const __grid_consta
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// dQ = sum over key blocks of the fp32 partials (fixed order) -> bf16; 8 values per thread
+__global__ void __launch_bounds__(256) attn_dq_reduce_kernel(const float* __restrict__ part, long stride, int nkb, bf16* __restrict__ dq, long n8) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    for (int z = 0; z < nkb; ++z) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(part + (long)z * stride + i * 8));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(part + (long)z * stride + i * 8 + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += c.x; v[5] += c.y; v[6] += c.z; v[7] += c.w;
+    }
+    Vec<bf16>::st(dq, i * 8, v);
+  }
+}
+
 // delta[b,i] = sum_c dO[b,i,c] * O[b,i,c]
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, long rows, int dv) {
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -325,8 +384,13 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
   delta[r] = s;
 }
 
+extern "C" size_t bg_attn2_bwd_workspace_bytes(int B, int Nq, int Nk, int dq) {
+  return (size_t)bg_cdiv(Nk, AB_T) * B * Nq * dq * sizeof(float) + 256;
+}
+
 extern "C" int bg_attn2_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse, float* delta,
-                            void* dq_out, void* dk_out, void* dv_out, int B, int Nq, int Nk, int dq, int dv, void* stream) {
+                            void* dq_out, void* dk_out, void* dv_out, int B, int Nq, int Nk, int dq, int dv, void* ws, size_t ws_bytes,
+                            void* stream) {
   BG_REQUIRE(bg_has_tensor_core_path(), BG_ERR_UNSUPPORTED, "attn2: tensor-core path unavailable on this device");
   BG_REQUIRE(dq % 16 == 0 && dq >= 16 && dq <= 64, BG_ERR_UNSUPPORTED, "attn2: dq=%d must be 16..64, multiple of 16", dq);
   BG_REQUIRE(dv % 16 == 0 && dv >= 16 && dv <= 128, BG_ERR_UNSUPPORTED, "attn2 backward: dv=%d must be 16..128, multiple of 16", dv);
@@ -345,6 +409,11 @@ extern "C" int bg_attn2_bwd(const void* q, const void* k, const void* v, const v
   P.B = B; P.Nq = Nq; P.Nk = Nk; P.dq = dq; P.dv = dv;
   P.nqt = (int)bg_cdiv(Nq, AB_T); P.nkb = (int)bg_cdiv(Nk, AB_T); P.nvblk = (dv + 63) / 64;
   P.lse = lse; P.delta = delta; P.dq_out = (bf16*)dq_out; P.dk_out = (bf16*)dk_out; P.dv_out = (bf16*)dv_out;
+  // with workspace: the dkdv kernel also writes this key block's dQ contribution and a reduce pass replaces the dq kernel
+  const long part_stride = (long)B * Nq * dq;
+  const bool fuse_dq = ws != nullptr && ws_bytes >= (size_t)P.nkb * part_stride * sizeof(float) && (((uintptr_t)ws) & 15) == 0 &&
+                       (part_stride % 8) == 0;
+  P.dq_part = fuse_dq ? (float*)ws : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     BG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -356,7 +425,13 @@ extern "C" int bg_attn2_bwd(const void* q, const void* k, const void* v, const v
   const size_t smem_q = 16384 + vb + 2 * 16384 + 2 * vb + 32768 + 1024;
   attn_bwd_dkdv_kernel<<<dim3((unsigned)P.nkb, (unsigned)B), 320, smem_kv, st>>>(P);
   BG_LAUNCH_CHECK();
-  attn_bwd_dq_kernel<<<dim3((unsigned)P.nqt, (unsigned)B), 320, smem_q, st>>>(P);
+  if (fuse_dq) {
+    const long n8 = part_stride / 8;
+    const int blocks = (int)min(bg_cdiv(n8, 256), (long)bg_num_sms() * 16);
+    attn_dq_reduce_kernel<<<blocks, 256, 0, st>>>(P.dq_part, part_stride, P.nkb, (bf16*)dq_out, n8);
+  } else {
+    attn_bwd_dq_kernel<<<dim3((unsigned)P.nqt, (unsigned)B), 320, smem_q, st>>>(P);
+  }
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

@@ -767,8 +767,10 @@ def _attn2_fused(q, k, v):
                 return
             gq, gk, gv = torch.empty_like(q.data), torch.empty_like(k.data), torch.empty_like(v.data)
             delta = empty([Bn, Nq], F32)
+            nb = 0 if os.environ.get("BG_ATTN_BWD_TWO_KERNELS") == "1" else query("bg_attn2_bwd_workspace_bytes", Bn, Nq, Nk, dq)
+            ws = workspace(nb) if nb else None
             call("bg_attn2_bwd", q.data, k.data, v.data, o.data, o.grad.contiguous(), lse, delta, gq, gk, gv, Bn, Nq, Nk, dq, dv,
-                 stream(), flops=2.0 * Bn * Nq * Nk * (3 * dq + 4 * dv), tag="attn2_bwd")
+                 ws, ws.numel() if nb else 0, stream(), flops=2.0 * Bn * Nq * Nk * (3 * dq + 4 * dv), tag="attn2_bwd")
             for t, g in ((q, gq), (k, gk), (v, gv)):
                 if t.requires_grad:
                     accumulate_grad(t, g, own=True)

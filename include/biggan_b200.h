@@ -164,10 +164,13 @@ int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const floa
 int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk,
                  int dq, int dv, void* stream);
 /* backward of bg_attn2_fwd: d_o [B,Nq,dv] -> dq [B,Nq,dq], dk [B,Nk,dq], dv [B,Nk,dv] (bf16);
- * delta [B,Nq] fp32 scratch (row-wise <d_o, o>).  Recomputes the probabilities from lse. */
+ * delta [B,Nq] fp32 scratch (row-wise <d_o, o>).  Recomputes the probabilities from lse.
+ * ws (bg_attn2_bwd_workspace_bytes, may be NULL): fp32 per-key-block partials of dQ -- with it the dK/dV kernel also
+ * forms dQ and a fixed-order reduce finishes it; without it a second kernel recomputes the probabilities for dQ. */
+size_t bg_attn2_bwd_workspace_bytes(int B, int Nq, int Nk, int dq);
 int bg_attn2_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                  const float* lse, float* delta, void* dq_out, void* dk_out, void* dv_out, int B, int Nq,
-                 int Nk, int dq, int dv, void* stream);
+                 int Nk, int dq, int dv, void* ws, size_t ws_bytes, void* stream);
 int bg_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 int bg_maxpool2_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype,
                     void* stream);

@@ -618,8 +618,9 @@ extern "C" int bg_attn2_fwd(const void* q_, const void* k_, const void* v_, void
   }
   return BG_OK;
 }
+extern "C" size_t bg_attn2_bwd_workspace_bytes(int, int, int, int) { return 16; }
 extern "C" int bg_attn2_bwd(const void* q_, const void* k_, const void* v_, const void* o_, const void* do_, const float* lse, float* delta, void* dq_,
-                            void* dk_, void* dv_, int B, int Nq, int Nk, int dq, int dv, void*) {
+                            void* dk_, void* dv_, int B, int Nq, int Nk, int dq, int dv, void*, size_t, void*) {
   In q(q_, (long)B * Nq * dq, BG_BF16), k(k_, (long)B * Nk * dq, BG_BF16), v(v_, (long)B * Nk * dv, BG_BF16), o(o_, (long)B * Nq * dv, BG_BF16),
      go(do_, (long)B * Nq * dv, BG_BF16);
   Out gq(dq_, (long)B * Nq * dq, BG_BF16), gk(dk_, (long)B * Nk * dq, BG_BF16), gv(dv_, (long)B * Nk * dv, BG_BF16);

@@ -32,10 +32,13 @@ def test_attn2_forward(B, Nq, Nk, dq, dv):
     assert_close(o.float().cpu().numpy(), ro.numpy(), 2e-2, "o")
 
 
+@pytest.mark.parametrize("fused_dq", [True, False], ids=["dq-in-dkdv", "two-kernels"])
 @pytest.mark.parametrize("B,Nq,Nk,dq,dv", [(2, 256, 64, 16, 16), (2, 1024, 256, 32, 96), (1, 4096, 1024, 32, 96),
                                            (2, 4096, 1024, 16, 48), (1, 64, 16, 16, 32), (2, 320, 80, 32, 64), (1, 512, 128, 64, 128)])
-def test_attn2_backward(B, Nq, Nk, dq, dv):
-    from biggan_tensorflow_b200._lib import call
+def test_attn2_backward(B, Nq, Nk, dq, dv, fused_dq):
+    """fused_dq: with the workspace the dK/dV kernel also forms dQ (per-key-block partials + fixed-order reduce); without
+    it the separate dQ kernel runs.  Both against the float64 reference."""
+    from biggan_tensorflow_b200._lib import call, query
     from biggan_tensorflow_b200.tensor import stream
     rng = np.random.default_rng(1)
     mk = lambda *sh: torch.from_numpy(rng.standard_normal(sh).astype(np.float32)).cuda().bfloat16()
@@ -45,7 +48,8 @@ def test_attn2_backward(B, Nq, Nk, dq, dv):
     call("bg_attn2_fwd", q, k, v, o, lse, B, Nq, Nk, dq, dv, stream())
     gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     delta = torch.empty(B, Nq, dtype=torch.float32, device="cuda")
-    call("bg_attn2_bwd", q, k, v, o, do, lse, delta, gq, gk, gv, B, Nq, Nk, dq, dv, stream())
+    ws = torch.empty(int(query("bg_attn2_bwd_workspace_bytes", B, Nq, Nk, dq)), dtype=torch.uint8, device="cuda") if fused_dq else None
+    call("bg_attn2_bwd", q, k, v, o, do, lse, delta, gq, gk, gv, B, Nq, Nk, dq, dv, ws, ws.numel() if fused_dq else 0, stream())
     torch.cuda.synchronize()
     rq, rk, rv = [t.double().cpu().requires_grad_(True) for t in (q, k, v)]
     ro, _ = _ref(rq, rk, rv)
