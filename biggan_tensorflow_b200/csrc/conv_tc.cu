@@ -52,6 +52,12 @@ struct TcFwdParams {
   // [128 pixels][32 B] and written with cp.async.bulk.tensor -- full 32-byte sectors in a few bulk requests instead of one
   // 16-byte store per thread and slab, which saturated the SM's L1 -> crossbar request port (ncu: l1tex__m_l1tex2xbar_req
   // 65 % busy at 33 % tensor-pipe activity on the 96-channel 3x3 layers)
+  // resident-weights mode (plain kernel, Co == BN, all weight tiles fit): the (tap, k-block) weight tiles are loaded ONCE per
+  // persistent CTA into their own shared-memory region; ring stages then carry activations only.  For the layers with few
+  // output channels / small K (1x1 projections, the RGB layers) the weights were 40-75 % of every tile's ingest.
+  int resident_b;
+  uint32_t bres_off;         // resident weight region, bytes from the 1024-aligned dynamic shared memory base
+  int nwidx;                 // weight tiles per k-block in the region (max widx + 1)
   int tma_store;             // 0 = direct stores
   uint32_t ostage_off;       // staging area, bytes from the 1024-aligned dynamic shared memory base
   uint32_t ostage_half;      // bytes per epilogue half and set
@@ -220,11 +226,13 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
   __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = 16384u + (uint32_t)p.BN * 128u;
+  const uint32_t wtile = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = p.resident_b ? 16384u : 16384u + wtile;
   const int tiles_pp = p.tw * p.th * p.tb;
   const int ntn = p.Co / p.BN;
   const int ntiles = tiles_pp * p.nphase * ntn;
@@ -234,6 +242,7 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
     tma_prefetch_desc(&p.bmap);
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 8); }
+    mbar_init(smem_u32(&bres_bar), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
@@ -249,6 +258,13 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, par = 1, sa = smem_base;
       const int S = p.ksplit;
+      if (p.resident_b) {                            // every weight tile of the layer, once per CTA
+        const uint32_t bb = smem_u32(&bres_bar);
+        mbar_expect_tx(bb, (uint32_t)(p.nwidx * p.nkb) * wtile);
+        uint32_t dst = smem_base + p.bres_off;
+        for (int w = 0; w < p.nwidx; ++w)
+          for (int kb = 0; kb < p.nkb; ++kb, dst += wtile) tma_load_3d(dst, &p.bmap, bb, kb * 64, 0, w);
+      }
       for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x) {
         const int tile = wi / S, split = wi - tile * S;
         const int nt = tile % ntn; int t = tile / ntn;
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
           const uint32_t fb = full0 + s * 8u;
           mbar_expect_tx(fb, stage_bytes);
           tma_load_4d(sa, &p.amap[tap.map], fb, kb * 64, j0 + tap.dx, i0 + tap.dy, b0);
-          tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
+          if (!p.resident_b) tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
           if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
           if (++kb == p.nkb) { kb = 0; ++tp; if (li + 1 < hi) tap = p.taps[phase][tp]; }
         }
@@ -281,6 +297,9 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
       uint32_t s = 0, par = 0, a_lo = a_lo0;
       int lt = 0;
       const int S = p.ksplit;
+      const uint32_t res = (uint32_t)p.resident_b;
+      const uint32_t bres_lo = umma_desc_lo(smem_base + p.bres_off, 16), wtile_q = wtile >> 4;
+      if (res) { mbar_wait(smem_u32(&bres_bar), 0); tc_fence_after(); }
       for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
         const int tile = wi / S, split = wi - tile * S;
         const int phase = (tile / ntn) / tiles_pp;
@@ -290,14 +309,15 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
         mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
-        int kb = lo % p.nkb;
+        int kb = lo % p.nkb, tp = lo / p.nkb;
         uint32_t acc = 0u;
+        uint32_t bw_lo = res ? bres_lo + (uint32_t)(p.taps[phase][tp].widx * p.nkb + kb) * wtile_q : 0u;
         for (int li = lo; li < hi; ++li) {
           mbar_wait(full0 + s * 8u, par);
           tc_fence_after();
           const int nk = (kb == p.nkb - 1) ? p.ktail : 4;
           if (!dry) {
-            const uint32_t b_lo = a_lo + 1024u;          // weight tile: 16 KB behind the activation tile
+            const uint32_t b_lo = res ? bw_lo : a_lo + 1024u;     // weight tile: resident region, or 16 KB behind the activation tile
             umma_bf16_w(tacc, a_lo, UMMA_DESC_HI_KMAJOR_SW128, b_lo, UMMA_DESC_HI_KMAJOR_SW128, idesc, acc);
             acc = 1u;
             if (nk > 1) umma_bf16_w(tacc, a_lo + 2u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 2u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
@@ -305,7 +325,10 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
             if (nk > 3) umma_bf16_w(tacc, a_lo + 6u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 6u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
           }
           umma_commit(empty0 + s * 8u);
-          if (++kb == p.nkb) kb = 0;
+          if (++kb == p.nkb) {
+            kb = 0; ++tp;
+            if (res && li + 1 < hi) bw_lo = bres_lo + (uint32_t)(p.taps[phase][tp].widx * p.nkb) * wtile_q;
+          } else bw_lo += wtile_q;
           if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; a_lo = a_lo0; } else a_lo += stage_q;
         }
         umma_commit(smem_u32(&tfull_bar[buf]));
@@ -634,9 +657,25 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   P.nkb = (int)bg_cdiv(g.Ci, 64);
   P.ktail = (int)bg_cdiv(g.Ci - (P.nkb - 1) * 64, 16);
   P.BN = BN; P.act = act;
-  const int stage_bytes = 16384 + BN * 128;
-  // TMA-store epilogue for layers with a short main loop (see TcFwdParams): the staging slabs come out of the ring's budget
   int ring_budget = 200 * 1024;
+  // resident-weights mode (see TcFwdParams): one n-tile, no split-K, not a halo layer, all weight tiles fit beside >= 4 stages
+  int bres_bytes = 0;
+  {
+    static int rb_env = -1;                       // A/B knob
+    if (rb_env < 0) { const char* e = getenv("BG_TC_RESIDENT_B"); rb_env = e ? atoi(e) : 1; }
+    const char* he0 = getenv("BG_TC_HALO");
+    const bool halo_possible = (he0 ? atoi(he0) : 1) && g.nphase == 1 && s == 1 && bw == 128 && bh == 1 && bb == 1 && g.ph[0].ntaps > 1;
+    const int region = (maxw + 1) * P.nkb * BN * 128;
+    if (rb_env && g.Co == BN && pl.ksplit <= 1 && !halo_possible && !box_override && region <= 112 * 1024 &&
+        (ring_budget - region) / 16384 >= 4) {
+      P.resident_b = 1;
+      P.nwidx = maxw + 1;
+      bres_bytes = region;
+      ring_budget -= region;
+    }
+  }
+  const int stage_bytes = P.resident_b ? 16384 : 16384 + BN * 128;
+  // TMA-store epilogue for layers with a short main loop (see TcFwdParams): the staging slabs come out of the ring's budget
   {
     static int ts_env = -1;                       // A/B knob: 0 = never, 1 = automatic (default), 2 = whenever possible
     if (ts_env < 0) { const char* e = getenv("BG_TC_TMA_STORE"); ts_env = e ? atoi(e) : 1; }
@@ -752,8 +791,9 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
       }
     }
   }
-  P.ostage_off = (uint32_t)(stages * stage_bytes);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + (P.tma_store ? 2 * P.ostage_sets * P.ostage_half : 0);
+  P.bres_off = (uint32_t)(stages * stage_bytes);
+  P.ostage_off = P.bres_off + (uint32_t)bres_bytes;
+  const size_t smem = (size_t)stages * stage_bytes + bres_bytes + 1024 + (P.tma_store ? 2 * P.ostage_sets * P.ostage_half : 0);
 #define TC_LAUNCH(COLS)                                                                                          \
   do {                                                                                                           \
     static bool attr_set = false;                                                                                \
