@@ -351,24 +351,33 @@ __global__ void reflect_fold_scalar_kernel(const T* __restrict__ dxp, const T* r
   }
 }
 
-template <typename T, int VEC>
+// One block per padded row (b, yp): the source row is resolved once, threads move 16-byte vectors (raw copy, no conversion).
+template <int ACT>
 __global__ void __launch_bounds__(256)
-reflect_pad_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int pt, int pl, int pb, int pr) {
+reflect_pad_rows_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int CV, int pt, int pl, int pb, int pr) {
   const int Hp = H + pt + pb, Wp = W + pl + pr;
-  const int CV = C / VEC;
-  const long total = (long)B * Hp * Wp * CV;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % CV); const long pix = idx / CV;
-    const int xp = (int)(pix % Wp); const long r = pix / Wp;
-    const int yp = (int)(r % Hp); const int b = (int)(r / Hp);
-    int iy = yp - pt, ix = xp - pl;
-    if (iy < 0) iy = -iy;
-    if (iy >= H) iy = 2 * (H - 1) - iy;
+  const int yp = blockIdx.x % Hp, b = blockIdx.x / Hp;
+  int iy = yp - pt;
+  if (iy < 0) iy = -iy;
+  if (iy >= H) iy = 2 * (H - 1) - iy;
+  const uint4* src = x + ((long)b * H + iy) * W * CV;
+  uint4* dst = y + (long)blockIdx.x * Wp * CV;
+  const int n = Wp * CV;
+  for (int v = threadIdx.x; v < n; v += 256) {
+    const int xp = v / CV, cv = v - xp * CV;
+    int ix = xp - pl;
     if (ix < 0) ix = -ix;
     if (ix >= W) ix = 2 * (W - 1) - ix;
-    const long src = (((long)b * H + iy) * W + ix) * C + (long)cv * VEC, dst = pix * C + (long)cv * VEC;
+    uint4 t = __ldg(src + (long)ix * CV + cv);
+    if (ACT == BG_ACT_RELU) {                        // bf16 only: clear every negative element (sign bit set)
+      uint32_t* w = reinterpret_cast<uint32_t*>(&t);
 #pragma unroll
-    for (int e = 0; e < VEC; e += 4) bg_st4(y, dst + e, bg_ld4(x, src + e));
+      for (int e = 0; e < 4; ++e) {
+        if (w[e] & 0x00008000u) w[e] &= 0xFFFF0000u;
+        if (w[e] & 0x80000000u) w[e] &= 0x0000FFFFu;
+      }
+    }
+    dst[v] = t;
   }
 }
 
@@ -734,15 +743,25 @@ extern "C" int bg_colsum(const void* dy, float* db, long rows, int C, int dtype,
   return BG_OK;
 }
 
+// y = relu(reflect_pad(x)) in one pass (bf16, 16-byte vectors): the `act(x)` in front of the first conv of resblock_down
+// (ops.py:297-301) rides in the padding copy that conv needs anyway
+extern "C" int bg_reflect_pad_relu(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr, int dtype,
+                                   void* stream) {
+  BG_REQUIRE(dtype == BG_BF16 && C % 8 == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (long)B * (H + pt + pb) < 2147483647L,
+             BG_ERR_UNSUPPORTED, "bg_reflect_pad_relu: bf16, C a multiple of 8, 16-byte aligned");
+  reflect_pad_rows_kernel<BG_ACT_RELU><<<(unsigned)(B * (H + pt + pb)), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, H, W, C / 8, pt, pl,
+                                                                                                    pb, pr);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
 extern "C" int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr, int dtype,
                               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long total = (long)B * (H + pt + pb) * (W + pl + pr) * C;
   const int vec = dtype == BG_F32 ? 4 : 8;
-  if (C % vec == 0) {
-    const int blocks = (int)min(bg_cdiv(total / vec, 256), (long)bg_num_sms() * 32);
-    if (dtype == BG_F32) reflect_pad_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, B, H, W, C, pt, pl, pb, pr);
-    else reflect_pad_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, pt, pl, pb, pr);
+  if (C % vec == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (long)B * (H + pt + pb) < 2147483647L) {
+    reflect_pad_rows_kernel<BG_ACT_NONE><<<(unsigned)(B * (H + pt + pb)), 256, 0, st>>>((const uint4*)x, (uint4*)y, H, W, C / vec, pt, pl, pb, pr);
   } else {
     const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
     BG_DISPATCH_DTYPE(dtype, T, reflect_pad_scalar_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, pt, pl, pb, pr));

@@ -206,8 +206,9 @@ def _conv_tag(d):
     return "[%s k%d s%d %dx%d %d>%d b%d]" % ("deconv" if d.transposed else "conv", d.kh, d.stride, d.Hi, d.Wi, d.Ci, d.Co, d.B)
 
 
-def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
-    """y = act(conv(x; wn) + bias + residual) and its tape entry (dgrad / wgrad / bias grad)."""
+def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None, pre_relu=False):
+    """y = act(conv(x; wn) + bias + residual) and its tape entry (dgrad / wgrad / bias grad).
+    pre_relu (bf16 reflect-padded convs only): y = conv(relu(x)); the ReLU rides in the padding copy."""
     dt = bg_dtype(x)
     fs = _state["force_simt"]
     y = Tensor(empty([desc.B, desc.Ho, desc.Wo, desc.Co], x.dtype),
@@ -221,10 +222,12 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
             and (desc.pad_t | desc.pad_l | desc.pad_b | desc.pad_r)):
         Hp, Wp = desc.Hi + desc.pad_t + desc.pad_b, desc.Wi + desc.pad_l + desc.pad_r
         xin = empty([desc.B, Hp, Wp, desc.Ci], x.dtype)
-        call("bg_reflect_pad", x.data, xin, desc.B, desc.Hi, desc.Wi, desc.Ci, desc.pad_t, desc.pad_l, desc.pad_b, desc.pad_r, dt,
-             stream(), tag="reflect_pad")
+        call("bg_reflect_pad_relu" if pre_relu else "bg_reflect_pad", x.data, xin, desc.B, desc.Hi, desc.Wi, desc.Ci, desc.pad_t,
+             desc.pad_l, desc.pad_b, desc.pad_r, dt, stream(), tag="reflect_pad")
         desc_f = ConvDesc(desc.B, Hp, Wp, desc.Ci, desc.Ho, desc.Wo, desc.Co, desc.kh, desc.kw, desc.stride, 0, 0, 0, 0,
                           _lib.PAD_ZERO, 0)
+    else:
+        assert not pre_relu, "pre_relu needs the materialised reflect padding (bf16 mode)"
     nbf = query("bg_conv2d_fwd_workspace_bytes", desc_f, dt)
     wsf = workspace(nbf) if nbf else None
     call("bg_conv2d_fwd", desc_f, xin, wn.data, w_t, bias.data if bias is not None else None,
@@ -260,7 +263,17 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None):
                 call("bg_colsum", dy, dst, rows, desc.Co, dt, ws, ws.numel(), stream())
                 if fin:
                     fin()
-            if x.requires_grad:
+            if x.requires_grad and pre_relu:          # d relu(x) first, then the mask (what the stand-alone relu's entry did)
+                nb = query("bg_conv2d_dgrad_workspace_bytes", desc, dt)
+                ws = workspace(nb) if nb else None
+                dxr = torch.empty_like(x.data)
+                call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, None, dxr, dt, ws, ws.numel() if nb else 0, fs, stream(),
+                     flops=_conv_flops(desc), tag="conv_dgrad" + _conv_tag(desc))
+                dst, fin = grad_target(x)
+                call("bg_relu_bwd", x.data, dxr, dst, x.numel(), dt, stream())
+                if fin:
+                    fin()
+            elif x.requires_grad:
                 nb = query("bg_conv2d_dgrad_workspace_bytes", desc, dt)
                 ws = workspace(nb) if nb else None
                 res = x.grad
@@ -414,8 +427,11 @@ def _im2col_rgb(x, desc, cz):
 
 
 def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True, scope='conv_0',
-         _residual=None, _act=_lib.ACT_NONE, _pad_cout_to=0):
-    """ops.py:49-113."""
+         _residual=None, _act=_lib.ACT_NONE, _pad_cout_to=0, _pre_relu=False):
+    """ops.py:49-113.  _pre_relu: conv(relu(x)) (the activation resblock_down applies in front of its first conv)."""
+    if _pre_relu and not (x.dtype == BF16 and pad > 0 and opt.get("conv", {}).get("padding_type", "reflect") == "reflect"
+                          and x.shape[-1] % 8 == 0 and c_real(x) == x.shape[-1] and not isinstance(kernel, str)):
+        x, _pre_relu = relu(x), False                # no padding copy to ride in: the plain activation
     with variable_scope(scope):
         if isinstance(kernel, str):
             raise ValueError("channel-sliced multi-kernel conv (ops.py:52-59) is out of scope")
@@ -451,7 +467,7 @@ def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True,
             if c_pad != channels:
                 bias = _padded_bias(bias, c_pad)
         desc.Co = c_pad          # extra output channels are exactly zero (zero weights, zero bias)
-        y = _conv_op(x, wn, bias, desc, act=_act, residual=_residual)
+        y = _conv_op(x, wn, bias, desc, act=_act, residual=_residual, pre_relu=_pre_relu)
         if c_pad != channels:
             y.aux = {"c_real": channels}
         return y
@@ -639,14 +655,14 @@ def resblock_down(x_init, channels, opt, use_bias=True, scope='resblock_down'):
                 x = bn(x_init, opt=opt)
             else:
                 x = x_init
-            x = opt["act"](x)
             res_method = opt["downsampling_method"]
             if res_method != 'strided_conv3':
                 res_method = 'resize_conv3'
             fuse = opt["act"] is relu and not opt["bn_in_d"] and res_method == 'strided_conv3'
-            if fuse:
-                x = conv(x, channels, kernel=3, stride=2, pad=1, use_bias=use_bias, opt=opt, _act=_lib.ACT_RELU)
+            if fuse:                 # act -> conv -> act with both activations fused into the conv's padding copy / epilogue
+                x = conv(x, channels, kernel=3, stride=2, pad=1, use_bias=use_bias, opt=opt, _act=_lib.ACT_RELU, _pre_relu=True)
             else:
+                x = opt["act"](x)
                 x = downconv(x, channels, use_bias=use_bias, opt=opt, method=res_method)
         with variable_scope('res2'):
             if opt["bn_in_d"]:

@@ -211,6 +211,10 @@ int bg_pad_channels(const void* src, int src_dtype, void* dst, int dst_dtype, lo
                     void* stream);
 int bg_reflect_pad(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr,
                    int dtype, void* stream);
+/* y = relu(reflect_pad(x)) in one pass (bf16, C a multiple of 8): the activation in front of the first conv of
+ * resblock_down (ops.py:297-301) rides in the padding copy */
+int bg_reflect_pad_relu(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr,
+                        int dtype, void* stream);
 /* bf16 image tensors stored zero-padded to Cx >= 3 channels (ops.py:49-113 with Cin = 3, the first D convs):
  * z[b,oy,ox,(ky*kw+kx)*3+c] = x[b, R(oy*stride+ky-pad_t), R(ox*stride+kx-pad_l), c] (R: reflect / zero), channels
  * kh*kw*3..Cz-1 zero -- the conv then runs as a 1x1 GEMM with K = Cz.  col2im is the adjoint (gather, deterministic):

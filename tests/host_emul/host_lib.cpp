@@ -713,3 +713,14 @@ extern "C" int bg_maxpool2_slice_bwd(const void* x_, long ldx, const void* dy_, 
   }
   return BG_OK;
 }
+
+extern "C" int bg_reflect_pad_relu(const void* x, void* y, int B, int H, int W, int C, int pt, int pl, int pb, int pr, int dtype, void*) {
+  if (dtype != BG_BF16 || C % 8) { bg_set_error("bg_reflect_pad_relu: bf16, C a multiple of 8"); return BG_ERR_UNSUPPORTED; }
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  In xi(x, (long)B * H * W * C, dtype); Out yo(y, (long)B * Hp * Wp * C, dtype);
+  for (int b = 0; b < B; ++b) for (int i = 0; i < Hp; ++i) for (int j = 0; j < Wp; ++j) {
+    const int si = reflect_idx(i - pt, H), sj = reflect_idx(j - pl, W);
+    for (int c = 0; c < C; ++c) { const float v = xi.p[(((long)b * H + si) * W + sj) * C + c]; yo.p[(((long)b * Hp + i) * Wp + j) * C + c] = v > 0.f ? v : 0.f; }
+  }
+  return BG_OK;
+}
