@@ -725,13 +725,20 @@ extern "C" int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x, const void*
   return BG_OK;
 }
 
+size_t bg_bn_colsum_ws(long rows, int C);            // norm.cu: column sums on the vectorised statistics kernels
+bool bg_bn_colsum_applicable(int C, int dtype);
+int bg_bn_colsum(const void* x, float* out, long rows, int C, int dtype, void* ws, cudaStream_t st);
+
 extern "C" size_t bg_colsum_workspace_bytes(long rows, int C) {
   long nchunk = min(bg_cdiv(rows, 64), 1024L);
-  return (size_t)nchunk * C * sizeof(float) + 256;
+  const size_t a = (size_t)nchunk * C * sizeof(float) + 256, b = (C % 4 == 0) ? bg_bn_colsum_ws(rows, C) : 0;
+  return a > b ? a : b;
 }
 
 extern "C" int bg_colsum(const void* dy, float* db, long rows, int C, int dtype, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (rows >= 256 && bg_bn_colsum_applicable(C, dtype) && ws && ws_bytes >= bg_bn_colsum_ws(rows, C) && (((uintptr_t)dy) & 15) == 0)
+    return bg_bn_colsum(dy, db, rows, C, dtype, ws, st);
   long nchunk = min(bg_cdiv(rows, 64), 1024L);
   BG_REQUIRE(ws && ws_bytes >= (size_t)nchunk * C * sizeof(float), BG_ERR_WORKSPACE, "colsum workspace too small");
   const long rpc = bg_cdiv(rows, nchunk);

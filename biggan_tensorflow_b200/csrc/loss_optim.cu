@@ -61,11 +61,13 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 logistic_cls_kernel(const T* __restrict__ logits, const float* __restrict__ labels, const float* __restrict__ cls_w, int B,
                     int n_labels, float weight, float inv_count, float* __restrict__ loss, T* __restrict__ dlogits,
-                    int accumulate_loss) {
+                    int accumulate_loss, float* __restrict__ part) {
   __shared__ float sh[33];
   const long n = (long)B * n_labels;
   float s = 0.f;
-  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+  // blocks take interleaved 1024-element slabs; with `part` every block leaves its partial sum and logistic_sum_kernel adds
+  // them in block order (deterministic), without it the launch is a single block that finishes the loss itself
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float x = bg_ld(logits, i), z = labels[i];
     const float w = cls_w ? cls_w[i % n_labels] : 1.f;
     s += w * (fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x))));
@@ -73,14 +75,35 @@ logistic_cls_kernel(const T* __restrict__ logits, const float* __restrict__ labe
     bg_st(dlogits, i, weight * inv_count * w * (sig - z));
   }
   s = bg_block_sum(s, sh);
-  if (threadIdx.x == 0) loss[0] = (accumulate_loss ? loss[0] : 0.f) + weight * inv_count * s;
+  if (threadIdx.x == 0) {
+    if (part) part[blockIdx.x] = s;
+    else loss[0] = (accumulate_loss ? loss[0] : 0.f) + weight * inv_count * s;
+  }
 }
+__global__ void logistic_sum_kernel(const float* __restrict__ part, int np, float scale, float* __restrict__ loss, int accumulate_loss) {
+  float s = 0.f;
+  for (int i = 0; i < np; ++i) s += part[i];
+  loss[0] = (accumulate_loss ? loss[0] : 0.f) + scale * s;
+}
+
+extern "C" size_t bg_logistic_cls_workspace_bytes(int B, int n_labels) { (void)B; (void)n_labels; return 256 * sizeof(float); }
 
 extern "C" int bg_logistic_cls_fwd_bwd(const void* logits, const float* labels, const float* cls_w, int B, int n_labels,
                                        float weight, float inv_count, float* loss, void* dlogits, int accumulate_loss,
-                                       int dtype, void* stream) {
-  BG_DISPATCH_DTYPE(dtype, T, logistic_cls_kernel<T><<<1, 1024, 0, (cudaStream_t)stream>>>((const T*)logits, labels, cls_w, B, n_labels, weight,
-                                                                                       inv_count, loss, (T*)dlogits, accumulate_loss));
+                                       int dtype, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long n = (long)B * n_labels;
+  int nb = (int)min(bg_cdiv(n, 4096), 148L);
+  if (!ws || ws_bytes < 256 * sizeof(float) || nb <= 1) {
+    BG_DISPATCH_DTYPE(dtype, T, logistic_cls_kernel<T><<<1, 1024, 0, st>>>((const T*)logits, labels, cls_w, B, n_labels, weight, inv_count, loss,
+                                                                        (T*)dlogits, accumulate_loss, nullptr));
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+  }
+  BG_DISPATCH_DTYPE(dtype, T, logistic_cls_kernel<T><<<nb, 1024, 0, st>>>((const T*)logits, labels, cls_w, B, n_labels, weight, inv_count, loss,
+                                                                       (T*)dlogits, accumulate_loss, (float*)ws));
+  BG_LAUNCH_CHECK();
+  logistic_sum_kernel<<<1, 1, 0, st>>>((const float*)ws, nb, weight * inv_count, loss, accumulate_loss);
   BG_LAUNCH_CHECK();
   return BG_OK;
 }

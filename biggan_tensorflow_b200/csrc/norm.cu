@@ -173,6 +173,47 @@ extern "C" int bg_bn_stats(const void* x, double* sums, int B, long HW, int C, i
   return BG_OK;
 }
 
+// Column sums of a [rows, C] matrix (bias gradients) on the statistics kernels above: the vectorised reduce pass
+// (16-byte loads, full lines whatever C is) + a fixed-order tree over its partial rows.
+__global__ void __launch_bounds__(1024) colsum_from_part_kernel(const float* __restrict__ part, float* __restrict__ out, int nrow, int C) {
+  __shared__ double sa[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double a = 0.0;
+  if (c < C) {
+    int i = ty;
+    for (; i + 7 * 32 < nrow; i += 8 * 32) {
+      float va[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) va[k] = __ldg(part + ((long)(i + k * 32) * 2) * C + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += (double)va[k];
+    }
+    for (; i < nrow; i += 32) a += (double)part[((long)i * 2) * C + c];
+  }
+  sa[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sa[i][tx];
+    out[c] = (float)t;
+  }
+}
+size_t bg_bn_colsum_ws(long rows, int C) { return bg_bn_workspace_bytes(1, rows, C); }
+bool bg_bn_colsum_applicable(int C, int dtype) { return bn_vec_ok(C, dtype); }
+int bg_bn_colsum(const void* x, float* out, long rows, int C, int dtype, void* ws, cudaStream_t st) {
+  const int nchunk = bn_nchunk(1, rows, C);
+  const BnLayout L = bn_layout(C, dtype);
+  dim3 grid(L.nxb, nchunk, 1);
+  const size_t shb = (size_t)2 * L.R * L.TPRB * L.V * sizeof(float);
+  BG_DISPATCH_DTYPE(dtype, T, bn_reduce_kernel<T, 0><<<grid, L.threads, shb, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0,
+                                                                                0.f, (float*)ws, rows, C, nchunk, L.TPRB, L.R));
+  BG_LAUNCH_CHECK();
+  colsum_from_part_kernel<<<(unsigned)bg_cdiv(C, 32), 1024, 0, st>>>((const float*)ws, out, nchunk, C);
+  BG_LAUNCH_CHECK();
+  return BG_OK;
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, float* __restrict__ mean,
                                    float* __restrict__ var, float* run_mean, float* run_var, float momentum,
                                    float var_correction, int C) {

@@ -1506,8 +1506,9 @@ def cls_loss_fn(type, cls_weights):
         out = Tensor(empty([1], F32), requires_grad=answer.requires_grad)
         dl = torch.empty_like(a32.data)
         tdata = truth.data if isinstance(truth, Tensor) else truth
+        wsl = workspace(query("bg_logistic_cls_workspace_bytes", Bn, nl))
         call("bg_logistic_cls_fwd_bwd", a32.data, tdata, cls_weights, Bn, nl, 1.0,
-             1.0 / (Bn * nl * dist.world_size), out.data, dl, 0, _lib.BG_F32, stream())
+             1.0 / (Bn * nl * dist.world_size), out.data, dl, 0, _lib.BG_F32, wsl, wsl.numel(), stream())
         if recording(a32):
             def bw():
                 if out.grad is not None:

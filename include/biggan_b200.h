@@ -234,9 +234,10 @@ int bg_hinge_d_fwd_bwd(const void* real, const void* fake, int n_real, int n_fak
                        float flood, float* loss, void* dreal, void* dfake, int dtype, void* stream);
 int bg_hinge_g_fwd_bwd(const void* fake, int n, float inv_count, float flood, float* loss,
                        void* dfake, int dtype, void* stream);
+size_t bg_logistic_cls_workspace_bytes(int B, int n_labels);   /* ws may be NULL (single-block kernel) */
 int bg_logistic_cls_fwd_bwd(const void* logits, const float* labels, const float* cls_w, int B,
                             int n_labels, float weight, float inv_count, float* loss, void* dlogits,
-                            int accumulate_loss, int dtype, void* stream);
+                            int accumulate_loss, int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DiffAugment -- DiffAugment_tf.py:8-73.  x [B,H,W,C]; per-sample randoms are INPUTS:

@@ -483,8 +483,9 @@ extern "C" int bg_hinge_g_fwd_bwd(const void* fake_, int n, float inv_count, flo
   for (int i = 0; i < n; ++i) ((float*)dfake)[i] = -sgn * inv_count;
   return BG_OK;
 }
+extern "C" size_t bg_logistic_cls_workspace_bytes(int, int) { return 16; }
 extern "C" int bg_logistic_cls_fwd_bwd(const void* logits_, const float* labels, const float* cls_w, int B, int n_labels, float weight,
-                                       float inv_count, float* loss, void* dlogits, int accumulate_loss, int dtype, void*) {
+                                       float inv_count, float* loss, void* dlogits, int accumulate_loss, int dtype, void*, size_t, void*) {
   DTYPE_OK(dtype); In li(logits_, (long)B * n_labels, dtype); Out dlo(dlogits, (long)B * n_labels, dtype); logits_ = li.p; dlogits = dlo.p;
   const float* logits = (const float*)logits_;
   double s = 0;
