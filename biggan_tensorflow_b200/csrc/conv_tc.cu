@@ -657,7 +657,10 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   P.nkb = (int)bg_cdiv(g.Ci, 64);
   P.ktail = (int)bg_cdiv(g.Ci - (P.nkb - 1) * 64, 16);
   P.BN = BN; P.act = act;
-  int ring_budget = 200 * 1024;
+  static int smem_kb = -1;                        // A/B knob (<= 224: + 1 KB alignment slack stays under the 227 KB per-block limit);
+  // measured: 224 KB gives the halo layers a 4th stage but changes the step by < 0.3 % either way, so the default stays 200
+  if (smem_kb < 0) { const char* e = getenv("BG_TC_SMEM_KB"); smem_kb = e ? atoi(e) : 200; if (smem_kb < 96 || smem_kb > 224) smem_kb = 200; }
+  int ring_budget = smem_kb * 1024;
   // resident-weights mode (see TcFwdParams): one n-tile, no split-K, not a halo layer, all weight tiles fit beside >= 4 stages
   int bres_bytes = 0;
   {
