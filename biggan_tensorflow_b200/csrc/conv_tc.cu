@@ -55,6 +55,9 @@ struct TcFwdParams {
   // resident-weights mode (plain kernel, Co == BN, all weight tiles fit): the (tap, k-block) weight tiles are loaded ONCE per
   // persistent CTA into their own shared-memory region; ring stages then carry activations only.  For the layers with few
   // output channels / small K (1x1 projections, the RGB layers) the weights were 40-75 % of every tile's ingest.
+  // paired-tile mode (plain kernel, BN <= 128, streamed weights): a work item is TWO consecutive 128-pixel tiles sharing every weight
+  // stage (two TMEM accumulators): the weight tiles enter the SM once per 256 pixels instead of once per 128
+  int mt;                    // m-tiles per work item: 1 or 2
   int resident_b;
   uint32_t bres_off;         // resident weight region, bytes from the 1024-aligned dynamic shared memory base
   int nwidx;                 // weight tiles per k-block in the region (max widx + 1)
@@ -78,10 +81,14 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
     const int w = row % p.bw, h = (row / p.bw) % p.bh, bl = row / (p.bw * p.bh);
     int lt = 0;
     const int S = p.ksplit;
+    const int MT = p.mt;
+    const int tpp_items = (tiles_pp + MT - 1) / MT;          // work items per phase and n-tile (ntiles counts items)
     for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
-      const int tile = wi / S, split = wi - tile * S;
-      const int nt = tile % ntn; int t = tile / ntn;
-      const int phase = t / tiles_pp; t -= phase * tiles_pp;
+      const int item = wi / S, split = wi - item * S;
+      const int nt = item % ntn; int ti = item / ntn;
+      const int phase = ti / tpp_items; ti -= phase * tpp_items;
+     for (int m = 0; m < MT; ++m) {
+      int t = ti * MT + m;                                   // a tile index past the phase decodes to b0 >= B: nothing valid, boxes clipped
       const int j0 = (t % p.tw) * p.bw; t /= p.tw;
       const int i0 = (t % p.th) * p.bh; t /= p.th;
       const int b0 = t * p.bb;
@@ -98,7 +105,8 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         else { outb = p.ring; res_ok = false; }
       }
       const int buf = lt & 1;
-      // residual (fused accumulate / skip connection) is read in groups of 4 x 16 channels, one group ahead of its use; the
+      const uint32_t tcol = (uint32_t)(buf * MT * p.BN + m * p.BN);          // this tile's accumulator columns
+      // residual (fused accumulate / skip connection) is read in groups of 2 x 16 channels, one group ahead of its use; the
       // first group is in flight while this warp still waits for the accumulator, so the global-load latency is off the
       // per-tile critical path
       if (S > 1) {                                   // split-K work item: raw fp32 partials, finished by the reduce kernel
@@ -107,7 +115,7 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         float* pp = p.part + (long)split * p.part_stride + obase;
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
           uint32_t r[16];
-          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), r);
+          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
           if (valid) {
             float4* o = reinterpret_cast<float4*>(pp + c0);
 #pragma unroll
@@ -125,7 +133,7 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
       const bool tstore = p.tma_store != 0;
       // staging slabs are double-buffered per half: tile lt writes set lt & 1 while the bulk stores of tile lt - 1 still read
       // the other set; the stores of tile lt - 2 (same set) must have finished reading
-      const uint32_t hset = smem_base + p.ostage_off + (uint32_t)(p.ostage_sets * half + (p.ostage_sets == 2 ? (lt & 1) : 0)) * p.ostage_half;
+      const uint32_t hset = smem_base + p.ostage_off + (uint32_t)(p.ostage_sets * half + (p.ostage_sets == 2 ? ((lt * MT + m) & 1) : 0)) * p.ostage_half;
       const uint32_t hb = hset + (uint32_t)row * 32u;
       if (tstore) {
         if ((ew & 3) == 0 && elect_one_sync()) {                            // same elected lane as the one issuing the stores
@@ -133,10 +141,10 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         }
         named_bar_sync(1u + (uint32_t)half, 128u);
       }
-      uint4 rb[2][4][2];
+      uint4 rb[2][2][2];
       auto load_group = [&](int g, int cg) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 2; ++j)
           if (use_res && cg + j * 16 < cend) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg + j * 16);
             rb[g][j][0] = __ldg(rp);
@@ -144,17 +152,19 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
           }
       };
       load_group(0, cbeg);
-      mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
-      tc_fence_after();
+      if (m == 0) {
+        mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
+        tc_fence_after();
+      }
       int gsel = 0;
-      for (int cg = cbeg; cg < cend; cg += 64, gsel ^= 1) {
-        if (gsel == 0) load_group(1, cg + 64); else load_group(0, cg + 64);
+      for (int cg = cbeg; cg < cend; cg += 32, gsel ^= 1) {
+        if (gsel == 0) load_group(1, cg + 32); else load_group(0, cg + 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           const int c0 = cg + j * 16;
           if (c0 >= cend) break;
           uint32_t r[16];
-          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.BN + c0), r);
+          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
           if (valid || tstore) {
             float v[16];
 #pragma unroll
@@ -200,9 +210,11 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+      if (m == MT - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+      }
       if (tstore) {
         fence_proxy_async_smem();
         named_bar_sync(1u + (uint32_t)half, 128u);
@@ -212,6 +224,7 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
           tma_store_commit();
         }
       }
+     }
     }
     if (p.tma_store && (ew & 3) == 0 && elect_one_sync()) tma_store_wait_all();     // shared memory must outlive the last bulk store
 }
@@ -232,10 +245,13 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t wtile = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = p.resident_b ? 16384u : 16384u + wtile;
+  const int MT = p.mt;                                   // m-tiles per work item (1 or 2)
+  const uint32_t abytes = (uint32_t)MT * 16384u;         // activation tiles of a stage
+  const uint32_t stage_bytes = p.resident_b ? abytes : abytes + wtile;
   const int tiles_pp = p.tw * p.th * p.tb;
+  const int tpp_items = (tiles_pp + MT - 1) / MT;
   const int ntn = p.Co / p.BN;
-  const int ntiles = tiles_pp * p.nphase * ntn;
+  const int ntiles = tpp_items * p.nphase * ntn;          // work items
 
   if (warp == 0 && elect_one_sync()) {
     for (int m = 0; m < 4; ++m) tma_prefetch_desc(&p.amap[m]);
@@ -266,12 +282,17 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
           for (int kb = 0; kb < p.nkb; ++kb, dst += wtile) tma_load_3d(dst, &p.bmap, bb, kb * 64, 0, w);
       }
       for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x) {
-        const int tile = wi / S, split = wi - tile * S;
-        const int nt = tile % ntn; int t = tile / ntn;
-        const int phase = t / tiles_pp; t -= phase * tiles_pp;
+        const int item = wi / S, split = wi - item * S;
+        const int nt = item % ntn; int ti = item / ntn;
+        const int phase = ti / tpp_items; ti -= phase * tpp_items;
+        int t = ti * MT;
         const int j0 = (t % p.tw) * p.bw; t /= p.tw;
         const int i0 = (t % p.th) * p.bh; t /= p.th;
         const int b0 = t * p.bb;
+        int t1 = ti * MT + 1;                                  // second tile of a pair (past the phase: b >= B, zero fill)
+        const int j1 = (t1 % p.tw) * p.bw; t1 /= p.tw;
+        const int i1 = (t1 % p.th) * p.bh; t1 /= p.th;
+        const int b1 = t1 * p.bb;
         const int n0 = nt * p.BN;
         const int total = p.ntaps[phase] * p.nkb;
         const int lo = total * split / S, hi = total * (split + 1) / S;     // this work item's (tap, k-block) stages
@@ -282,7 +303,8 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
           const uint32_t fb = full0 + s * 8u;
           mbar_expect_tx(fb, stage_bytes);
           tma_load_4d(sa, &p.amap[tap.map], fb, kb * 64, j0 + tap.dx, i0 + tap.dy, b0);
-          if (!p.resident_b) tma_load_3d(sa + 16384u, &p.bmap, fb, kb * 64, n0, tap.widx);
+          if (MT == 2) tma_load_4d(sa + 16384u, &p.amap[tap.map], fb, kb * 64, j1 + tap.dx, i1 + tap.dy, b1);
+          if (!p.resident_b) tma_load_3d(sa + abytes, &p.bmap, fb, kb * 64, n0, tap.widx);
           if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; sa = smem_base; } else sa += stage_bytes;
           if (++kb == p.nkb) { kb = 0; ++tp; if (li + 1 < hi) tap = p.taps[phase][tp]; }
         }
@@ -301,14 +323,14 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
       const uint32_t bres_lo = umma_desc_lo(smem_base + p.bres_off, 16), wtile_q = wtile >> 4;
       if (res) { mbar_wait(smem_u32(&bres_bar), 0); tc_fence_after(); }
       for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
-        const int tile = wi / S, split = wi - tile * S;
-        const int phase = (tile / ntn) / tiles_pp;
+        const int item = wi / S, split = wi - item * S;
+        const int phase = (item / ntn) / tpp_items;
         const int total = p.ntaps[phase] * p.nkb;
         const int lo = total * split / S, hi = total * (split + 1) / S;
         const int buf = lt & 1;
         mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(buf * p.BN);
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * MT * p.BN);
         int kb = lo % p.nkb, tp = lo / p.nkb;
         uint32_t acc = 0u;
         uint32_t bw_lo = res ? bres_lo + (uint32_t)(p.taps[phase][tp].widx * p.nkb + kb) * wtile_q : 0u;
@@ -317,12 +339,19 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
           tc_fence_after();
           const int nk = (kb == p.nkb - 1) ? p.ktail : 4;
           if (!dry) {
-            const uint32_t b_lo = res ? bw_lo : a_lo + 1024u;     // weight tile: resident region, or 16 KB behind the activation tile
+            const uint32_t b_lo = res ? bw_lo : a_lo + (abytes >> 4);     // weight tile: resident region, or behind the activation tile(s)
             umma_bf16_w(tacc, a_lo, UMMA_DESC_HI_KMAJOR_SW128, b_lo, UMMA_DESC_HI_KMAJOR_SW128, idesc, acc);
-            acc = 1u;
             if (nk > 1) umma_bf16_w(tacc, a_lo + 2u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 2u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
             if (nk > 2) umma_bf16_w(tacc, a_lo + 4u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 4u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
             if (nk > 3) umma_bf16_w(tacc, a_lo + 6u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 6u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+            if (MT == 2) {                                     // second tile of the pair: its own activation tile and accumulator, same weights
+              const uint32_t a1 = a_lo + 1024u, t1 = tacc + (uint32_t)p.BN;
+              umma_bf16_w(t1, a1, UMMA_DESC_HI_KMAJOR_SW128, b_lo, UMMA_DESC_HI_KMAJOR_SW128, idesc, acc);
+              if (nk > 1) umma_bf16_w(t1, a1 + 2u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 2u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+              if (nk > 2) umma_bf16_w(t1, a1 + 4u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 4u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+              if (nk > 3) umma_bf16_w(t1, a1 + 6u, UMMA_DESC_HI_KMAJOR_SW128, b_lo + 6u, UMMA_DESC_HI_KMAJOR_SW128, idesc, 1u);
+            }
+            acc = 1u;
           }
           umma_commit(empty0 + s * 8u);
           if (++kb == p.nkb) {
@@ -677,7 +706,19 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
       ring_budget -= region;
     }
   }
-  const int stage_bytes = P.resident_b ? 16384 : 16384 + BN * 128;
+  // paired-tile mode (see TcFwdParams): streamed weights that are a sizeable part of a stage, two accumulators fit TMEM
+  P.mt = 1;
+  {
+    static int pair_env = -1;                     // A/B knob
+    if (pair_env < 0) { const char* e = getenv("BG_TC_PAIR"); pair_env = e ? atoi(e) : 1; }
+    const char* he1 = getenv("BG_TC_HALO");
+    const bool halo_possible = (he1 ? atoi(he1) : 1) && g.nphase == 1 && s == 1 && bw == 128 && bh == 1 && bb == 1 && g.ph[0].ntaps > 1;
+    const long tiles_pp0 = (long)P.tw * P.th * P.tb;
+    if (pair_env && !P.resident_b && pl.ksplit <= 1 && !halo_possible && !box_override && BN >= 64 && BN <= 128 && tiles_pp0 >= 2 &&
+        tiles_pp0 * g.nphase * (g.Co / BN) >= 4L * bg_num_sms() && ring_budget / (32768 + BN * 128) >= 3)
+      P.mt = 2;
+  }
+  const int stage_bytes = P.resident_b ? 16384 : P.mt * 16384 + BN * 128;
   // TMA-store epilogue for layers with a short main loop (see TcFwdParams): the staging slabs come out of the ring's budget
   {
     static int ts_env = -1;                       // A/B knob: 0 = never, 1 = automatic (default), 2 = whenever possible
@@ -721,7 +762,7 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     }
   }
   P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
-  const long ntiles = (long)P.tw * P.th * P.tb * g.nphase * (g.Co / BN);
+  const long ntiles = bg_cdiv((long)P.tw * P.th * P.tb, (long)P.mt) * g.nphase * (g.Co / BN);      // work items
   const long out_numel = (long)g.B * g.Ho * g.Wo * g.Co;
   if (fold) { P.fold = 1; P.f_pt = fold->pt; P.f_pl = fold->pl; P.f_Hi = fold->Hi; P.f_Wi = fold->Wi; P.ring = (bf16*)fold->ring; }
   P.ksplit = 1;
@@ -806,7 +847,7 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     }                                                                                                            \
     tc_fwd_kernel<COLS><<<grid, 320, smem, st>>>(P);                                                             \
   } while (0)
-  const int cols = 2 * BN;                       // double-buffered accumulator
+  const int cols = 2 * P.mt * BN;                // double-buffered accumulator(s)
   if (cols <= 32) TC_LAUNCH(32);
   else if (cols <= 64) TC_LAUNCH(64);
   else if (cols <= 128) TC_LAUNCH(128);
