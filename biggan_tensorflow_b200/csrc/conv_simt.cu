@@ -246,7 +246,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
 // One thread per (pixel, VEC channels): 16-byte accesses when C % VEC == 0 (VEC = 8 bf16 / 4 fp32).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, int H, int W, int C, int pt, int pl, int pb, int pr) {
+reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, const T* __restrict__ mask, T* dx, int B, int H, int W, int C, int pt, int pl,
+                    int pb, int pr) {
   const int Hp = H + pt + pb, Wp = W + pl + pr;
   const int CV = C / VEC;
   const long total = (long)B * H * W * CV;
@@ -265,16 +266,26 @@ reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, 
     const long o = pix * C + (long)cv * VEC;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
-    if (residual) {
-#pragma unroll
-      for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(residual, o + e); acc[e] += v.x; acc[e + 1] += v.y; acc[e + 2] += v.z; acc[e + 3] += v.w; }
-    }
     for (int a = 0; a < ny; ++a)
       for (int q = 0; q < nx; ++q) {
         const long src = (((long)b * Hp + ys[a]) * Wp + xs[q]) * C + (long)cv * VEC;
 #pragma unroll
         for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(dxp, src + e); acc[e] += v.x; acc[e + 1] += v.y; acc[e + 2] += v.z; acc[e + 3] += v.w; }
       }
+    if (mask) {                                      // ReLU mask of the conv's input: applies to the gradient, not to the residual
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) {
+        f4 m = bg_ld4(mask, o + e);
+        if (!(m.x > 0.f)) acc[e] = 0.f;
+        if (!(m.y > 0.f)) acc[e + 1] = 0.f;
+        if (!(m.z > 0.f)) acc[e + 2] = 0.f;
+        if (!(m.w > 0.f)) acc[e + 3] = 0.f;
+      }
+    }
+    if (residual) {
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(residual, o + e); acc[e] += v.x; acc[e + 1] += v.y; acc[e + 2] += v.z; acc[e + 3] += v.w; }
+    }
 #pragma unroll
     for (int e = 0; e < VEC; e += 4) bg_st4(dx, o + e, f4{acc[e], acc[e + 1], acc[e + 2], acc[e + 3]});
   }
@@ -285,7 +296,8 @@ reflect_fold_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, 
 // preimages kept in the padded-domain buffer.  Requires H >= pt + pb + 2 and W >= pl + pr + 2 (disjoint bands).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-reflect_fold_band_kernel(const T* __restrict__ ring, T* dx, int B, int H, int W, int C, int pt, int pl, int pb, int pr) {
+reflect_fold_band_kernel(const T* __restrict__ ring, const T* __restrict__ mask, T* dx, int B, int H, int W, int C, int pt, int pl, int pb,
+                         int pr) {
   const int Hp = H + pt + pb, Wp = W + pl + pr;
   const int CV = C / VEC;
   const int nR = pt + pb, nC = pl + pr;
@@ -313,24 +325,38 @@ reflect_fold_band_kernel(const T* __restrict__ ring, T* dx, int B, int H, int W,
     if (x >= 1 && x <= pl) xs[nx++] = pl - x;
     if (x >= W - 1 - pr && x <= W - 2) xs[nx++] = 2 * (W - 1) - x + pl;
     const long o = (((long)b * H + y) * W + x) * C + (long)cv * VEC;
-    float acc[VEC];
+    float acc[VEC], add[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(dx, o + e); acc[e] = v.x; acc[e + 1] = v.y; acc[e + 2] = v.z; acc[e + 3] = v.w; }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) add[e] = 0.f;
     for (int a = 0; a < ny; ++a)
       for (int q = 0; q < nx; ++q) {
         if (a == 0 && q == 0) continue;             // the interior preimage is already in dx
         const long src = (((long)b * Hp + ys[a]) * Wp + xs[q]) * C + (long)cv * VEC;
 #pragma unroll
-        for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(ring, src + e); acc[e] += v.x; acc[e + 1] += v.y; acc[e + 2] += v.z; acc[e + 3] += v.w; }
+        for (int e = 0; e < VEC; e += 4) { f4 v = bg_ld4(ring, src + e); add[e] += v.x; add[e + 1] += v.y; add[e + 2] += v.z; add[e + 3] += v.w; }
       }
+    if (mask) {                                      // the interior preimage was masked by the dgrad epilogue; mask the ring's share too
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) {
+        f4 m = bg_ld4(mask, o + e);
+        if (!(m.x > 0.f)) add[e] = 0.f;
+        if (!(m.y > 0.f)) add[e + 1] = 0.f;
+        if (!(m.z > 0.f)) add[e + 2] = 0.f;
+        if (!(m.w > 0.f)) add[e + 3] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] += add[e];
 #pragma unroll
     for (int e = 0; e < VEC; e += 4) bg_st4(dx, o + e, f4{acc[e], acc[e + 1], acc[e + 2], acc[e + 3]});
   }
 }
 
 template <typename T>
-__global__ void reflect_fold_scalar_kernel(const T* __restrict__ dxp, const T* residual, T* dx, int B, int H, int W, int C,
-                                           int pt, int pl, int pb, int pr) {
+__global__ void reflect_fold_scalar_kernel(const T* __restrict__ dxp, const T* residual, const T* __restrict__ mask, T* dx, int B, int H, int W,
+                                           int C, int pt, int pl, int pb, int pr) {
   const int Hp = H + pt + pb, Wp = W + pl + pr;
   const long total = (long)B * H * W * C;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -344,9 +370,11 @@ __global__ void reflect_fold_scalar_kernel(const T* __restrict__ dxp, const T* r
     xs[nx++] = x + pl;
     if (x >= 1 && x <= pl) xs[nx++] = pl - x;
     if (x >= W - 1 - pr && x <= W - 2) xs[nx++] = 2 * (W - 1) - x + pl;
-    float s = residual ? bg_ld(residual, idx) : 0.f;
+    float s = 0.f;
     for (int a = 0; a < ny; ++a)
       for (int e = 0; e < nx; ++e) s += bg_ld(dxp, (((long)b * Hp + ys[a]) * Wp + xs[e]) * C + c);
+    if (mask && !(bg_ld(mask, idx) > 0.f)) s = 0.f;
+    if (residual) s += bg_ld(residual, idx);
     bg_st(dx, idx, s);
   }
 }
@@ -439,7 +467,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
                      const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, const struct BgTcFold* fold,
                      cudaStream_t st, int* taken);
-struct BgTcFold { int pt, pl, Hi, Wi; void* ring; };
+struct BgTcFold { int pt, pl, Hi, Wi; void* ring; const void* mask; };
 size_t bg_tc_fwd_splitk_bytes(const BgGeom& g);
 static inline size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 int bg_tc_conv_wgrad(const BgGeom& g, const bg_conv_desc* d, const void* in, const void* og, float* dw,
@@ -591,12 +619,13 @@ extern "C" size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dty
 }
 
 extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void* w, const void* w_t, const void* residual,
-                               void* dx, int dtype, void* ws, size_t ws_bytes, int force_simt, void* stream) {
+                               const void* relu_mask, void* dx, int dtype, void* ws, size_t ws_bytes, int force_simt, void* stream) {
   BgGeom g;
   int rc = bg_build_geom(d, BG_OP_DGRAD, &g);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool padded = dgrad_padded(d);
+  BG_REQUIRE(!relu_mask || padded, BG_ERR_UNSUPPORTED, "bg_conv2d_dgrad: relu_mask is implemented for reflect-padded convs (the fold pass applies it)");
   if (padded) BG_REQUIRE(ws && ws_bytes >= dgrad_padded_bytes(d, dtype), BG_ERR_WORKSPACE, "dgrad workspace too small");
   void* gout = padded ? ws : dx;
   const void* gres = padded ? nullptr : residual;
@@ -619,14 +648,15 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
                         bg_tc_fwd_splitk_bytes(g) == 0;
       if (band) {
         BgTcFold fold = {d->pad_t, d->pad_l, d->Hi, d->Wi, ws};
+        fold.mask = relu_mask;
         rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, residual, dx, BG_ACT_NONE, nullptr, 0, &fold, st, &taken);
         if (rc) return rc;
         if (taken) {
           const long total = (long)d->B * ((long)(d->pad_t + d->pad_b) * d->Wi + (long)(d->Hi - d->pad_t - d->pad_b) * (d->pad_l + d->pad_r)) *
                              (d->Ci / 8);
           const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
-          reflect_fold_band_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)ws, (bf16*)dx, d->B, d->Hi, d->Wi, d->Ci, d->pad_t,
-                                                                  d->pad_l, d->pad_b, d->pad_r);
+          reflect_fold_band_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)ws, (const bf16*)relu_mask, (bf16*)dx, d->B, d->Hi, d->Wi, d->Ci,
+                                                                  d->pad_t, d->pad_l, d->pad_b, d->pad_r);
           BG_LAUNCH_CHECK();
           return BG_OK;
         }
@@ -647,15 +677,16 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
     if (d->Ci % vec == 0) {
       const int blocks = (int)min(bg_cdiv(total / vec, 256), (long)bg_num_sms() * 32);
       if (dtype == BG_F32)
-        reflect_fold_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)ws, (const float*)residual, (float*)dx, d->B, d->Hi, d->Wi, d->Ci,
-                                                            d->pad_t, d->pad_l, d->pad_b, d->pad_r);
+        reflect_fold_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)ws, (const float*)residual, (const float*)relu_mask, (float*)dx, d->B,
+                                                            d->Hi, d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r);
       else
-        reflect_fold_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)ws, (const bf16*)residual, (bf16*)dx, d->B, d->Hi, d->Wi, d->Ci,
-                                                           d->pad_t, d->pad_l, d->pad_b, d->pad_r);
+        reflect_fold_kernel<bf16, 8><<<blocks, 256, 0, st>>>((const bf16*)ws, (const bf16*)residual, (const bf16*)relu_mask, (bf16*)dx, d->B,
+                                                           d->Hi, d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r);
     } else {
       const int blocks = (int)min(bg_cdiv(total, 256), (long)bg_num_sms() * 16);
-      BG_DISPATCH_DTYPE(dtype, T, reflect_fold_scalar_kernel<T><<<blocks, 256, 0, st>>>((const T*)ws, (const T*)residual, (T*)dx, d->B, d->Hi,
-                                                                                     d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b, d->pad_r));
+      BG_DISPATCH_DTYPE(dtype, T, reflect_fold_scalar_kernel<T><<<blocks, 256, 0, st>>>((const T*)ws, (const T*)residual, (const T*)relu_mask, (T*)dx,
+                                                                                     d->B, d->Hi, d->Wi, d->Ci, d->pad_t, d->pad_l, d->pad_b,
+                                                                                     d->pad_r));
     }
     BG_LAUNCH_CHECK();
   }

@@ -35,6 +35,7 @@ struct TcFwdParams {
   // (unpadded tensor, + residual), the ring of pad pixels to `ring` (padded-domain buffer), folded back by a band kernel
   int fold, f_pt, f_pl, f_Hi, f_Wi;
   bf16* ring;
+  const bf16* mask;          // fold mode: ReLU mask (the conv's input, same layout as `out`): interior gradients are zeroed where mask <= 0
   int ksplit;                // split-K: each tile's (tap, k-block) stage sequence is cut into ksplit work items whose fp32
   float* part;               //   partial accumulators go to part[split * part_stride + out offset] (summed by tc_splitk_reduce_kernel)
   long part_stride;
@@ -172,6 +173,19 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
             if (p.bias) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
+            }
+            if (p.mask != nullptr && valid && res_ok) {      // fold mode, interior pixel: d relu -- before the residual joins
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + obase + c0);
+              const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+              const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
+              const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (!(__low2float(g0[e]) > 0.f)) v[2 * e] = 0.f;
+                if (!(__high2float(g0[e]) > 0.f)) v[2 * e + 1] = 0.f;
+                if (!(__low2float(g1[e]) > 0.f)) v[8 + 2 * e] = 0.f;
+                if (!(__high2float(g1[e]) > 0.f)) v[8 + 2 * e + 1] = 0.f;
+              }
             }
             if (use_res) {
               const uint4 r0 = gsel == 0 ? rb[0][j][0] : rb[1][j][0], r1 = gsel == 0 ? rb[0][j][1] : rb[1][j][1];
@@ -605,7 +619,7 @@ tc_splitk_reduce_kernel(const float* __restrict__ part, long stride, int nz, con
 // Split-K: when the tile count leaves most SMs idle (small maps / small per-GPU batch) or its last wave is mostly empty,
 // each tile's (tap, k-block) stage sequence is cut into S work items with fp32 partials in workspace.
 struct TcFwdPlan { int ok, BN, bw, bh, bb, tw, th, tb, ntiles, ksplit; };
-struct BgTcFold { int pt, pl, Hi, Wi; void* ring; };
+struct BgTcFold { int pt, pl, Hi, Wi; void* ring; const void* mask; };
 static TcFwdPlan tc_fwd_plan(const BgGeom& g) {
   TcFwdPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -764,7 +778,7 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
   const long ntiles = bg_cdiv((long)P.tw * P.th * P.tb, (long)P.mt) * g.nphase * (g.Co / BN);      // work items
   const long out_numel = (long)g.B * g.Ho * g.Wo * g.Co;
-  if (fold) { P.fold = 1; P.f_pt = fold->pt; P.f_pl = fold->pl; P.f_Hi = fold->Hi; P.f_Wi = fold->Wi; P.ring = (bf16*)fold->ring; }
+  if (fold) { P.fold = 1; P.f_pt = fold->pt; P.f_pl = fold->pl; P.f_Hi = fold->Hi; P.f_Wi = fold->Wi; P.ring = (bf16*)fold->ring; P.mask = (const bf16*)fold->mask; }
   P.ksplit = 1;
   if (pl.ksplit > 1 && !fold && !box_override && sk_ws && sk_bytes >= (size_t)pl.ksplit * out_numel * sizeof(float) &&
       (((uintptr_t)sk_ws) & 15) == 0) {

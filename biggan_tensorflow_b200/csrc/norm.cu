@@ -352,18 +352,20 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
   const int b = blockIdx.z;
   const long rpc = (HW + nchunk - 1) / nchunk;
   const long r0 = (long)blockIdx.y * rpc, r1 = min(HW, r0 + rpc);
-  float rs[V], gm[V], inv[V], shift[V], mu[V], m1[V], m2[V];
+  // dx = inv*g + kb + kx*x with inv = rstd*gamma, kx = -rstd^2*m2, kb = -rstd*m1 + mean*rstd^2*m2: four per-channel constants
+  // instead of seven, which leaves registers for two rows in flight per thread
+  float inv[V], shift[V], kb[V], kx[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) {
-    rs[e] = rsqrtf(var[c + e] + eps);
-    gm[e] = gamma[(long)b * gb_bstride + c + e];
-    mu[e] = mean[c + e];
-    inv[e] = rs[e] * gm[e];
-    shift[e] = beta[(long)b * gb_bstride + c + e] - mu[e] * inv[e];
-    m1[e] = (float)(s[c + e] / count);
-    m2[e] = (float)(s[C + c + e] / count);
+    const float rs = rsqrtf(var[c + e] + eps), mu = mean[c + e];
+    const float m1 = (float)(s[c + e] / count), m2 = (float)(s[C + c + e] / count);
+    inv[e] = rs * gamma[(long)b * gb_bstride + c + e];
+    shift[e] = beta[(long)b * gb_bstride + c + e] - mu * inv[e];
+    kx[e] = -rs * rs * m2;
+    kb[e] = -rs * m1 - mu * kx[e];
   }
   const long base = (long)b * HW * C + c;
+#pragma unroll 2
   for (long r = r0 + r_in; r < r1; r += R) {
     float xe[V], de[V];
     Vec<T>::ld(x, base + r * C, xe);
@@ -372,7 +374,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
     for (int e = 0; e < V; ++e) {
       float g = de[e];
       if (act == BG_ACT_RELU && !(xe[e] * inv[e] + shift[e] > 0.f)) g = 0.f;
-      de[e] = rs[e] * (gm[e] * g - m1[e] - (xe[e] - mu[e]) * rs[e] * m2[e]);
+      de[e] = fmaf(inv[e], g, fmaf(kx[e], xe[e], kb[e]));
     }
     Vec<T>::st(dx, base + r * C, de);
   }

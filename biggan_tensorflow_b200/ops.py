@@ -233,6 +233,11 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None, pre_relu=False
     call("bg_conv2d_fwd", desc_f, xin, wn.data, w_t, bias.data if bias is not None else None,
          residual.data if residual is not None else None, y.data, act, dt, wsf, wsf.numel() if nbf else 0, fs, stream(),
          flops=_conv_flops(desc), tag="conv_fwd" + _conv_tag(desc))
+    y.relu_out = act == _lib.ACT_RELU
+    # the gradient w.r.t. x passes a ReLU whose mask is (x.data > 0) -- x is a fused-ReLU output, or this conv applies the ReLU in
+    # its padding copy: the reflect-padded dgrad applies that mask where it produces the gradient (bg_conv2d_dgrad relu_mask)
+    reflect = (not desc.transposed and desc.pad_mode == _lib.PAD_REFLECT and (desc.pad_t | desc.pad_l | desc.pad_b | desc.pad_r) != 0)
+    mask_x = reflect and (pre_relu or x.relu_out) and os.environ.get("BG_NO_RELU_MASK_FUSION") != "1"
     if recording(x, wn, bias, residual):
         def bw():
             dy = y.grad
@@ -242,8 +247,8 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None, pre_relu=False
                 g = torch.empty_like(dy)
                 call("bg_tanh_bwd", y.data, dy, g, g.numel(), bg_dtype(g), stream())
                 dy = g
-            elif act == _lib.ACT_RELU:
-                g = torch.empty_like(dy)
+            elif act == _lib.ACT_RELU and not (y.n_contribs > 0 and y.n_masked == y.n_contribs):
+                g = torch.empty_like(dy)      # (skipped when every consumer's dgrad already applied this mask)
                 call("bg_relu_bwd", y.data, dy, g, g.numel(), bg_dtype(g), stream())
                 dy = g
             if residual is not None and residual.requires_grad:
@@ -263,19 +268,19 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None, pre_relu=False
                 call("bg_colsum", dy, dst, rows, desc.Co, dt, ws, ws.numel(), stream())
                 if fin:
                     fin()
-            if x.requires_grad and pre_relu:          # d relu(x) first, then the mask (what the stand-alone relu's entry did)
+            if x.requires_grad:
                 nb = query("bg_conv2d_dgrad_workspace_bytes", desc, dt)
                 ws = workspace(nb) if nb else None
-                dxr = torch.empty_like(x.data)
-                call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, None, dxr, dt, ws, ws.numel() if nb else 0, fs, stream(),
-                     flops=_conv_flops(desc), tag="conv_dgrad" + _conv_tag(desc))
-                dst, fin = grad_target(x)
-                call("bg_relu_bwd", x.data, dxr, dst, x.numel(), dt, stream())
-                if fin:
-                    fin()
-            elif x.requires_grad:
-                nb = query("bg_conv2d_dgrad_workspace_bytes", desc, dt)
-                ws = workspace(nb) if nb else None
+                mask = x.data if mask_x else None
+                if pre_relu and not mask_x:              # (fusion switched off) d relu(x) first, then the mask in its own pass
+                    dxr = torch.empty_like(x.data)
+                    call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, None, None, dxr, dt, ws, ws.numel() if nb else 0, fs, stream(),
+                         flops=_conv_flops(desc), tag="conv_dgrad" + _conv_tag(desc))
+                    dst, fin = grad_target(x)
+                    call("bg_relu_bwd", x.data, dxr, dst, x.numel(), dt, stream())
+                    if fin:
+                        fin()
+                    return
                 res = x.grad
                 if res is None:
                     dx = torch.empty_like(x.data)
@@ -283,8 +288,11 @@ def _conv_op(x, wn, bias, desc, act=_lib.ACT_NONE, residual=None, pre_relu=False
                     dx = res                      # fused accumulate in the dgrad epilogue
                 else:
                     dx = torch.empty_like(x.data)
-                call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, res, dx, dt, ws, ws.numel() if nb else 0, fs, stream(),
+                call("bg_conv2d_dgrad", desc, dy, wn.data, w_t, res, mask, dx, dt, ws, ws.numel() if nb else 0, fs, stream(),
                      flops=_conv_flops(desc), tag="conv_dgrad" + _conv_tag(desc))
+                x.n_contribs += 1
+                if mask_x and x.relu_out:
+                    x.n_masked += 1
                 x.grad, x.grad_owned, x.grad_set = dx, True, True
         record(bw)
     return y

@@ -51,7 +51,8 @@ def workspace(nbytes, slot=0):
 
 class Tensor:
     """NHWC activation / parameter handle.  `.data` is the device buffer (a torch tensor)."""
-    __slots__ = ("data", "grad", "requires_grad", "name", "grad_view", "grad_set", "grad_owned", "aux")
+    __slots__ = ("data", "grad", "requires_grad", "name", "grad_view", "grad_set", "grad_owned", "aux", "relu_out", "n_contribs",
+                 "n_masked")
 
     def __init__(self, data, requires_grad=False, name=None):
         self.data = data
@@ -62,6 +63,12 @@ class Tensor:
         self.grad_set = False
         self.grad_owned = True     # False while .grad aliases a buffer another tensor may also hold
         self.aux = None
+        # ReLU-backward fusion (ops._conv_op): `relu_out` marks the output of a conv with a fused ReLU; every gradient
+        # contribution is counted, and those a consumer's dgrad already multiplied by the mask (data > 0) separately -- the
+        # producer skips its own mask pass exactly when all contributions arrived masked
+        self.relu_out = False
+        self.n_contribs = 0
+        self.n_masked = 0
 
     @property
     def shape(self):
@@ -129,6 +136,7 @@ def grad_target(t, dtype=None):
 
     First contribution: written in place (into the parameter's arena slice when it has one).
     Later contributions: written to a temporary and accumulated with bg_add."""
+    t.n_contribs += 1
     if t.grad_view is not None and not t.grad_set:
         t.grad_set = True
         t.grad = t.grad_view
@@ -146,6 +154,7 @@ def grad_target(t, dtype=None):
 def accumulate_grad(t, g, own=False):
     """t.grad (+)= g.  With own=True the buffer g may be adopted as t.grad and mutated later;
     otherwise it is only borrowed (copied on the next accumulation)."""
+    t.n_contribs += 1
     if t.grad_view is not None and not t.grad_set:
         t.grad_view.copy_(g.reshape(t.grad_view.shape))
         t.grad_set = True

@@ -102,11 +102,14 @@ int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const voi
                   const float* bias, const void* residual, void* y, int act, int dtype,
                   void* ws, size_t ws_bytes, int force_simt, void* stream);
 /* dx = conv_dgrad(dy) (+ residual).  For pad_mode REFLECT with padding the caller gets the gradient
- * w.r.t. the *unpadded* x (the reflect-pad adjoint is folded inside; ws holds the padded gradient). */
+ * w.r.t. the *unpadded* x (the reflect-pad adjoint is folded inside; ws holds the padded gradient).
+ * relu_mask (may be NULL; reflect-padded convs only; same shape and dtype as dx): dx = residual + (relu_mask > 0 ?
+ * conv_dgrad(dy) : 0) -- the backward of a ReLU sitting on the conv's input (ops.py:297-301: act -> conv in the
+ * residual blocks) is applied where the gradient is produced instead of in a pass of its own. */
 size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype);
 int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void* w, const void* w_t,
-                    const void* residual, void* dx, int dtype, void* ws, size_t ws_bytes,
-                    int force_simt, void* stream);
+                    const void* residual, const void* relu_mask, void* dx, int dtype, void* ws,
+                    size_t ws_bytes, int force_simt, void* stream);
 /* dw (fp32, TF-native layout of w) = wgrad(x, dy); deterministic split-K through ws. */
 size_t bg_conv2d_wgrad_workspace_bytes(const bg_conv_desc* d, int dtype);
 int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x, const void* dy, float* dw, int dtype,

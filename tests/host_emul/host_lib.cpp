@@ -272,12 +272,15 @@ extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x_, const void* 
   }
   return BG_OK;
 }
-extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy_, const void* w_, const void*, const void* res_, void* dx_, int dtype, void*,
-                               size_t, int, void*) {
+extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy_, const void* w_, const void*, const void* res_, const void* mask_, void* dx_,
+                               int dtype, void*, size_t, int, void*) {
   DTYPE_OK(dtype);
   const long nxe = (long)d->B * d->Hi * d->Wi * d->Ci, nye = (long)d->B * d->Ho * d->Wo * d->Co, nwe = (long)d->kh * d->kw * d->Ci * d->Co;
-  In gi(dy_, nye, dtype), wi(w_, nwe, dtype), ri(res_, nxe, dtype); Out xo(dx_, nxe, dtype); dy_ = gi.p; w_ = wi.p; res_ = ri.p; dx_ = xo.p;
-  const float *dy = (const float*)dy_, *w = (const float*)w_, *res = (const float*)res_;
+  if (mask_ && !(d->pad_mode == BG_PAD_REFLECT && !d->transposed && (d->pad_t | d->pad_l | d->pad_b | d->pad_r))) {
+    bg_set_error("bg_conv2d_dgrad: relu_mask is implemented for reflect-padded convs"); return BG_ERR_UNSUPPORTED;
+  }
+  In gi(dy_, nye, dtype), wi(w_, nwe, dtype), ri(res_, nxe, dtype), mi(mask_, nxe, dtype); Out xo(dx_, nxe, dtype); dy_ = gi.p; w_ = wi.p; res_ = ri.p; dx_ = xo.p;
+  const float *dy = (const float*)dy_, *w = (const float*)w_, *res = (const float*)res_, *mask = mi.p;
   float* dx = (float*)dx_;
   const long nx = (long)d->B * d->Hi * d->Wi * d->Ci;
   std::vector<double> acc(nx, 0.0);
@@ -290,7 +293,7 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy_, const voi
       for (int co = 0; co < d->Co; ++co) { const float* wp = w + widx(d, ky, kx, 0, co); const double gv = gp[co]; for (int ci = 0; ci < d->Ci; ++ci) ap[ci] += gv * wp[ci]; }
     }
   });
-  for (long i = 0; i < nx; ++i) dx[i] = (float)acc[i] + (res ? res[i] : 0.f);
+  for (long i = 0; i < nx; ++i) dx[i] = ((mask && !(mask[i] > 0.f)) ? 0.f : (float)acc[i]) + (res ? res[i] : 0.f);
   return BG_OK;
 }
 extern "C" int bg_conv2d_wgrad(const bg_conv_desc* d, const void* x_, const void* dy_, float* dw, int dtype, void*, size_t, int, void*) {

@@ -20,6 +20,7 @@ ap.add_argument("--stride", type=int, default=1)
 ap.add_argument("--deconv", action="store_true")
 ap.add_argument("--pad", default="reflect", choices=["reflect", "zero"])
 ap.add_argument("--residual", action="store_true", help="fused residual add (fwd) / gradient accumulate (dgrad)")
+ap.add_argument("--relu-mask", action="store_true", help="dgrad of a reflect-padded conv: fused ReLU mask of the conv's input")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
 args = ap.parse_args()
@@ -66,7 +67,8 @@ if args.op == "fwd":
 elif args.op == "dgrad":
     ws, n = ws_for("bg_conv2d_dgrad_workspace_bytes")
     res = torch.randn_like(dx) if args.residual else None
-    fn = lambda: call("bg_conv2d_dgrad", d, dy, w, w_t, res, dx, dt, ws if n else None, n, 0, stream())
+    mask = torch.randn_like(dx) if args.relu_mask else None
+    fn = lambda: call("bg_conv2d_dgrad", d, dy, w, w_t, res, mask, dx, dt, ws if n else None, n, 0, stream())
 else:
     ws, n = ws_for("bg_conv2d_wgrad_workspace_bytes")
     fn = lambda: call("bg_conv2d_wgrad", d, x, dy, dw, dt, ws, ws.numel(), 0, stream())
