@@ -742,7 +742,9 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     const long mma_cycles = (long)min_taps2 * bg_cdiv(g.Ci, 16) * (BN <= 128 ? 60 : BN / 2);   // issue-rate model of one tile
     const int half_bytes = ((BN / 16 + 1) / 2) * 4096;
     // (not in fold mode: boxes starting at negative coordinates are fine for TMA loads but fault on stores -- measured)
-    if (ts_env > 0 && !fold && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < 3L * 16 * BN) &&
+    static int ts_k = -1;                         // threshold of the issue-rate model, in units of 16 x BN cycles (tuning knob)
+    if (ts_k < 0) { const char* e = getenv("BG_TC_TMA_STORE_K"); ts_k = e ? atoi(e) : 3; if (ts_k < 1) ts_k = 3; }
+    if (ts_env > 0 && !fold && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < (long)ts_k * 16 * BN) &&
         (ring_budget - 2 * half_bytes) / stage_bytes >= 3) {
       P.tma_store = 1;
       P.ostage_half = (uint32_t)half_bytes;
