@@ -50,9 +50,10 @@ def leaf_stand_ins(monkeypatch):
         return torch.relu(y) if a == _lib.ACT_RELU else (torch.tanh(y) if a == _lib.ACT_TANH else y)
 
     def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True, scope='conv_0', _residual=None, _act=_lib.ACT_NONE,
-             _pad_cout_to=0):
+             _pad_cout_to=0, _pre_relu=False):
         sync()
-        y = R.conv(rs, x.data, channels, opt, kernel, stride, pad, dilation, use_bias, scope)
+        xin = torch.relu(x.data) if _pre_relu else x.data       # conv(relu(x)): the activation resblock_down fuses into its first conv
+        y = R.conv(rs, xin, channels, opt, kernel, stride, pad, dilation, use_bias, scope)
         return T(act(y if _residual is None else y + _residual.data, _act))
 
     def deconv(x, channels, opt, kernel=4, stride=2, padding='SAME', use_bias=True, scope='deconv_0', _residual=None):
