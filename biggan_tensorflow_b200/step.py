@@ -98,14 +98,20 @@ class Trainer:
         if self.world > 1 and dev.type == "cuda" and self.peer is None and os.environ.get("BG_BN_SYNC", "p2p") == "p2p":
             # cross-replica BN statistics: one-shot all-reduce over NVLink peer memory (csrc/comm.cu) instead of NCCL
             from .comm import MAX_DOUBLES, PeerComm
-            self.peer = PeerComm(self.rank, self.world, self.pg)
-            nccl_sum = ops.dist.all_reduce_sum
+            peer = PeerComm(self.rank, self.world, self.pg)          # collective; never raises on a local failure
+            if peer.error is not None:
+                print("[biggan_b200] rank %d: peer-memory exchange unavailable (%r)" % (self.rank, peer.error))
+            if peer.agree():                                         # every rank takes the same decision
+                self.peer = peer
+                nccl_sum = ops.dist.all_reduce_sum
 
-            def peer_sum(buf):
-                if buf.dtype == torch.float64 and buf.numel() <= MAX_DOUBLES:
-                    return self.peer.all_reduce_sum(buf)
-                return nccl_sum(buf)
-            ops.dist.all_reduce_sum = peer_sum
+                def peer_sum(buf):
+                    if buf.dtype == torch.float64 and buf.numel() <= MAX_DOUBLES:
+                        return self.peer.all_reduce_sum(buf)
+                    return nccl_sum(buf)
+                ops.dist.all_reduce_sum = peer_sum
+            else:                                                    # BN statistics stay on NCCL
+                peer.close()
         z = torch.zeros(2, 1, 1, cfg.z_dim, device=dev)
         cls = torch.zeros(2, max(cfg.n_labels, 1), device=dev)
         set_store(self.store)
