@@ -59,7 +59,11 @@ __device__ __forceinline__ void issue_s_dp(uint32_t tS, uint32_t tdP, uint32_t Q
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdParams p) {
+// 18 warps: TMA producer, MMA issuer, and SIXTEEN softmax warps -- four per TMEM lane quarter, each taking 32 of the 128 key
+// columns of a block.  The P / dS production (exp, two bf16 packs, swizzled stores per score) is what bounds this kernel
+// (12-18 % tensor-pipe activity); with 8 warps it took ~2x the MMA time of a (query tile, key block) pair.
+#define AB_SW 16                                   // softmax warps
+__global__ void __launch_bounds__(64 + 32 * AB_SW, 1) attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t kv_full, qd_full[2], qd_empty[2], s_full, s_empty, pds_full, pds_empty, acc_full;
   __shared__ uint32_t tmem_slot;
@@ -73,8 +77,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.domap);
     mbar_init(smem_u32(&kv_full), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&qd_full[i]), 1); mbar_init(smem_u32(&qd_empty[i]), 1); }
-    mbar_init(smem_u32(&s_full), 1); mbar_init(smem_u32(&s_empty), 8);
-    mbar_init(smem_u32(&pds_full), 8); mbar_init(smem_u32(&pds_empty), 1); mbar_init(smem_u32(&acc_full), 1);
+    mbar_init(smem_u32(&s_full), 1); mbar_init(smem_u32(&s_empty), AB_SW);
+    mbar_init(smem_u32(&pds_full), AB_SW); mbar_init(smem_u32(&pds_empty), 1); mbar_init(smem_u32(&acc_full), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
@@ -144,10 +148,24 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
     }
   } else {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;          // two warps per TMEM lane quarter split the 128 key columns
+    const int part = (warp - 2) >> 2;          // AB_SW / 4 warps per TMEM lane quarter split the 128 key columns
+    constexpr int NPART = AB_SW / 4, PCOLS = AB_T / NPART;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
+    // accumulator drains (dQ partials, dV, dK): 16-column chunks dealt round-robin to the warps of a lane quarter
+    auto drain_dq = [&](int qp) {
+      for (int c0 = part * 16; c0 < p.dq; c0 += NPART * 16) {
+        uint32_t r[16];
+        tmem_ld_x16(tdQ + lane_base + (uint32_t)c0, r);
+        if (qp < p.Nq) {
+          float4* o = reinterpret_cast<float4*>(p.dq_part + (((long)j * p.B + b) * p.Nq + qp) * p.dq + c0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+        }
+      }
+    };
     for (int i = 0; i < p.nqt; ++i) {
       const int qi = i * AB_T + row;
       const bool qv = qi < p.Nq;
@@ -159,22 +177,11 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
       mbar_wait(smem_u32(&pds_empty), (uint32_t)((i & 1) ^ 1));
       if (p.dq_part != nullptr && i > 0) {           // the MMAs of tile i - 1 are complete: its dQ partial leaves TMEM before
         tc_fence_after();                            // tile i's dS (and with it the next dQ MMA group) is released
-        const int qp = (i - 1) * AB_T + row;
-        const int qsplit = ((p.dq / 16 + 1) / 2) * 16;
-        for (int c0 = half ? qsplit : 0; c0 < (half ? p.dq : qsplit); c0 += 16) {
-          uint32_t r[16];
-          tmem_ld_x16(tdQ + lane_base + (uint32_t)c0, r);
-          if (qp < p.Nq) {
-            float4* o = reinterpret_cast<float4*>(p.dq_part + (((long)j * p.B + b) * p.Nq + qp) * p.dq + c0);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
-          }
-        }
+        drain_dq((i - 1) * AB_T + row);
         tc_fence_before();
       }
-      for (int cc = 0; cc < 64; cc += 16) {
-        const int c0 = half * 64 + cc;
+      for (int cc = 0; cc < PCOLS; cc += 16) {
+        const int c0 = part * PCOLS + cc;
         uint32_t rs[16], rp[16], pk[8], dk[8];
         tmem_ld_x16(tS + lane_base + (uint32_t)c0, rs);
         tmem_ld_x16(tdP + lane_base + (uint32_t)c0, rp);
@@ -202,28 +209,14 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_dkdv_kernel(const __grid_cons
     }
     mbar_wait(smem_u32(&acc_full), 0);
     tc_fence_after();
-    if (p.dq_part != nullptr) {                      // dQ partial of the last query tile
-      const int qp = (p.nqt - 1) * AB_T + row;
-      const int qsplit = ((p.dq / 16 + 1) / 2) * 16;
-      for (int c0 = half ? qsplit : 0; c0 < (half ? p.dq : qsplit); c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_x16(tdQ + lane_base + (uint32_t)c0, r);
-        if (qp < p.Nq) {
-          float4* o = reinterpret_cast<float4*>(p.dq_part + (((long)j * p.B + b) * p.Nq + qp) * p.dq + c0);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            o[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
-        }
-      }
-    }
+    if (p.dq_part != nullptr) drain_dq((p.nqt - 1) * AB_T + row);      // dQ partial of the last query tile
     const int key = j * AB_T + row;          // accumulator rows are keys
-    const int vsplit = ((p.dv / 16 + 1) / 2) * 16, ksplit = ((p.dq / 16 + 1) / 2) * 16;
-    for (int c0 = half ? vsplit : 0; c0 < (half ? p.dv : vsplit); c0 += 16) {
+    for (int c0 = part * 16; c0 < p.dv; c0 += NPART * 16) {
       uint32_t r[16];
       tmem_ld_x16(tdV + lane_base + (uint32_t)c0, r);
       if (key < p.Nk) store_acc_bf16(p.dv_out + ((long)b * p.Nk + key) * p.dv + c0, r);
     }
-    for (int c0 = half ? ksplit : 0; c0 < (half ? p.dq : ksplit); c0 += 16) {
+    for (int c0 = part * 16; c0 < p.dq; c0 += NPART * 16) {
       uint32_t r[16];
       tmem_ld_x16(tdK + lane_base + (uint32_t)c0, r);
       if (key < p.Nk) store_acc_bf16(p.dk_out + ((long)b * p.Nk + key) * p.dq + c0, r);
@@ -423,7 +416,7 @@ extern "C" int bg_attn2_bwd(const void* q, const void* k, const void* v, const v
   const size_t vb = (size_t)P.nvblk * 16384;
   const size_t smem_kv = 16384 + vb + 2 * 16384 + 2 * vb + 32768 + 32768 + 1024;
   const size_t smem_q = 16384 + vb + 2 * 16384 + 2 * vb + 32768 + 1024;
-  attn_bwd_dkdv_kernel<<<dim3((unsigned)P.nkb, (unsigned)B), 320, smem_kv, st>>>(P);
+  attn_bwd_dkdv_kernel<<<dim3((unsigned)P.nkb, (unsigned)B), 64 + 32 * AB_SW, smem_kv, st>>>(P);
   BG_LAUNCH_CHECK();
   if (fuse_dq) {
     const long n8 = part_stride / 8;
