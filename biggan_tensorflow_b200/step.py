@@ -167,6 +167,7 @@ class Trainer:
             v.grad = None
             v.grad_set = False
             v.grad_owned = True
+            v.n_contribs = v.n_masked = 0
         self.store.begin_phase()
         clear_tape()
         # every forward of a network advances its u once per phase.  In the G phase D's spectral norm waits until the
