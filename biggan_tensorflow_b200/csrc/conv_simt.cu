@@ -625,7 +625,9 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool padded = dgrad_padded(d);
-  BG_REQUIRE(!relu_mask || padded, BG_ERR_UNSUPPORTED, "bg_conv2d_dgrad: relu_mask is implemented for reflect-padded convs (the fold pass applies it)");
+  // relu_mask: reflect-padded convs (the fold pass applies it) or, without padding, the tensor-core kernel's epilogue (bf16)
+  BG_REQUIRE(!relu_mask || padded || (dtype == BG_BF16 && !force_simt && !d->transposed && !(d->pad_t | d->pad_l | d->pad_b | d->pad_r)),
+             BG_ERR_UNSUPPORTED, "bg_conv2d_dgrad: relu_mask needs a reflect-padded conv, or an unpadded conv on the bf16 tensor-core path");
   if (padded) BG_REQUIRE(ws && ws_bytes >= dgrad_padded_bytes(d, dtype), BG_ERR_WORKSPACE, "dgrad workspace too small");
   void* gout = padded ? ws : dx;
   const void* gres = padded ? nullptr : residual;
@@ -661,11 +663,14 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
           return BG_OK;
         }
       }
-      rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, gres, gout, BG_ACT_NONE, sk, sk_bytes, nullptr, st, &taken);
+      BgTcFold mask_only = {0, 0, 0, 0, nullptr, relu_mask};
+      rc = bg_tc_fwd_launch(g, dy, g.Hi, g.Wi, 0, 0, wk, nullptr, gres, gout, BG_ACT_NONE, sk, sk_bytes, (relu_mask && !padded) ? &mask_only : nullptr,
+                            st, &taken);
       if (rc) return rc;
       done = taken != 0;
     }
   }
+  BG_REQUIRE(done || !relu_mask || padded, BG_ERR_UNSUPPORTED, "bg_conv2d_dgrad: relu_mask on an unpadded conv was not taken by the tensor-core kernel");
   if (!done) {
     BG_DISPATCH_DTYPE(dtype, T, rc = launch_fwd_type<T>(g, (const T*)dy, (const T*)w, nullptr, (const T*)gres, (T*)gout, BG_ACT_NONE, st,
                                                         padded ? nullptr : ws, padded ? 0 : ws_bytes));

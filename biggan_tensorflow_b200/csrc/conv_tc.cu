@@ -67,7 +67,24 @@ struct TcFwdParams {
   uint32_t ostage_half;      // bytes per epilogue half and set
   int ostage_sets;           // 1, or 2 when the ring can spare the memory (tile i's bulk stores overlap the staging of tile i + 1)
   CUtensorMap omap[4];       // per phase: the output sampled with step `ostep` from (oy0, ox0); box (16, bw, bh, bb), no swizzle
+  int o_di[4], o_dj[4];      // fold mode: omap covers the UNPADDED tensor from the phase's first interior row / column; tile row i0 is
+                             //   its row i0 - o_di (tiles that are interior pixels only take the bulk-store path, the others store directly)
+  int aux_prefetch;          // L2 prefetch of the next tile's residual / mask rows (A/B knob BG_TC_AUX_PREFETCH)
+  int aux_batch;             // BN <= 96: all residual / mask vectors of a half-tile requested up front (A/B knob BG_TC_AUX_BATCH)
+  FastDiv fd_S, fd_ntn, fd_tpp, fd_tw, fd_th;   // per-tile index decode without runtime divisions (ksplit, n-tiles, items per phase, tw, th)
 };
+
+// tile index within a phase -> first pixel of its box
+__device__ __forceinline__ void tc_tile_origin(const TcFwdParams& p, int t, int& j0, int& i0, int& b0) {
+  int q = fast_div(t, p.fd_tw); j0 = (t - q * p.tw) * p.bw; t = q;
+  q = fast_div(t, p.fd_th); i0 = (t - q * p.th) * p.bh; b0 = q * p.bb;
+}
+// work item -> (split, n-tile, phase, item within the phase)
+__device__ __forceinline__ void tc_item_decode(const TcFwdParams& p, int wi, int ntn, int tpp_items, int& split, int& nt, int& phase, int& ti) {
+  const int item = fast_div(wi, p.fd_S); split = wi - item * p.ksplit;
+  const int q = fast_div(item, p.fd_ntn); nt = item - q * ntn;
+  phase = fast_div(q, p.fd_tpp); ti = q - phase * tpp_items;
+}
 
 // Epilogue warps (8): drain the double-buffered TMEM accumulator of every tile this CTA owns:
 // tcgen05.ld -> bias / residual / activation -> bf16 -> global.  Shared by the plain and the halo kernel.
@@ -80,19 +97,16 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
     const int cbeg = half ? csplit : 0, cend = half ? p.BN : csplit;
     const int row = q * 32 + lane;
     const int w = row % p.bw, h = (row / p.bw) % p.bh, bl = row / (p.bw * p.bh);
-    int lt = 0;
+    int lt = 0, nstored = 0;
     const int S = p.ksplit;
     const int MT = p.mt;
     const int tpp_items = (tiles_pp + MT - 1) / MT;          // work items per phase and n-tile (ntiles counts items)
     for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
-      const int item = wi / S, split = wi - item * S;
-      const int nt = item % ntn; int ti = item / ntn;
-      const int phase = ti / tpp_items; ti -= phase * tpp_items;
+      int split, nt, phase, ti;
+      tc_item_decode(p, wi, ntn, tpp_items, split, nt, phase, ti);
      for (int m = 0; m < MT; ++m) {
-      int t = ti * MT + m;                                   // a tile index past the phase decodes to b0 >= B: nothing valid, boxes clipped
-      const int j0 = (t % p.tw) * p.bw; t /= p.tw;
-      const int i0 = (t % p.th) * p.bh; t /= p.th;
-      const int b0 = t * p.bb;
+      int j0, i0, b0;                                        // a tile index past the phase decodes to b0 >= B: nothing valid, boxes clipped
+      tc_tile_origin(p, ti * MT + m, j0, i0, b0);
       const int n0 = nt * p.BN;
       const int pi = i0 + h, pj = j0 + w, b = b0 + bl;
       const bool valid = (b < p.B) && (pi < p.Hp[phase]) && (pj < p.Wp[phase]);
@@ -131,96 +145,180 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         continue;
       }
       const bool use_res = (p.residual != nullptr) && valid && res_ok;
-      const bool tstore = p.tma_store != 0;
+      const bool use_mask = (p.mask != nullptr) && valid && res_ok;      // fold mode, interior pixel: d relu
+      bool tstore = p.tma_store != 0;
+      if (tstore && p.fold) {                    // fold mode: bulk stores only for tiles made of interior pixels (tile-uniform)
+        const int y_lo = p.oy0[phase] + i0 * p.ostep - p.f_pt, y_hi = y_lo + (p.bh - 1) * p.ostep;
+        const int x_lo = p.ox0[phase] + j0 * p.ostep - p.f_pl, x_hi = x_lo + (p.bw - 1) * p.ostep;
+        tstore = y_lo >= 0 && y_hi < p.f_Hi && x_lo >= 0 && x_hi < p.f_Wi;
+      }
+      // L2 prefetch of the NEXT work item's residual / mask rows (same m): by the time that tile's epilogue asks for them, the
+      // lines have arrived from DRAM and the demand loads pay an L2 hit instead of a DRAM round trip per tile
+      if (p.aux_prefetch && (p.residual != nullptr || p.mask != nullptr) && wi + (int)gridDim.x < ntiles) {
+        int split2, nt2, phase2, ti2, j2, i2, b2;
+        tc_item_decode(p, wi + (int)gridDim.x, ntn, tpp_items, split2, nt2, phase2, ti2);
+        tc_tile_origin(p, ti2 * MT + m, j2, i2, b2);
+        const int pi2 = i2 + h, pj2 = j2 + w, bb2 = b2 + bl;
+        if ((bb2 < p.B) && (pi2 < p.Hp[phase2]) && (pj2 < p.Wp[phase2])) {
+          const int oy2 = p.oy0[phase2] + pi2 * p.ostep, ox2 = p.ox0[phase2] + pj2 * p.ostep;
+          long ob2 = (((long)bb2 * p.Ho + oy2) * p.Wo + ox2) * p.Co;
+          bool ok2 = true;
+          if (p.fold) {
+            const int iy = oy2 - p.f_pt, ix = ox2 - p.f_pl;
+            if (iy >= 0 && iy < p.f_Hi && ix >= 0 && ix < p.f_Wi) ob2 = (((long)bb2 * p.f_Hi + iy) * p.f_Wi + ix) * p.Co;
+            else ok2 = false;
+          }
+          const int nbytes = (cend - cbeg) * 2;
+          if (ok2 && nbytes > 0) {
+            ob2 += nt2 * p.BN + cbeg;
+            for (int off = 0; off < nbytes + 112; off += 128) {       // every 128-byte line the row segment touches
+              const int o2 = min(off, nbytes - 16);
+              if (p.residual != nullptr) prefetch_l2(reinterpret_cast<const char*>(p.residual + ob2) + o2);
+              if (p.mask != nullptr) prefetch_l2(reinterpret_cast<const char*>(p.mask + ob2) + o2);
+            }
+          }
+        }
+      }
       // staging slabs are double-buffered per half: tile lt writes set lt & 1 while the bulk stores of tile lt - 1 still read
       // the other set; the stores of tile lt - 2 (same set) must have finished reading
-      const uint32_t hset = smem_base + p.ostage_off + (uint32_t)(p.ostage_sets * half + (p.ostage_sets == 2 ? ((lt * MT + m) & 1) : 0)) * p.ostage_half;
+      const uint32_t hset = smem_base + p.ostage_off + (uint32_t)(p.ostage_sets * half + (p.ostage_sets == 2 ? (nstored & 1) : 0)) * p.ostage_half;
+      if (tstore) ++nstored;                     // sets alternate per BULK-STORED tile (direct tiles of the fold mode in between commit nothing)
       const uint32_t hb = hset + (uint32_t)row * 32u;
-      if (tstore) {
-        if ((ew & 3) == 0 && elect_one_sync()) {                            // same elected lane as the one issuing the stores
-          if (p.ostage_sets == 2) tma_store_wait_read1(); else tma_store_wait_read0();
-        }
-        named_bar_sync(1u + (uint32_t)half, 128u);
-      }
-      uint4 rb[2][2][2];
-      auto load_group = [&](int g, int cg) {
+      // one 16-channel slab: accumulator -> bias -> d relu mask -> residual -> activation -> bf16 -> staging slab / global
+      auto do_slab = [&](int c0, const uint4& r0, const uint4& r1, const uint4& m0, const uint4& m1) {
+        uint32_t r[16];
+        tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
+        if (valid || tstore) {
+          float v[16];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (use_res && cg + j * 16 < cend) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg + j * 16);
-            rb[g][j][0] = __ldg(rp);
-            rb[g][j][1] = __ldg(rp + 1);
-          }
-      };
-      load_group(0, cbeg);
-      if (m == 0) {
-        mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
-        tc_fence_after();
-      }
-      int gsel = 0;
-      for (int cg = cbeg; cg < cend; cg += 32, gsel ^= 1) {
-        if (gsel == 0) load_group(1, cg + 32); else load_group(0, cg + 32);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c0 = cg + j * 16;
-          if (c0 >= cend) break;
-          uint32_t r[16];
-          tmem_ld_x16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r);
-          if (valid || tstore) {
-            float v[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-            if (p.bias) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] += p.bias[n0 + c0 + e];
-            }
-            if (p.mask != nullptr && valid && res_ok) {      // fold mode, interior pixel: d relu -- before the residual joins
-              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + obase + c0);
-              const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-              const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
-              const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (!(__low2float(g0[e]) > 0.f)) v[2 * e] = 0.f;
-                if (!(__high2float(g0[e]) > 0.f)) v[2 * e + 1] = 0.f;
-                if (!(__low2float(g1[e]) > 0.f)) v[8 + 2 * e] = 0.f;
-                if (!(__high2float(g1[e]) > 0.f)) v[8 + 2 * e + 1] = 0.f;
-              }
-            }
-            if (use_res) {
-              const uint4 r0 = gsel == 0 ? rb[0][j][0] : rb[1][j][0], r1 = gsel == 0 ? rb[0][j][1] : rb[1][j][1];
-              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
-                v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
-              }
-            }
-            if (p.act == BG_ACT_RELU) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-            } else if (p.act == BG_ACT_TANH) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
-            }
-            uint4 o0, o1;
-            __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-            __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-              q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+              const float4 bv = __ldg(bp + e);
+              v[4 * e] += bv.x; v[4 * e + 1] += bv.y; v[4 * e + 2] += bv.z; v[4 * e + 3] += bv.w;
             }
-            if (tstore) {
-              const uint32_t a = hb + (uint32_t)((c0 - cbeg) >> 4) * 4096u;
-              st_shared_v4(a, o0);
-              st_shared_v4(a + 16u, o1);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(outb + obase + c0);
-              op[0] = o0;
-              op[1] = o1;
+          }
+          if (use_mask) {                                    // before the residual joins
+            const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&m0);
+            const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&m1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (!(__low2float(g0[e]) > 0.f)) v[2 * e] = 0.f;
+              if (!(__high2float(g0[e]) > 0.f)) v[2 * e + 1] = 0.f;
+              if (!(__low2float(g1[e]) > 0.f)) v[8 + 2 * e] = 0.f;
+              if (!(__high2float(g1[e]) > 0.f)) v[8 + 2 * e + 1] = 0.f;
             }
+          }
+          if (use_res) {
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] += __low2float(h0[e]); v[2 * e + 1] += __high2float(h0[e]);
+              v[8 + 2 * e] += __low2float(h1[e]); v[8 + 2 * e + 1] += __high2float(h1[e]);
+            }
+          }
+          if (p.act == BG_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (p.act == BG_ACT_TANH) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fast_tanh(v[e]);
+          }
+          uint4 o0, o1;
+          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+          }
+          if (tstore) {
+            const uint32_t a = hb + (uint32_t)((c0 - cbeg) >> 4) * 4096u;
+            st_shared_v4(a, o0);
+            st_shared_v4(a + 16u, o1);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(outb + obase + c0);
+            op[0] = o0;
+            op[1] = o1;
+          }
+        }
+      };
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      if (p.aux_batch && cend - cbeg <= 48) {
+        // BN <= 96: EVERY residual / mask vector of this half-tile is requested up front (3 slabs x 2 x 16 B each), before the
+        // staging-set and accumulator waits -- one global-memory latency per tile instead of one per slab (ncu on the 96-channel
+        // fold-mode dgrads: 62 % of the epilogue warps' samples were long-scoreboard stalls on the mask loads, issued one slab at a time)
+        uint4 ra[3][2], ma[3][2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          ra[i][0] = ra[i][1] = ma[i][0] = ma[i][1] = z4;
+          const int c0 = cbeg + 16 * i;
+          if (c0 < cend) {
+            if (use_res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+              ra[i][0] = __ldg(rp); ra[i][1] = __ldg(rp + 1);
+            }
+            if (use_mask) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + obase + c0);
+              ma[i][0] = __ldg(mp); ma[i][1] = __ldg(mp + 1);
+            }
+          }
+        }
+        if (tstore) {
+          if ((ew & 3) == 0 && elect_one_sync()) {                          // same elected lane as the one issuing the stores
+            if (p.ostage_sets == 2) tma_store_wait_read1(); else tma_store_wait_read0();
+          }
+          named_bar_sync(1u + (uint32_t)half, 128u);
+        }
+        if (m == 0) {
+          mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int c0 = cbeg + 16 * i;
+          if (c0 < cend) do_slab(c0, ra[i][0], ra[i][1], ma[i][0], ma[i][1]);
+        }
+      } else {
+        // BN > 96 (long main loops): residual in groups of 2 x 16 channels, one group ahead of its use; the first group is in
+        // flight while this warp still waits for the accumulator
+        uint4 rb[2][2][2];
+        auto load_group = [&](int g, int cg) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (use_res && cg + j * 16 < cend) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg + j * 16);
+              rb[g][j][0] = __ldg(rp);
+              rb[g][j][1] = __ldg(rp + 1);
+            }
+        };
+        load_group(0, cbeg);
+        if (tstore) {
+          if ((ew & 3) == 0 && elect_one_sync()) {
+            if (p.ostage_sets == 2) tma_store_wait_read1(); else tma_store_wait_read0();
+          }
+          named_bar_sync(1u + (uint32_t)half, 128u);
+        }
+        if (m == 0) {
+          mbar_wait(smem_u32(&tfull_bar[buf]), (uint32_t)((lt >> 1) & 1));
+          tc_fence_after();
+        }
+        int gsel = 0;
+        for (int cg = cbeg; cg < cend; cg += 32, gsel ^= 1) {
+          if (gsel == 0) load_group(1, cg + 32); else load_group(0, cg + 32);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c0 = cg + j * 16;
+            if (c0 >= cend) break;
+            uint4 m0 = z4, m1 = z4;
+            if (use_mask) {
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + obase + c0);
+              m0 = __ldg(mp); m1 = __ldg(mp + 1);
+            }
+            do_slab(c0, gsel == 0 ? rb[0][j][0] : rb[1][j][0], gsel == 0 ? rb[0][j][1] : rb[1][j][1], m0, m1);
           }
         }
       }
@@ -234,7 +332,8 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         named_bar_sync(1u + (uint32_t)half, 128u);
         if ((ew & 3) == 0 && elect_one_sync()) {
           uint32_t src = hset;
-          for (int c0 = cbeg; c0 < cend; c0 += 16, src += 4096u) tma_store_4d(&p.omap[phase], src, n0 + c0, j0, i0, b0);
+          for (int c0 = cbeg; c0 < cend; c0 += 16, src += 4096u)
+            tma_store_4d(&p.omap[phase], src, n0 + c0, j0 - p.o_dj[phase], i0 - p.o_di[phase], b0);
           tma_store_commit();
         }
       }
@@ -296,21 +395,15 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
           for (int kb = 0; kb < p.nkb; ++kb, dst += wtile) tma_load_3d(dst, &p.bmap, bb, kb * 64, 0, w);
       }
       for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x) {
-        const int item = wi / S, split = wi - item * S;
-        const int nt = item % ntn; int ti = item / ntn;
-        const int phase = ti / tpp_items; ti -= phase * tpp_items;
-        int t = ti * MT;
-        const int j0 = (t % p.tw) * p.bw; t /= p.tw;
-        const int i0 = (t % p.th) * p.bh; t /= p.th;
-        const int b0 = t * p.bb;
-        int t1 = ti * MT + 1;                                  // second tile of a pair (past the phase: b >= B, zero fill)
-        const int j1 = (t1 % p.tw) * p.bw; t1 /= p.tw;
-        const int i1 = (t1 % p.th) * p.bh; t1 /= p.th;
-        const int b1 = t1 * p.bb;
+        int split, nt, phase, ti;
+        tc_item_decode(p, wi, ntn, tpp_items, split, nt, phase, ti);
+        int j0, i0, b0, j1 = 0, i1 = 0, b1 = 0;
+        tc_tile_origin(p, ti * MT, j0, i0, b0);
+        if (MT == 2) tc_tile_origin(p, ti * MT + 1, j1, i1, b1);   // second tile of a pair (past the phase: b >= B, zero fill)
         const int n0 = nt * p.BN;
         const int total = p.ntaps[phase] * p.nkb;
-        const int lo = total * split / S, hi = total * (split + 1) / S;     // this work item's (tap, k-block) stages
-        int tp = lo / p.nkb, kb = lo - tp * p.nkb;
+        int lo = 0, hi = total, tp = 0, kb = 0;                              // this work item's (tap, k-block) stages
+        if (S > 1) { lo = total * split / S; hi = total * (split + 1) / S; tp = lo / p.nkb; kb = lo - tp * p.nkb; }
         TcTap tap = p.taps[phase][tp];
         for (int li = lo; li < hi; ++li) {
           mbar_wait(empty0 + s * 8u, par);
@@ -337,15 +430,15 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_kernel(const __grid_constant__ 
       const uint32_t bres_lo = umma_desc_lo(smem_base + p.bres_off, 16), wtile_q = wtile >> 4;
       if (res) { mbar_wait(smem_u32(&bres_bar), 0); tc_fence_after(); }
       for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
-        const int item = wi / S, split = wi - item * S;
-        const int phase = (item / ntn) / tpp_items;
+        int split, nt_, phase, ti_;
+        tc_item_decode(p, wi, ntn, tpp_items, split, nt_, phase, ti_);
         const int total = p.ntaps[phase] * p.nkb;
-        const int lo = total * split / S, hi = total * (split + 1) / S;
+        int lo = 0, hi = total, kb = 0, tp = 0;
+        if (S > 1) { lo = total * split / S; hi = total * (split + 1) / S; tp = lo / p.nkb; kb = lo - tp * p.nkb; }
         const int buf = lt & 1;
         mbar_wait(smem_u32(&tempty_bar[buf]), (uint32_t)(((lt >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(buf * MT * p.BN);
-        int kb = lo % p.nkb, tp = lo / p.nkb;
         uint32_t acc = 0u;
         uint32_t bw_lo = res ? bres_lo + (uint32_t)(p.taps[phase][tp].widx * p.nkb + kb) * wtile_q : 0u;
         for (int li = lo; li < hi; ++li) {
@@ -426,10 +519,9 @@ __global__ void __launch_bounds__(320, 1) tc_fwd_halo_kernel(const __grid_consta
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, par = 1, sa = smem_base;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nt = tile % ntn; int t = tile / ntn;
-        const int j0 = (t % p.tw) * p.bw; t /= p.tw;
-        const int i0 = (t % p.th) * p.bh; t /= p.th;
-        const int b0 = t * p.bb;
+        const int t = fast_div(tile, p.fd_ntn), nt = tile - t * ntn;
+        int j0, i0, b0;
+        tc_tile_origin(p, t, j0, i0, b0);
         const int n0 = nt * p.BN;
         for (int g = 0; g < p.ngroups; ++g) {
           const TcGroup& grp = p.groups[g];
@@ -619,7 +711,7 @@ tc_splitk_reduce_kernel(const float* __restrict__ part, long stride, int nz, con
 // Split-K: when the tile count leaves most SMs idle (small maps / small per-GPU batch) or its last wave is mostly empty,
 // each tile's (tap, k-block) stage sequence is cut into S work items with fp32 partials in workspace.
 struct TcFwdPlan { int ok, BN, bw, bh, bb, tw, th, tb, ntiles, ksplit; };
-struct BgTcFold { int pt, pl, Hi, Wi; void* ring; const void* mask; };
+struct BgTcFold { int pt, pl, Hi, Wi; void* ring; const void* mask; };   // ring == nullptr: no fold, only the ReLU mask (same layout as `out`)
 static TcFwdPlan tc_fwd_plan(const BgGeom& g) {
   TcFwdPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -665,9 +757,11 @@ static int g_cnt_tc_fwd = 0, g_cnt_tc_wgrad = 0;   // launches taken by the tens
 // `in` must already be zero-pad semantics (reflect inputs are pre-padded by the caller, with
 // tap offsets shifted accordingly through pad_shift_y/x).
 int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int shift_y, int shift_x, const void* w_kmajor,
-                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, const BgTcFold* fold,
+                     const float* bias, const void* residual, void* out, int act, void* sk_ws, size_t sk_bytes, const BgTcFold* fold_in,
                      cudaStream_t st, int* taken) {
   *taken = 0;
+  const void* mask_only = (fold_in && !fold_in->ring) ? fold_in->mask : nullptr;
+  const BgTcFold* fold = (fold_in && fold_in->ring) ? fold_in : nullptr;
   const TcFwdPlan pl = tc_fwd_plan(g);
   if (!pl.ok) return BG_OK;
   if (((uintptr_t)in | (uintptr_t)w_kmajor | (uintptr_t)out | (uintptr_t)residual) & 15) return BG_OK;
@@ -744,16 +838,28 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     // (not in fold mode: boxes starting at negative coordinates are fine for TMA loads but fault on stores -- measured)
     static int ts_k = -1;                         // threshold of the issue-rate model, in units of 16 x BN cycles (tuning knob)
     if (ts_k < 0) { const char* e = getenv("BG_TC_TMA_STORE_K"); ts_k = e ? atoi(e) : 3; if (ts_k < 1) ts_k = 3; }
-    if (ts_env > 0 && !fold && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < (long)ts_k * 16 * BN) &&
+    const char* tsf = getenv("BG_TC_TMA_STORE_FOLD");       // A/B knob (read per call): bulk stores for the interior tiles of the fold mode
+    const int tsf_env = tsf ? atoi(tsf) : 1;
+    if (ts_env > 0 && (!fold || tsf_env) && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < (long)ts_k * 16 * BN) &&
         (ring_budget - 2 * half_bytes) / stage_bytes >= 3) {
       P.tma_store = 1;
       P.ostage_half = (uint32_t)half_bytes;
       P.ostage_sets = (ring_budget - 4 * half_bytes) / stage_bytes >= 4 ? 2 : 1;
       ring_budget -= 2 * P.ostage_sets * half_bytes;
-      for (int ph = 0; ph < g.nphase; ++ph)
-        if ((rc = make_act_map(&P.omap[ph], out, g.B, g.Ho, g.Wo, g.Co, g.ostep, g.ph[ph].oy0, g.ph[ph].ox0, bw, bh, bb, 16,
-                               CU_TENSOR_MAP_SWIZZLE_NONE)))
+      for (int ph = 0; ph < g.nphase; ++ph) {
+        if (fold) {
+          // the kernel iterates the padded domain; the map covers the unpadded tensor from this phase's first interior row / column
+          const int di = g.ph[ph].oy0 >= fold->pt ? 0 : (fold->pt - g.ph[ph].oy0 + g.ostep - 1) / g.ostep;
+          const int dj = g.ph[ph].ox0 >= fold->pl ? 0 : (fold->pl - g.ph[ph].ox0 + g.ostep - 1) / g.ostep;
+          P.o_di[ph] = di; P.o_dj[ph] = dj;
+          const int y0 = g.ph[ph].oy0 + di * g.ostep - fold->pt, x0 = g.ph[ph].ox0 + dj * g.ostep - fold->pl;
+          if (y0 >= fold->Hi || x0 >= fold->Wi) { P.omap[ph] = P.omap[0]; continue; }      // no interior pixel in this phase: never used
+          if ((rc = make_act_map(&P.omap[ph], out, g.B, fold->Hi, fold->Wi, g.Co, g.ostep, y0, x0, bw, bh, bb, 16, CU_TENSOR_MAP_SWIZZLE_NONE)))
+            return rc;
+        } else if ((rc = make_act_map(&P.omap[ph], out, g.B, g.Ho, g.Wo, g.Co, g.ostep, g.ph[ph].oy0, g.ph[ph].ox0, bw, bh, bb, 16,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE)))
           return rc;
+      }
       for (int ph = g.nphase; ph < 4; ++ph) P.omap[ph] = P.omap[0];
     }
   }
@@ -780,12 +886,24 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   P.bias = bias; P.residual = (const bf16*)residual; P.out = (bf16*)out;
   const long ntiles = bg_cdiv((long)P.tw * P.th * P.tb, (long)P.mt) * g.nphase * (g.Co / BN);      // work items
   const long out_numel = (long)g.B * g.Ho * g.Wo * g.Co;
+  if (mask_only) {
+    if (pl.ksplit > 1 || (((uintptr_t)mask_only) & 15)) return BG_OK;     // the split-K reduce pass has no mask: not taken
+    P.mask = (const bf16*)mask_only;
+  }
   if (fold) { P.fold = 1; P.f_pt = fold->pt; P.f_pl = fold->pl; P.f_Hi = fold->Hi; P.f_Wi = fold->Wi; P.ring = (bf16*)fold->ring; P.mask = (const bf16*)fold->mask; }
   P.ksplit = 1;
   if (pl.ksplit > 1 && !fold && !box_override && sk_ws && sk_bytes >= (size_t)pl.ksplit * out_numel * sizeof(float) &&
       (((uintptr_t)sk_ws) & 15) == 0) {
     P.ksplit = pl.ksplit; P.part = (float*)sk_ws; P.part_stride = out_numel;
   }
+  {
+    const char* e = getenv("BG_TC_AUX_PREFETCH");     // A/B knobs, read per call (tools/layer_sweep.py toggles them in one process)
+    P.aux_prefetch = e ? atoi(e) : 0;
+    e = getenv("BG_TC_AUX_BATCH");
+    P.aux_batch = e ? atoi(e) : 1;
+  }
+  P.fd_S = make_fastdiv(P.ksplit); P.fd_ntn = make_fastdiv(g.Co / BN); P.fd_tw = make_fastdiv(P.tw); P.fd_th = make_fastdiv(P.th);
+  P.fd_tpp = make_fastdiv((int)bg_cdiv((long)P.tw * P.th * P.tb, (long)P.mt));
   dim3 grid((unsigned)min(ntiles * P.ksplit, (long)bg_num_sms()));
   // halo mode: stride-1 layer tiled in full 128-pixel row segments -> taps differing only in dx share one activation box
   {

@@ -641,3 +641,4 @@ extern "C" int bg_col2im_rgb(const void* dz, void* dx, int B, int H, int W, int 
   BG_LAUNCH_CHECK();
   return BG_OK;
 }
+

@@ -3,6 +3,30 @@
 #include <cuda.h>
 #include "bg_common.cuh"
 
+// Division by a launch-time constant in the per-tile index decode of the persistent kernels: the epilogue warps and the two
+// single-thread issue loops are latency-bound dependent instruction streams, and one runtime `/` is ~25 instructions (MUFU.RCP
+// + fix-ups) -- ncu on the short-main-loop layers showed ~200 of the ~510 instructions per warp and tile in these divisions.
+// q = umulhi(n, mul) >> shr is exact for 0 <= n < 2^31 (round-up multiplier with p = 31 + ceil(log2 d) bits).
+struct FastDiv { uint32_t mul, shr; int d; };
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f; f.d = d; f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1u << lg) < (uint32_t)d) ++lg;                // ceil(log2 d)
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + (uint32_t)d - 1) / (uint32_t)d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+__host__ __device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+#ifdef __CUDA_ARCH__
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+#else
+  return f.d == 1 ? n : (int)((((unsigned long long)(uint32_t)n * f.mul) >> 32) >> f.shr);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -125,6 +149,13 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+// MUFU.TANH (max relative error 2^-11): the result is rounded to bf16 (8 mantissa bits) right after
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 // 32 lanes x 16 consecutive fp32 columns: thread i gets row (lane base + i)

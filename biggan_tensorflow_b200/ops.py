@@ -434,6 +434,61 @@ def _im2col_rgb(x, desc, cz):
     return z
 
 
+def _conv_rgb_out(x, wn, desc, c_pad, act):
+    """3x3 / stride 1 / one-pixel-padded conv to 3 (zero-padded to c_pad) channels in tensor-core mode -- `G_logit`, BigGAN.py:570.
+    The nine taps are stacked along N: ONE 1x1 GEMM Ci -> 27 (32) on the unpadded input, then the shifted tap sum + activation
+    (bg_rgb_tapsum_fwd).  Backward: the tap sum's adjoint, then a 1x1 dgrad (with the ReLU mask of x) and a 1x1 wgrad.
+    A 3x3 conv with N = 16 costs 54 tensor-core instructions per 128-pixel tile at the operand-read floor of the tensor pipe
+    (7x the layer's HBM time) plus a reflect-padded copy of x, a padded-domain gradient and a fold pass."""
+    dt = _lib.BG_BF16
+    fs = _state["force_simt"]
+    B, H, W, Ci = desc.B, desc.Hi, desc.Wi, desc.Ci
+    wall, wall_t = empty([Ci, 32], BF16), empty([32, Ci], BF16)
+    call("bg_rgb_stack_weights", wn.data, wall, wall_t, Ci, c_pad, stream())
+    d1 = ConvDesc(B, H, W, Ci, H, W, 32, 1, 1, 1, 0, 0, 0, 0, _lib.PAD_ZERO, 0)
+    ycol = empty([B, H, W, 32], BF16)
+    nbf = query("bg_conv2d_fwd_workspace_bytes", d1, dt)
+    wsf = workspace(nbf) if nbf else None
+    call("bg_conv2d_fwd", d1, x.data, wall, wall_t, None, None, ycol, _lib.ACT_NONE, dt, wsf, wsf.numel() if nbf else 0, fs, stream(),
+         flops=_conv_flops(desc), tag="conv_fwd" + _conv_tag(desc))
+    y = Tensor(empty([B, H, W, c_pad], BF16), requires_grad=x.requires_grad or wn.requires_grad)
+    call("bg_rgb_tapsum_fwd", ycol, None, y.data, B, H, W, c_pad, desc.pad_mode, act, stream(), tag="rgb_tapsum")
+    y.relu_out = act == _lib.ACT_RELU
+    mask_x = bool(x.relu_out) and os.environ.get("BG_NO_RELU_MASK_FUSION") != "1"
+    if recording(x, wn):
+        def bw():
+            if y.grad is None:
+                return
+            dcol = empty([B, H, W, 32], BF16)
+            call("bg_rgb_tapsum_bwd", y.data, y.grad, dcol, B, H, W, c_pad, desc.pad_mode, act, stream(), tag="rgb_tapsum")
+            if wn.requires_grad:
+                dwall = empty([Ci, 32], F32)
+                nb = query("bg_conv2d_wgrad_workspace_bytes", d1, dt)
+                ws = workspace(nb)
+                call("bg_conv2d_wgrad", d1, x.data, dcol, dwall, dt, ws, ws.numel(), fs, stream(),
+                     flops=_conv_flops(desc), tag="conv_wgrad" + _conv_tag(desc))
+                dst, fin = grad_target(wn, dtype=F32)
+                call("bg_rgb_unstack_wgrad", dwall, dst, Ci, c_pad, stream())
+                if fin:
+                    fin()
+            if x.requires_grad:
+                nb = query("bg_conv2d_dgrad_workspace_bytes", d1, dt)
+                ws = workspace(nb) if nb else None
+                res = x.grad
+                dx = res if (res is not None and x.grad_owned) else torch.empty_like(x.data)
+                if mask_x:
+                    call("bg_conv2d_dgrad", d1, dcol, wall, wall_t, res, x.data, dx, dt, ws, ws.numel() if nb else 0, fs, stream(),
+                         flops=_conv_flops(desc), tag="conv_dgrad" + _conv_tag(desc))
+                    x.n_masked += 1
+                else:
+                    call("bg_conv2d_dgrad", d1, dcol, wall, wall_t, res, None, dx, dt, ws, ws.numel() if nb else 0, fs, stream(),
+                         flops=_conv_flops(desc), tag="conv_dgrad" + _conv_tag(desc))
+                x.n_contribs += 1
+                x.grad, x.grad_owned, x.grad_set = dx, True, True
+        record(bw)
+    return y
+
+
 def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True, scope='conv_0',
          _residual=None, _act=_lib.ACT_NONE, _pad_cout_to=0, _pre_relu=False):
     """ops.py:49-113.  _pre_relu: conv(relu(x)) (the activation resblock_down applies in front of its first conv)."""
@@ -469,6 +524,14 @@ def conv(x, channels, opt, kernel=4, stride=2, pad=0, dilation=1, use_bias=True,
                 y.aux = {"c_real": channels}
             return y
         wn = _sn_weight(w, kernel * kernel, True, x.dtype, pad_c=c_pad, pad_r=cin_x if cin_x != cin else 0)
+        if (channels == 3 and c_pad % 8 == 0 and c_pad > 3 and kernel == 3 and stride == 1 and not use_bias and _residual is None
+                and not _pre_relu and (desc.pad_t, desc.pad_l, desc.pad_b, desc.pad_r) == (1, 1, 1, 1) and x.dtype == BF16
+                and cin_x == cin and cin % 16 == 0 and x.shape[1] >= 2 and x.shape[2] >= 2 and not _state["force_simt"]
+                and _lib.lib.bg_has_tensor_core_path() == 1 and os.environ.get("BG_RGB_TAPSUM") != "0"):
+            # image OUTPUT in tensor-core mode (G_logit): nine taps stacked along N, one 1x1 GEMM + shifted tap sum
+            y = _conv_rgb_out(x, wn, desc, c_pad, _act)
+            y.aux = {"c_real": channels}
+            return y
         bias = None
         if use_bias:
             bias = get_variable("bias", [channels], initializer=constant_initializer(0.0))

@@ -226,6 +226,21 @@ int bg_im2col_rgb(const void* x, void* z, int B, int H, int W, int Cx, int Ho, i
                   int pad_t, int pad_l, int pad_mode, int Cz, void* stream);
 int bg_col2im_rgb(const void* dz, void* dx, int B, int H, int W, int Cx, int Ho, int Wo, int kh, int kw, int stride,
                   int pad_t, int pad_l, int pad_b, int pad_r, int pad_mode, int Cz, void* stream);
+/* RGB OUTPUT conv in tensor-core mode (ops.py:49-113 with channels = 3, kernel 3, stride 1, pad 1 -- `G_logit`,
+ * BigGAN.py:570): the nine taps are stacked along the GEMM's N.  bg_rgb_stack_weights builds, from the normalised
+ * HWIO weights wn [3,3,Ci,c_pad] (bf16), the 1x1 operand wall [Ci,32] (column (a*3+c)*3+n = wn[a,c,:,n], columns
+ * 27..31 zero) and its K-major copy wall_t [32,Ci]; Y = conv1x1(x, wall) is a plain bg_conv2d_fwd on the UNPADDED
+ * input; bg_rgb_tapsum_fwd finishes  out[b,i,j,n] = act(bias[n] + sum_{a,c} Y[b,R(i+a-1),R(j+c-1),(a*3+c)*3+n])
+ * (R: reflect or zero padding of ONE pixel; out has Co channels, 3..Co-1 zero).  Backward: bg_rgb_tapsum_bwd is the
+ * adjoint of the tap sum and of the activation (y = the forward output, d_out its gradient) -> dY [B,H,W,32];
+ * dx = bg_conv2d_dgrad of the 1x1 conv (relu_mask allowed), d wall [Ci,32] = bg_conv2d_wgrad of the 1x1 conv, and
+ * bg_rgb_unstack_wgrad scatters it back to d wn [3,3,Ci,c_pad] (fp32; columns 3..c_pad-1 zero). */
+int bg_rgb_stack_weights(const void* wn, void* wall, void* wall_t, int Ci, int c_pad, void* stream);
+int bg_rgb_unstack_wgrad(const float* dwall, float* dwn, int Ci, int c_pad, void* stream);
+int bg_rgb_tapsum_fwd(const void* Y, const float* bias, void* out, int B, int H, int W, int Co, int pad_mode,
+                      int act, void* stream);
+int bg_rgb_tapsum_bwd(const void* y, const void* d_out, void* dY, int B, int H, int W, int Co, int pad_mode,
+                      int act, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses -- ops.py:753-797 (discriminator_loss 'hinge'), :799-840 (generator_loss 'hinge'),

@@ -88,6 +88,20 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   bg_emul_wait(bg_emul_warp_bars[w]);
   return r;
 }
+// lane l receives lane l - delta's value (lanes below delta keep their own) / lane l + delta's (lanes past the end keep their own)
+inline float bg_emul_shfl_rel(float v, int rel) {
+  if (bg_emul_sequential) throw bg_emul_needs_threads();
+  const unsigned t = bg_emul_cur, w = t >> 5;
+  bg_emul_shfl[t] = v;
+  bg_emul_wait(bg_emul_warp_bars[w]);
+  const int lane = (int)(t & 31u) + rel;
+  const unsigned src = (t & ~31u) + (unsigned)lane;
+  const float r = (lane >= 0 && lane < 32 && src < blockDim.x) ? bg_emul_shfl[src] : v;
+  bg_emul_wait(bg_emul_warp_bars[w]);
+  return r;
+}
+inline float __shfl_up_sync(unsigned, float v, unsigned delta) { return bg_emul_shfl_rel(v, -(int)delta); }
+inline float __shfl_down_sync(unsigned, float v, unsigned delta) { return bg_emul_shfl_rel(v, (int)delta); }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 using std::min;
 using std::max;

@@ -276,8 +276,9 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy_, const voi
                                int dtype, void*, size_t, int, void*) {
   DTYPE_OK(dtype);
   const long nxe = (long)d->B * d->Hi * d->Wi * d->Ci, nye = (long)d->B * d->Ho * d->Wo * d->Co, nwe = (long)d->kh * d->kw * d->Ci * d->Co;
-  if (mask_ && !(d->pad_mode == BG_PAD_REFLECT && !d->transposed && (d->pad_t | d->pad_l | d->pad_b | d->pad_r))) {
-    bg_set_error("bg_conv2d_dgrad: relu_mask is implemented for reflect-padded convs"); return BG_ERR_UNSUPPORTED;
+  const bool any_pad = (d->pad_t | d->pad_l | d->pad_b | d->pad_r) != 0;
+  if (mask_ && !(!d->transposed && ((d->pad_mode == BG_PAD_REFLECT && any_pad) || (!any_pad && dtype == BG_BF16)))) {
+    bg_set_error("bg_conv2d_dgrad: relu_mask needs a reflect-padded conv, or an unpadded conv on the bf16 tensor-core path"); return BG_ERR_UNSUPPORTED;
   }
   In gi(dy_, nye, dtype), wi(w_, nwe, dtype), ri(res_, nxe, dtype), mi(mask_, nxe, dtype); Out xo(dx_, nxe, dtype); dy_ = gi.p; w_ = wi.p; res_ = ri.p; dx_ = xo.p;
   const float *dy = (const float*)dy_, *w = (const float*)w_, *res = (const float*)res_, *mask = mi.p;
@@ -606,6 +607,59 @@ extern "C" int bg_col2im_rgb(const void* dz, void* dx, int B, int H, int W, int 
     for (int c = 0; c < 3; ++c) acc[(((size_t)b * H + iy) * W + ix) * 3 + c] += zi.p[(((long)b * Ho + oy) * Wo + ox) * Cz + (ky * kw + kx) * 3 + c];
   }
   for (long p = 0; p < (long)B * H * W; ++p) for (int c = 0; c < Cx; ++c) xo.p[p * Cx + c] = c < 3 ? (float)acc[p * 3 + c] : 0.f;
+  return BG_OK;
+}
+// tap-stacked RGB output conv (G_logit): see include/biggan_b200.h
+extern "C" int bg_rgb_stack_weights(const void* wn, void* wall, void* wall_t, int Ci, int c_pad, void*) {
+  In wi(wn, (long)9 * Ci * c_pad, BG_BF16); Out a(wall, (long)Ci * 32, BG_BF16), t(wall_t, (long)32 * Ci, BG_BF16);
+  for (int c = 0; c < Ci; ++c) for (int col = 0; col < 32; ++col) {
+    const float v = col < 27 ? wi.p[((long)(col / 3) * Ci + c) * c_pad + col % 3] : 0.f;
+    a.p[(long)c * 32 + col] = v; t.p[(long)col * Ci + c] = v;
+  }
+  return BG_OK;
+}
+extern "C" int bg_rgb_unstack_wgrad(const float* dwall, float* dwn, int Ci, int c_pad, void*) {
+  for (int tap = 0; tap < 9; ++tap) for (int c = 0; c < Ci; ++c) for (int n = 0; n < c_pad; ++n)
+    dwn[((long)tap * Ci + c) * c_pad + n] = n < 3 ? dwall[(long)c * 32 + tap * 3 + n] : 0.f;
+  return BG_OK;
+}
+static inline int rgb_pad1(int p, int n, int reflect) { if (p >= 0 && p < n) return p; if (!reflect) return -1; return p < 0 ? -p : 2 * (n - 1) - p; }
+extern "C" int bg_rgb_tapsum_fwd(const void* Y, const float* bias, void* out, int B, int H, int W, int Co, int pad_mode, int act, void*) {
+  In yi(Y, (long)B * H * W * 32, BG_BF16); Out oo(out, (long)B * H * W * Co, BG_BF16);
+  const int reflect = pad_mode == BG_PAD_REFLECT;
+  for (int b = 0; b < B; ++b) for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) {
+    float* op = oo.p + (((long)b * H + i) * W + j) * Co;
+    for (int n = 0; n < Co; ++n) op[n] = 0.f;
+    for (int n = 0; n < 3; ++n) {
+      double acc = bias ? bias[n] : 0.0;
+      for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) {
+        const int si = rgb_pad1(i + a - 1, H, reflect), sj = rgb_pad1(j + c - 1, W, reflect);
+        if (si < 0 || sj < 0) continue;
+        acc += yi.p[(((long)b * H + si) * W + sj) * 32 + (a * 3 + c) * 3 + n];
+      }
+      const float v = (float)acc;
+      op[n] = act == BG_ACT_RELU ? (v > 0.f ? v : 0.f) : (act == BG_ACT_TANH ? std::tanh(v) : v);
+    }
+  }
+  return BG_OK;
+}
+extern "C" int bg_rgb_tapsum_bwd(const void* y, const void* d_out, void* dY, int B, int H, int W, int Co, int pad_mode, int act, void*) {
+  In yi(y, (long)B * H * W * Co, BG_BF16), gi(d_out, (long)B * H * W * Co, BG_BF16); Out zo(dY, (long)B * H * W * 32, BG_BF16);
+  const int reflect = pad_mode == BG_PAD_REFLECT;
+  std::vector<double> acc((size_t)B * H * W * 32, 0.0);
+  // scatter form of the adjoint (the kernel uses the gather form): every (output pixel, tap) adds to the source pixel it read
+  for (int b = 0; b < B; ++b) for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) for (int n = 0; n < 3; ++n) {
+    const long o = (((long)b * H + i) * W + j) * Co + n;
+    float g = gi.p[o];
+    if (act == BG_ACT_TANH) g *= 1.f - yi.p[o] * yi.p[o];
+    else if (act == BG_ACT_RELU) g = yi.p[o] > 0.f ? g : 0.f;
+    for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) {
+      const int si = rgb_pad1(i + a - 1, H, reflect), sj = rgb_pad1(j + c - 1, W, reflect);
+      if (si < 0 || sj < 0) continue;
+      acc[((((size_t)b * H + si) * W + sj) * 32) + (a * 3 + c) * 3 + n] += g;
+    }
+  }
+  for (size_t k = 0; k < acc.size(); ++k) zo.p[k] = (float)acc[k];
   return BG_OK;
 }
 // o = softmax(q k^T) v, lse = log sum exp of the scores; backward recomputes the probabilities from lse

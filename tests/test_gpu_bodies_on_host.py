@@ -41,3 +41,24 @@ def test_parameters_after_update_on_the_host(host_all):
 
 def test_step_matches_oracle_golden_vectors_on_the_host(host_all):
     TG.test_cuda_step_matches_golden_vectors()
+
+
+@pytest.mark.parametrize("case", [(2, 8, 32, "reflect", True), (2, 33, 16, "reflect", False), (2, 30, 64, "zero", True), (3, 2, 16, "reflect", False)])
+def test_rgb_output_conv_tap_stacked_on_the_host(host_all, monkeypatch, case):
+    """tests/test_ops_gpu.py::test_conv_rgb_out_tap_stacked on the host library (BG_HOST_TC=1): the Python glue of the tap-stacked
+    G_logit path and the arithmetic of its four entry points (loop stand-ins in host_lib.cpp) against the oracle."""
+    from biggan_tensorflow_b200 import ops, _lib
+    import test_ops_gpu as O
+    monkeypatch.setenv("BG_HOST_TC", "1")
+    ops.set_compute_dtype(torch.bfloat16)
+    seen = []
+    real_call = _lib.call
+    monkeypatch.setattr(ops, "call", lambda name, *a, **k: (seen.append(name), real_call(name, *a, **k))[1])
+    O.rgb_out_body(case)
+    for name in ("bg_rgb_stack_weights", "bg_rgb_tapsum_fwd", "bg_rgb_tapsum_bwd", "bg_rgb_unstack_wgrad"):
+        assert name in seen, name
+    seen.clear()
+    monkeypatch.setenv("BG_RGB_TAPSUM", "0")               # the plain 3x3 path gives the same answer
+    O.rgb_out_body(case)
+    assert "bg_rgb_tapsum_fwd" not in seen
+

@@ -166,6 +166,41 @@ def test_conv_rgb_im2col(case):
              {"x": x}, torch.bfloat16)
 
 
+RGB_OUT_CASES = [(2, 8, 32, "reflect", True), (1, 128, 96, "reflect", True), (2, 33, 16, "reflect", False), (2, 30, 64, "zero", True),
+                 (3, 2, 16, "reflect", False), (1, 61, 32, "zero", False)]
+
+
+def rgb_out_body(case):
+    """G_logit in tensor-core mode (BigGAN.py:570 + tanh :580): conv(relu-output x, 3 channels zero-padded to 16, 3x3, stride 1, pad 1)
+    with the nine taps stacked along N -- bg_rgb_stack_weights, one 1x1 GEMM Ci -> 32 on the unpadded input, bg_rgb_tapsum_fwd
+    (reflect / zero tap sum + tanh); backward through bg_rgb_tapsum_bwd, the 1x1 dgrad with the ReLU mask of x in its epilogue,
+    the 1x1 wgrad and bg_rgb_unstack_wgrad.  Sizes cover one and several 30-pixel warp segments per row, ragged last segments,
+    the 2-pixel minimum, 128-pixel rows."""
+    from biggan_tensorflow_b200 import ops, _lib
+    B, H, Cin, padtype, masked = case
+    po, ro = _opt(pad=padtype)
+    x = np.random.default_rng(5).standard_normal((B, H, H, Cin)).astype(np.float32)
+
+    def prod(xs):
+        xr = ops.relu(xs["x"])
+        xr.relu_out = masked          # as after a fused BN + ReLU: the conv's dgrad applies the mask (relu's own backward repeats it)
+        y = ops.conv(xr, 3, po, kernel=3, stride=1, pad=1, use_bias=False, scope="G_logit", _act=_lib.ACT_TANH, _pad_cout_to=16)
+        assert y.shape[-1] == 16 and ops.c_real(y) == 3
+        assert float(y.data[..., 3:].float().abs().max()) == 0.0
+        return ops.slice_channels(y, 3)
+
+    run_case(prod, lambda rs, xs: torch.tanh(R.conv(rs, R.relu(xs["x"]), 3, ro, kernel=3, stride=1, pad=1, use_bias=False, scope="G_logit")),
+             {"x": x}, torch.bfloat16)
+
+
+@pytest.mark.parametrize("case", RGB_OUT_CASES)
+def test_conv_rgb_out_tap_stacked(case):
+    from biggan_tensorflow_b200 import _lib
+    n0 = _lib.launch_count
+    rgb_out_body(case)
+    assert _lib.launch_count > n0
+
+
 DECONV_CASES = [(2, 4, 32, 16, 4, 2), (2, 8, 16, 16, 3, 1), (2, 4, 16, 8, 3, 2), (1, 4, 8, 8, 6, 2),   # deconv4/3/6
                 (2, 5, 64, 64, 4, 2), (2, 4, 128, 64, 4, 2), (2, 4, 16, 16, 4, 1),
                 (4, 8, 256, 128, 4, 2), (2, 16, 128, 128, 3, 1), (3, 4, 512, 512, 4, 2), (2, 32, 96, 96, 3, 1)]
