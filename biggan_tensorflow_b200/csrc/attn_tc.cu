@@ -6,6 +6,12 @@
 // Forward, one CTA per (image, 128 queries), two passes over the key blocks (Nk <= a few thousand):
 //   pass 1: S_j = Q K_j^T (TMEM) -> row max;   pass 2: S_j again, P_j = exp(S_j - max) -> bf16 tile in
 //   shared memory (128B-swizzled K-major) -> O += P_j V_j (TMEM), row sums.  No accumulator rescaling.
+// Single-pass mode (bg_attn2_fwd_ws): softmax is invariant to the shift, so any m >= max_j s_ij works as long as nothing
+// underflows.  A tiny pre-kernel gives the per-image Cauchy-Schwarz bound  m_b = max_i |q_i| * max_j |k_j| >= |s_ij|; when
+// m_b <= 30 every row keeps exp(s_max - m_b) >= e^-60 and every element within e^-27 of its row maximum stays normal
+// (fp32 / bf16 exponent range: e^-87), so pass 1 -- half of the Q K^T
+// products and a quarter of the softmax warps' instructions -- is skipped and lse = m_b + log(sum).  Larger bounds (never seen
+// with spectrally normalised projections of batch-normalised activations) take the two-pass path.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue (one row per thread).
 #include "tc_ptx.cuh"
 
@@ -17,6 +23,8 @@ struct AttnFwdParams {
   int nvblk;                       // 64-channel blocks of V
   bf16* o;
   float* lse;
+  const float* bound;              // [B] upper bound of |s| per image, or nullptr (always two passes)
+  float bound_max;                 // single-pass threshold
 };
 
 // 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax / epilogue.  Two softmax warps
@@ -34,7 +42,10 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
   const uint32_t vbytes = (uint32_t)p.nvblk * 16384u;
   const uint32_t Qs = base, Ks = base + 16384u, Vs = Ks + 16384u, Ps = Vs + vbytes;
   const int b = blockIdx.y, q0 = blockIdx.x * 128;
-  const int T = 2 * p.nkb;
+  const float mb = p.bound ? __ldg(p.bound + b) : INFINITY;
+  const bool single = mb <= p.bound_max;          // CTA-uniform
+  const int first2 = single ? 0 : p.nkb;          // first iteration that forms P and P V
+  const int T = first2 + p.nkb;
 
   if (warp == 0 && elect_one_sync()) {
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap);
@@ -57,12 +68,12 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
       mbar_expect_tx(smem_u32(&q_full), 16384u);
       tma_load_3d(Qs, &p.qmap, smem_u32(&q_full), 0, q0, b);
       for (int it = 0; it < T; ++it) {
-        const int j = it % p.nkb;
+        const int j = it >= p.nkb ? it - p.nkb : it;
         mbar_wait(smem_u32(&k_empty), (uint32_t)((it & 1) ^ 1));
         mbar_expect_tx(smem_u32(&k_full), 16384u);
         tma_load_3d(Ks, &p.kmap, smem_u32(&k_full), 0, j * AT_KB, b);
-        if (it >= p.nkb) {
-          const int jj = it - p.nkb;
+        if (it >= first2) {
+          const int jj = it - first2;
           mbar_wait(smem_u32(&v_empty), (uint32_t)((jj & 1) ^ 1));
           mbar_expect_tx(smem_u32(&v_full), vbytes);
           for (int c = 0; c < p.nvblk; ++c)
@@ -86,7 +97,7 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
           umma_commit(smem_u32(&s_full));
           umma_commit(smem_u32(&k_empty));
         }
-        const int pv = it - 1 - p.nkb;            // the P V product of the previous (pass-2) iteration
+        const int pv = it - 1 - first2;           // the P V product of the previous (pass-2) iteration
         if (pv >= 0) {
           mbar_wait(smem_u32(&v_full), (uint32_t)(pv & 1));
           mbar_wait(smem_u32(&p_full), (uint32_t)(pv & 1));
@@ -111,16 +122,19 @@ __global__ void __launch_bounds__(320, 2) attn_fwd_kernel(const __grid_constant_
     const float LOG2E = 1.4426950408889634f;
     float m = -INFINITY, sum_true = 0.f;
     for (int it = 0; it < T; ++it) {
-      const int j = it % p.nkb;
-      const bool pass2 = it >= p.nkb;
-      if (it == p.nkb) {                          // pass 1 done: combine the two halves' row maxima
-        xch[0][half][row] = m;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        m = fmaxf(xch[0][0][row], xch[0][1][row]);
+      const int j = it >= p.nkb ? it - p.nkb : it;
+      const bool pass2 = it >= first2;
+      if (it == first2) {
+        if (single) m = mb;                       // the shift is the per-image bound: no pass 1
+        else {                                    // pass 1 done: combine the two halves' row maxima
+          xch[0][half][row] = m;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          m = fmaxf(xch[0][0][row], xch[0][1][row]);
+        }
       }
       mbar_wait(smem_u32(&s_full), (uint32_t)(it & 1));
       tc_fence_after();
-      if (pass2) mbar_wait(smem_u32(&p_empty), (uint32_t)(((it - p.nkb) & 1) ^ 1));
+      if (pass2) mbar_wait(smem_u32(&p_empty), (uint32_t)(((it - first2) & 1) ^ 1));
       const bool kmask = (j + 1) * AT_KB > p.Nk;       // only the last key block can be partial (block-uniform)
       const float mL = m * LOG2E;
       for (int cc = 0; cc < 64; cc += 16) {
@@ -225,8 +239,68 @@ int bg_attn_make_map(CUtensorMap* m, const void* base, int B, int rows, int C, i
   return BG_OK;
 }
 
+// bound[b] = max_i |q_i| * max_j |k_j| (+ margin): one CTA per image, bf16x2 loads, fixed-order block maximum
+__global__ void __launch_bounds__(256) attn_bound_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, float* __restrict__ bound,
+                                                         int Nq, int Nk, int dq) {
+  __shared__ float sh[2][8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mx[2] = {0.f, 0.f};
+  for (int t = 0; t < 2; ++t) {
+    const bf16* base = (t ? k : q) + (long)b * (t ? Nk : Nq) * dq;
+    const int rows = t ? Nk : Nq;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+      const uint4* rp = reinterpret_cast<const uint4*>(base + (long)r * dq);
+      float ss = 0.f;
+      for (int c = 0; c < dq / 8; ++c) {
+        const uint4 u = __ldg(rp + c);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
+      }
+      mx[t] = fmaxf(mx[t], ss);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx[t] = fmaxf(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], o));
+    if (lane == 0) sh[t][warp] = mx[t];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a = fmaxf(a, sh[0][w]); c = fmaxf(c, sh[1][w]); }
+    bound[b] = sqrtf(a * c) * 1.001f + 1e-3f;      // margin for the fp32 rounding of the norms and of the tensor-core dot products
+  }
+}
+
+static int attn2_fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk, int dq, int dv,
+                          float* bound, void* stream);
+extern "C" size_t bg_attn2_fwd_workspace_bytes(int B) { return (size_t)(B > 0 ? B : 0) * sizeof(float) + 16; }
+extern "C" int bg_attn2_fwd_ws(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk, int dq, int dv,
+                               void* ws, size_t ws_bytes, void* stream) {
+  float* bound = nullptr;
+  static int sp_env = -1;                           // A/B knob: 0 = always two passes
+  if (sp_env < 0) { const char* e = getenv("BG_ATTN_SINGLE_PASS"); sp_env = e ? atoi(e) : 1; }
+  if (sp_env && ws && ws_bytes >= bg_attn2_fwd_workspace_bytes(B) && (((uintptr_t)ws) & 3) == 0 && dq % 8 == 0 &&
+      ((((uintptr_t)q) | ((uintptr_t)k)) & 15) == 0)
+    bound = (float*)ws;
+  const int rc = attn2_fwd_impl(q, k, v, o, lse, B, Nq, Nk, dq, dv, bound, stream);
+  static int dbg_env = -1;                          // diagnostics (eager mode only): print the largest bound of each call
+  if (dbg_env < 0) { const char* e = getenv("BG_ATTN_DEBUG"); dbg_env = e ? atoi(e) : 0; }
+  if (dbg_env && bound && rc == BG_OK) {
+    float* h = (float*)malloc(sizeof(float) * B);
+    if (h && cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess && cudaMemcpy(h, bound, sizeof(float) * B, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      float mx = 0.f;
+      for (int i = 0; i < B; ++i) mx = h[i] > mx ? h[i] : mx;
+      fprintf(stderr, "[bg_attn2_fwd_ws] B=%d dq=%d dv=%d max score bound %.3f (single pass up to 30)\n", B, dq, dv, mx);
+    }
+    free(h);
+  }
+  return rc;
+}
 extern "C" int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk, int dq, int dv,
                             void* stream) {
+  return attn2_fwd_impl(q, k, v, o, lse, B, Nq, Nk, dq, dv, nullptr, stream);
+}
+static int attn2_fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk, int dq, int dv,
+                          float* bound, void* stream) {
   BG_REQUIRE(bg_has_tensor_core_path(), BG_ERR_UNSUPPORTED, "attn2: tensor-core path unavailable on this device");
   BG_REQUIRE(dq % 16 == 0 && dq >= 16 && dq <= 64, BG_ERR_UNSUPPORTED, "attn2: dq=%d must be 16..64, multiple of 16", dq);
   BG_REQUIRE(dv % 16 == 0 && dv >= 16 && dv <= 128, BG_ERR_UNSUPPORTED, "attn2: dv=%d must be 16..128, multiple of 16", dv);
@@ -241,6 +315,11 @@ extern "C" int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o
   P.nkb = (int)bg_cdiv(Nk, AT_KB);
   P.nvblk = (dv + 63) / 64;
   P.o = (bf16*)o; P.lse = lse;
+  P.bound = bound; P.bound_max = 30.f;
+  if (bound) {
+    attn_bound_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k, bound, Nq, Nk, dq);
+    BG_LAUNCH_CHECK();
+  }
   const size_t smem = 16384 + 16384 + (size_t)P.nvblk * 16384 + 32768 + 1024;
   static bool attr_set = false;
   if (!attr_set) {

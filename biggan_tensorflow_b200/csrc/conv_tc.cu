@@ -69,7 +69,7 @@ struct TcFwdParams {
   CUtensorMap omap[4];       // per phase: the output sampled with step `ostep` from (oy0, ox0); box (16, bw, bh, bb), no swizzle
   int o_di[4], o_dj[4];      // fold mode: omap covers the UNPADDED tensor from the phase's first interior row / column; tile row i0 is
                              //   its row i0 - o_di (tiles that are interior pixels only take the bulk-store path, the others store directly)
-  int aux_prefetch;          // L2 prefetch of the next tile's residual / mask rows (A/B knob BG_TC_AUX_PREFETCH)
+  int nwork;                 // work items x ksplit (loop bound of the persistent roles, kept in the parameter block)
   int aux_batch;             // BN <= 96: all residual / mask vectors of a half-tile requested up front (A/B knob BG_TC_AUX_BATCH)
   FastDiv fd_S, fd_ntn, fd_tpp, fd_tw, fd_th;   // per-tile index decode without runtime divisions (ksplit, n-tiles, items per phase, tw, th)
 };
@@ -100,10 +100,10 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
     int lt = 0, nstored = 0;
     const int S = p.ksplit;
     const int MT = p.mt;
-    const int tpp_items = (tiles_pp + MT - 1) / MT;          // work items per phase and n-tile (ntiles counts items)
-    for (int wi = blockIdx.x; wi < ntiles * S; wi += gridDim.x, ++lt) {
+    // (items per phase and n-tiles are read from the parameter block where needed: p.fd_tpp.d, p.fd_ntn.d -- no live registers)
+    for (int wi = blockIdx.x; wi < p.nwork; wi += gridDim.x, ++lt) {
       int split, nt, phase, ti;
-      tc_item_decode(p, wi, ntn, tpp_items, split, nt, phase, ti);
+      tc_item_decode(p, wi, p.fd_ntn.d, p.fd_tpp.d, split, nt, phase, ti);
      for (int m = 0; m < MT; ++m) {
       int j0, i0, b0;                                        // a tile index past the phase decodes to b0 >= B: nothing valid, boxes clipped
       tc_tile_origin(p, ti * MT + m, j0, i0, b0);
@@ -151,33 +151,6 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcFwdParams& p, uint32_t t
         const int y_lo = p.oy0[phase] + i0 * p.ostep - p.f_pt, y_hi = y_lo + (p.bh - 1) * p.ostep;
         const int x_lo = p.ox0[phase] + j0 * p.ostep - p.f_pl, x_hi = x_lo + (p.bw - 1) * p.ostep;
         tstore = y_lo >= 0 && y_hi < p.f_Hi && x_lo >= 0 && x_hi < p.f_Wi;
-      }
-      // L2 prefetch of the NEXT work item's residual / mask rows (same m): by the time that tile's epilogue asks for them, the
-      // lines have arrived from DRAM and the demand loads pay an L2 hit instead of a DRAM round trip per tile
-      if (p.aux_prefetch && (p.residual != nullptr || p.mask != nullptr) && wi + (int)gridDim.x < ntiles) {
-        int split2, nt2, phase2, ti2, j2, i2, b2;
-        tc_item_decode(p, wi + (int)gridDim.x, ntn, tpp_items, split2, nt2, phase2, ti2);
-        tc_tile_origin(p, ti2 * MT + m, j2, i2, b2);
-        const int pi2 = i2 + h, pj2 = j2 + w, bb2 = b2 + bl;
-        if ((bb2 < p.B) && (pi2 < p.Hp[phase2]) && (pj2 < p.Wp[phase2])) {
-          const int oy2 = p.oy0[phase2] + pi2 * p.ostep, ox2 = p.ox0[phase2] + pj2 * p.ostep;
-          long ob2 = (((long)bb2 * p.Ho + oy2) * p.Wo + ox2) * p.Co;
-          bool ok2 = true;
-          if (p.fold) {
-            const int iy = oy2 - p.f_pt, ix = ox2 - p.f_pl;
-            if (iy >= 0 && iy < p.f_Hi && ix >= 0 && ix < p.f_Wi) ob2 = (((long)bb2 * p.f_Hi + iy) * p.f_Wi + ix) * p.Co;
-            else ok2 = false;
-          }
-          const int nbytes = (cend - cbeg) * 2;
-          if (ok2 && nbytes > 0) {
-            ob2 += nt2 * p.BN + cbeg;
-            for (int off = 0; off < nbytes + 112; off += 128) {       // every 128-byte line the row segment touches
-              const int o2 = min(off, nbytes - 16);
-              if (p.residual != nullptr) prefetch_l2(reinterpret_cast<const char*>(p.residual + ob2) + o2);
-              if (p.mask != nullptr) prefetch_l2(reinterpret_cast<const char*>(p.mask + ob2) + o2);
-            }
-          }
-        }
       }
       // staging slabs are double-buffered per half: tile lt writes set lt & 1 while the bulk stores of tile lt - 1 still read
       // the other set; the stores of tile lt - 2 (same set) must have finished reading
@@ -840,7 +813,8 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     if (ts_k < 0) { const char* e = getenv("BG_TC_TMA_STORE_K"); ts_k = e ? atoi(e) : 3; if (ts_k < 1) ts_k = 3; }
     const char* tsf = getenv("BG_TC_TMA_STORE_FOLD");       // A/B knob (read per call): bulk stores for the interior tiles of the fold mode
     const int tsf_env = tsf ? atoi(tsf) : 1;
-    if (ts_env > 0 && (!fold || tsf_env) && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < (long)ts_k * 16 * BN) &&
+    // (fold mode: stride-1 layers only -- measured on the strided dgrads the bulk stores of four interleaved phases lose 20 %)
+    if (ts_env > 0 && (!fold || (tsf_env && g.ostep == 1) || tsf_env == 2) && pl.ksplit <= 1 && g.ostep >= 1 && (ts_env == 2 || mma_cycles < (long)ts_k * 16 * BN) &&
         (ring_budget - 2 * half_bytes) / stage_bytes >= 3) {
       P.tma_store = 1;
       P.ostage_half = (uint32_t)half_bytes;
@@ -897,13 +871,14 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
     P.ksplit = pl.ksplit; P.part = (float*)sk_ws; P.part_stride = out_numel;
   }
   {
-    const char* e = getenv("BG_TC_AUX_PREFETCH");     // A/B knobs, read per call (tools/layer_sweep.py toggles them in one process)
-    P.aux_prefetch = e ? atoi(e) : 0;
-    e = getenv("BG_TC_AUX_BATCH");
+    // A/B knob, read per call (tools/layer_sweep.py toggles it in one process).  (An L2 prefetch of the NEXT tile's residual / mask
+    // rows from the epilogue warps was measured too: it cost 0.7 ms per step -- more requests on an already busy L1 -> crossbar port.)
+    const char* e = getenv("BG_TC_AUX_BATCH");
     P.aux_batch = e ? atoi(e) : 1;
   }
   P.fd_S = make_fastdiv(P.ksplit); P.fd_ntn = make_fastdiv(g.Co / BN); P.fd_tw = make_fastdiv(P.tw); P.fd_th = make_fastdiv(P.th);
   P.fd_tpp = make_fastdiv((int)bg_cdiv((long)P.tw * P.th * P.tb, (long)P.mt));
+  P.nwork = (int)(ntiles * P.ksplit);
   dim3 grid((unsigned)min(ntiles * P.ksplit, (long)bg_num_sms()));
   // halo mode: stride-1 layer tiled in full 128-pixel row segments -> taps differing only in dx share one activation box
   {

@@ -151,7 +151,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 // MUFU.TANH (max relative error 2^-11): the result is rounded to bf16 (8 mantissa bits) right after
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;

@@ -846,7 +846,9 @@ def _attn2_fused(q, k, v):
     Nk, dv = k.shape[1], v.shape[2]
     o = Tensor(empty([Bn, Nq, dv], BF16), requires_grad=q.requires_grad or k.requires_grad or v.requires_grad)
     lse = empty([Bn, Nq], F32)
-    call("bg_attn2_fwd", q.data, k.data, v.data, o.data, lse, Bn, Nq, Nk, dq, dv, stream(),
+    nbw = query("bg_attn2_fwd_workspace_bytes", Bn)       # per-image score bound: images under it skip the row-maximum pass
+    wsf = workspace(nbw)
+    call("bg_attn2_fwd_ws", q.data, k.data, v.data, o.data, lse, Bn, Nq, Nk, dq, dv, wsf, wsf.numel(), stream(),
          flops=2.0 * Bn * Nq * Nk * (dq + dv), tag="attn2_fwd")
     if recording(q, k, v):
         def bw():

@@ -166,6 +166,12 @@ int bg_bn_bwd_apply(const void* dy, const void* x, const float* mean, const floa
  * (saved for the backward).  tcgen05 kernels only (no fallback): BG_ERR_UNSUPPORTED elsewhere. */
 int bg_attn2_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk,
                  int dq, int dv, void* stream);
+/* the same with a workspace of bg_attn2_fwd_workspace_bytes(B) bytes (B floats): a pre-kernel writes the per-image bound
+ * max_i |q_i| * max_j |k_j| >= |q_i . k_j| there; images whose bound is <= 30 skip the row-maximum pass (softmax is invariant
+ * to the shift; nothing underflows for shifts that small) and use the bound as the shift -- o and lse are the same numbers. */
+size_t bg_attn2_fwd_workspace_bytes(int B);
+int bg_attn2_fwd_ws(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk,
+                    int dq, int dv, void* ws, size_t ws_bytes, void* stream);
 /* backward of bg_attn2_fwd: d_o [B,Nq,dv] -> dq [B,Nq,dq], dk [B,Nk,dq], dv [B,Nk,dv] (bf16);
  * delta [B,Nq] fp32 scratch (row-wise <d_o, o>).  Recomputes the probabilities from lse.
  * ws (bg_attn2_bwd_workspace_bytes, may be NULL): fp32 per-key-block partials of dQ -- with it the dK/dV kernel also

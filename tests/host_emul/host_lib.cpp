@@ -676,6 +676,11 @@ extern "C" int bg_attn2_fwd(const void* q_, const void* k_, const void* v_, void
   }
   return BG_OK;
 }
+extern "C" size_t bg_attn2_fwd_workspace_bytes(int B) { return (size_t)B * 4 + 16; }
+extern "C" int bg_attn2_fwd_ws(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Nq, int Nk, int dq, int dv, void*, size_t,
+                               void* st) {
+  return bg_attn2_fwd(q, k, v, o, lse, B, Nq, Nk, dq, dv, st);
+}
 extern "C" size_t bg_attn2_bwd_workspace_bytes(int, int, int, int) { return 16; }
 extern "C" int bg_attn2_bwd(const void* q_, const void* k_, const void* v_, const void* o_, const void* do_, const float* lse, float* delta, void* dq_,
                             void* dk_, void* dv_, int B, int Nq, int Nk, int dq, int dv, void*, size_t, void*) {

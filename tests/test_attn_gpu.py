@@ -32,6 +32,34 @@ def test_attn2_forward(B, Nq, Nk, dq, dv):
     assert_close(o.float().cpu().numpy(), ro.numpy(), 2e-2, "o")
 
 
+@pytest.mark.parametrize("scales", [(0.3, 0.3), (1.0, 1.0), (0.3, 1.5), (0.0, 0.3)], ids=["single-pass", "two-pass", "mixed-batch", "zero-q"])
+@pytest.mark.parametrize("B,Nq,Nk,dq,dv", [(2, 4096, 1024, 32, 96), (2, 4096, 1024, 16, 48), (2, 320, 80, 32, 64), (4, 256, 64, 16, 16)])
+def test_attn2_forward_with_score_bound(B, Nq, Nk, dq, dv, scales):
+    """bg_attn2_fwd_ws: a pre-kernel bounds |q_i . k_j| per image by max|q_i| max|k_j|; images whose bound is <= 30 skip the
+    row-maximum pass and shift by the bound instead (same o, same lse), the others take the two-pass path -- decided per image."""
+    from biggan_tensorflow_b200._lib import call, query
+    from biggan_tensorflow_b200.tensor import stream
+    rng = np.random.default_rng(7)
+    sc = torch.tensor([scales[i % 2] for i in range(B)], dtype=torch.float32).view(B, 1, 1)
+    q = (torch.from_numpy(rng.standard_normal((B, Nq, dq)).astype(np.float32)) * sc).cuda().bfloat16()
+    k = (torch.from_numpy(rng.standard_normal((B, Nk, dq)).astype(np.float32)) * sc.clamp_min(0.3)).cuda().bfloat16()
+    v = torch.from_numpy(rng.standard_normal((B, Nk, dv)).astype(np.float32)).cuda().bfloat16()
+    o = torch.full((B, Nq, dv), float("nan"), dtype=torch.bfloat16, device="cuda")
+    lse = torch.full((B, Nq), float("nan"), dtype=torch.float32, device="cuda")
+    nb = int(query("bg_attn2_fwd_workspace_bytes", B))
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    call("bg_attn2_fwd_ws", q, k, v, o, lse, B, Nq, Nk, dq, dv, ws, nb, stream())
+    torch.cuda.synchronize()
+    bound = ws[:4 * B].view(torch.float32).cpu().numpy()
+    qn, kn = q.float().norm(dim=-1).amax(dim=1).cpu().numpy(), k.float().norm(dim=-1).amax(dim=1).cpu().numpy()
+    assert np.all(bound >= qn * kn) and np.all(bound <= qn * kn * 1.01 + 2e-3)
+    if scales == (0.3, 1.5):
+        assert bound[0] <= 30.0 < bound[1]              # both paths in one launch
+    ro, rl = _ref(q.double().cpu(), k.double().cpu(), v.double().cpu())
+    assert_close(lse.cpu().numpy(), rl.numpy(), 1e-5, "lse")
+    assert_close(o.float().cpu().numpy(), ro.numpy(), 2e-2, "o")
+
+
 @pytest.mark.parametrize("fused_dq", [True, False], ids=["dq-in-dkdv", "two-kernels"])
 @pytest.mark.parametrize("B,Nq,Nk,dq,dv", [(2, 256, 64, 16, 16), (2, 1024, 256, 32, 96), (1, 4096, 1024, 32, 96),
                                            (2, 4096, 1024, 16, 48), (1, 64, 16, 16, 32), (2, 320, 80, 32, 64), (1, 512, 128, 64, 128)])

@@ -40,15 +40,21 @@ for name, dq, dv in (("g", 32, 96), ("d", 16, 48)):
     if args.which not in (name, "both"):
         continue
     B, Nq, Nk = args.B, 4096, 1024
-    q = torch.randn(B, Nq, dq, device=dev).mul_(0.5).bfloat16()
-    k = torch.randn(B, Nk, dq, device=dev).mul_(0.5).bfloat16()
+    q = torch.randn(B, Nq, dq, device=dev).mul_(0.3).bfloat16()
+    k = torch.randn(B, Nk, dq, device=dev).mul_(0.3).bfloat16()
     v = torch.randn(B, Nk, dv, device=dev).bfloat16()
     o = torch.empty(B, Nq, dv, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, Nq, device=dev, dtype=torch.float32)
     fwd = lambda: call("bg_attn2_fwd", q, k, v, o, lse, B, Nq, Nk, dq, dv, stream())
+    nbf = int(query("bg_attn2_fwd_workspace_bytes", B))
+    wsf = torch.empty(nbf, dtype=torch.uint8, device=dev)
+    fwd_ws = lambda: call("bg_attn2_fwd_ws", q, k, v, o, lse, B, Nq, Nk, dq, dv, wsf, nbf, stream())
     if args.op in ("fwd", "both"):
-        ms = timed(fwd)
-        print("attn2_fwd %s b%d dq%d dv%d: %.3f ms  %.1f TFLOP/s" % (name, B, dq, dv, ms, 2.0 * B * Nq * Nk * (dq + dv) / ms / 1e9), flush=True)
+        for label, f in (("two-pass", fwd), ("score-bound (single pass if bound <= 30)", fwd_ws), ("two-pass", fwd), ("score-bound", fwd_ws)):
+            ms = timed(f)
+            print("attn2_fwd %s b%d dq%d dv%d %s: %.3f ms  %.1f TFLOP/s" % (name, B, dq, dv, label, ms, 2.0 * B * Nq * Nk * (dq + dv) / ms / 1e9),
+                  flush=True)
+        print("  max bound %.2f" % float(wsf[:4 * B].view(torch.float32).max()))
     if args.op in ("bwd", "both"):
         fwd()
         do = torch.randn_like(o)
