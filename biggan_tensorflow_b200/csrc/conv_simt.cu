@@ -600,6 +600,55 @@ extern "C" int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w
   BG_DISPATCH_DTYPE(dtype, T, return launch_fwd_type<T>(g, (const T*)x, (const T*)w, bias, (const T*)residual, (T*)y, act, st, ws, ws_bytes));
 }
 
+// Small reflect-padded maps (3x3 / stride 1 / pad 1, H <= 4): the padded-domain dgrad computes (H+2)^2 / H^2 = 2.25x the pixels at 4x4.
+// The fold commutes with the per-pixel weight contraction, so it is applied to dy instead, once per tap:
+//   dyf[b, t*H + i, j, :] = sum over padded coordinates (py, px) that reflect onto (i, j) of dy[b, py - (ky-1), px - (kx-1), :]   (t = ky*3 + kx)
+// and dx = sum_t dyf_t W_t^T is a plain 9-"tap" GEMM over the UNPADDED domain (tap t reads rows t*H .. t*H+H-1 of the stacked tensor; bulk
+// stores, ReLU mask and gradient accumulation in the ordinary epilogue, no pad ring, no fold pass).  dyf costs 9x dy, which at 4x4 is small.
+__global__ void __launch_bounds__(256)
+reflect_dyfold_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dyf, int B, int H, int W, int C) {
+  const int CV = C / 8;
+  const long total = (long)B * 9 * H * W * CV;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV); long k = idx / CV;
+    const int j = (int)(k % W); k /= W;
+    const int i = (int)(k % H); k /= H;
+    const int t = (int)(k % 9); const int b = (int)(k / 9);
+    const int oy = t / 3 - 1, ox = t % 3 - 1;
+    int py[3], px[3], ny = 0, nx = 0;
+    py[ny++] = i;
+    if (i == 1) py[ny++] = -1;
+    if (i == H - 2) py[ny++] = H;
+    px[nx++] = j;
+    if (j == 1) px[nx++] = -1;
+    if (j == W - 2) px[nx++] = W;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int u = 0; u < ny; ++u) {
+      const int sy = py[u] - oy;
+      if (sy < 0 || sy >= H) continue;
+      for (int v = 0; v < nx; ++v) {
+        const int sx = px[v] - ox;
+        if (sx < 0 || sx >= W) continue;
+        float r[8];
+        Vec<bf16>::ld(dy, ((((long)b * H + sy) * W + sx) * C) + (long)cv * 8, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += r[e];
+      }
+    }
+    Vec<bf16>::st(dyf, ((((long)b * 9 * H + (long)t * H + i) * W + j) * C) + (long)cv * 8, acc);
+  }
+}
+static bool dgrad_dyfold(const bg_conv_desc* d, int dtype) {
+  static int mh = -1;                               // A/B knob: largest map side taking this path (0 = off)
+  if (mh < 0) { const char* e = getenv("BG_TC_DYFOLD_MAXH"); mh = e ? atoi(e) : 4; }
+  return dtype == BG_BF16 && !d->transposed && d->pad_mode == BG_PAD_REFLECT && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad_t == 1 &&
+         d->pad_b == 1 && d->pad_l == 1 && d->pad_r == 1 && d->Hi >= 2 && d->Wi >= 2 && d->Hi <= mh && d->Wi <= mh && d->Co % 8 == 0 &&
+         d->Ci % 16 == 0 && d->Co >= 16 && 9 * d->Hi < 32768 && bg_has_tensor_core_path();
+}
+static size_t dgrad_dyfold_bytes(const bg_conv_desc* d) { return align256((size_t)d->B * 9 * d->Ho * d->Wo * d->Co * 2 + 256); }
+
 static bool dgrad_padded(const bg_conv_desc* d) {
   return !d->transposed && d->pad_mode == BG_PAD_REFLECT && (d->pad_t | d->pad_b | d->pad_l | d->pad_r);
 }
@@ -613,6 +662,7 @@ extern "C" size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dty
   const bool geom_ok = bg_build_geom(d, BG_OP_DGRAD, &g) == BG_OK;
   // [padded-domain gradient (reflect convs)][tensor-core split-K partials (bf16) | SIMT split-K partials (fp32, unpadded)]
   size_t n = dgrad_padded(d) ? dgrad_padded_bytes(d, dtype) : 0;
+  if (dgrad_dyfold(d, dtype) && dgrad_dyfold_bytes(d) > n) n = dgrad_dyfold_bytes(d);     // (the two layouts share the front of the workspace)
   if (geom_ok && dtype == BG_BF16) n += bg_tc_fwd_splitk_bytes(g);
   if (geom_ok && dtype == BG_F32 && !dgrad_padded(d)) n += fwd_ksplit_bytes(g);
   return n;
@@ -643,6 +693,23 @@ extern "C" int bg_conv2d_dgrad(const bg_conv_desc* d, const void* dy, const void
     const void* wk = d->transposed ? w_t : w;     // dgrad contracts over Co: HWIO [tap][ci][co] is K-major natively
     if (wk) {
       int taken = 0;
+      if (dgrad_dyfold(d, dtype) && ws && ws_bytes >= dgrad_dyfold_bytes(d) && ((((uintptr_t)ws) | ((uintptr_t)dy)) & 15) == 0) {
+        const long tot = (long)d->B * 9 * d->Ho * d->Wo * (d->Co / 8);
+        reflect_dyfold_kernel<<<(int)min(bg_cdiv(tot, 256), (long)bg_num_sms() * 16), 256, 0, st>>>((const bf16*)dy, (bf16*)ws, d->B, d->Ho, d->Wo, d->Co);
+        BG_LAUNCH_CHECK();
+        BgGeom g2;
+        memset(&g2, 0, sizeof(g2));
+        g2.B = d->B; g2.Hi = 9 * d->Ho; g2.Wi = d->Wo; g2.Ci = d->Co;
+        g2.Ho = d->Hi; g2.Wo = d->Wi; g2.Co = d->Ci;
+        g2.ostep = 1; g2.istep = 1; g2.pad_mode = BG_PAD_ZERO; g2.nphase = 1;
+        g2.wtap = g.wtap; g2.wk = g.wk; g2.wn = g.wn;
+        g2.ph[0].oy0 = 0; g2.ph[0].ox0 = 0; g2.ph[0].Hp = d->Hi; g2.ph[0].Wp = d->Wi; g2.ph[0].ntaps = 9;
+        for (int t = 0; t < 9; ++t) { g2.ph[0].taps[t].dy = (short)(t * d->Ho); g2.ph[0].taps[t].dx = 0; g2.ph[0].taps[t].widx = t; }
+        BgTcFold mo = {0, 0, 0, 0, nullptr, relu_mask};
+        rc = bg_tc_fwd_launch(g2, ws, g2.Hi, g2.Wi, 0, 0, wk, nullptr, residual, dx, BG_ACT_NONE, nullptr, 0, relu_mask ? &mo : nullptr, st, &taken);
+        if (rc) return rc;
+        if (taken) return BG_OK;
+      }
       static int fold_env = -1;
       if (fold_env < 0) { const char* e = getenv("BG_TC_FOLD"); fold_env = e ? atoi(e) : 1; }
       // reflect-padded conv: interior straight into dx (+ residual), pad ring into the padded buffer, band fold afterwards

@@ -69,6 +69,9 @@ struct TcFwdParams {
   CUtensorMap omap[4];       // per phase: the output sampled with step `ostep` from (oy0, ox0); box (16, bw, bh, bb), no swizzle
   int o_di[4], o_dj[4];      // fold mode: omap covers the UNPADDED tensor from the phase's first interior row / column; tile row i0 is
                              //   its row i0 - o_di (tiles that are interior pixels only take the bulk-store path, the others store directly)
+  int phase_minor;           // 4-phase (strided) launches: the phase is the fastest index after the n-tile, so the four interleaved
+                             //   sub-pixel phases of one output region run at the same time on neighbouring SMs and their partial-line
+                             //   writes (and residual / mask reads) meet in L2 instead of visiting DRAM four times, far apart
   int nwork;                 // work items x ksplit (loop bound of the persistent roles, kept in the parameter block)
   int aux_batch;             // BN <= 96: all residual / mask vectors of a half-tile requested up front (A/B knob BG_TC_AUX_BATCH)
   FastDiv fd_S, fd_ntn, fd_tpp, fd_tw, fd_th;   // per-tile index decode without runtime divisions (ksplit, n-tiles, items per phase, tw, th)
@@ -83,7 +86,8 @@ __device__ __forceinline__ void tc_tile_origin(const TcFwdParams& p, int t, int&
 __device__ __forceinline__ void tc_item_decode(const TcFwdParams& p, int wi, int ntn, int tpp_items, int& split, int& nt, int& phase, int& ti) {
   const int item = fast_div(wi, p.fd_S); split = wi - item * p.ksplit;
   const int q = fast_div(item, p.fd_ntn); nt = item - q * ntn;
-  phase = fast_div(q, p.fd_tpp); ti = q - phase * tpp_items;
+  if (p.phase_minor) { ti = q >> 2; phase = (q + ti) & 3; }           // nphase == 4; rotated so that a persistent CTA (stride = grid size) meets every phase
+  else { phase = fast_div(q, p.fd_tpp); ti = q - phase * tpp_items; }
 }
 
 // Epilogue warps (8): drain the double-buffered TMEM accumulator of every tile this CTA owns:
@@ -861,12 +865,12 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   const long ntiles = bg_cdiv((long)P.tw * P.th * P.tb, (long)P.mt) * g.nphase * (g.Co / BN);      // work items
   const long out_numel = (long)g.B * g.Ho * g.Wo * g.Co;
   if (mask_only) {
-    if (pl.ksplit > 1 || (((uintptr_t)mask_only) & 15)) return BG_OK;     // the split-K reduce pass has no mask: not taken
+    if (((uintptr_t)mask_only) & 15) return BG_OK;                         // (split-K is never combined with the mask: its reduce pass has none)
     P.mask = (const bf16*)mask_only;
   }
   if (fold) { P.fold = 1; P.f_pt = fold->pt; P.f_pl = fold->pl; P.f_Hi = fold->Hi; P.f_Wi = fold->Wi; P.ring = (bf16*)fold->ring; P.mask = (const bf16*)fold->mask; }
   P.ksplit = 1;
-  if (pl.ksplit > 1 && !fold && !box_override && sk_ws && sk_bytes >= (size_t)pl.ksplit * out_numel * sizeof(float) &&
+  if (pl.ksplit > 1 && !fold && !mask_only && !box_override && sk_ws && sk_bytes >= (size_t)pl.ksplit * out_numel * sizeof(float) &&
       (((uintptr_t)sk_ws) & 15) == 0) {
     P.ksplit = pl.ksplit; P.part = (float*)sk_ws; P.part_stride = out_numel;
   }
@@ -878,6 +882,10 @@ int bg_tc_fwd_launch(const BgGeom& g, const void* in, int in_H, int in_W, int sh
   }
   P.fd_S = make_fastdiv(P.ksplit); P.fd_ntn = make_fastdiv(g.Co / BN); P.fd_tw = make_fastdiv(P.tw); P.fd_th = make_fastdiv(P.th);
   P.fd_tpp = make_fastdiv((int)bg_cdiv((long)P.tw * P.th * P.tb, (long)P.mt));
+  {
+    const char* e = getenv("BG_TC_PHASE_MINOR");       // A/B knob, read per call
+    P.phase_minor = (g.nphase == 4 && (e ? atoi(e) : 1)) ? 1 : 0;
+  }
   P.nwork = (int)(ntiles * P.ksplit);
   dim3 grid((unsigned)min(ntiles * P.ksplit, (long)bg_num_sms()));
   // halo mode: stride-1 layer tiled in full 128-pixel row segments -> taps differing only in dx share one activation box

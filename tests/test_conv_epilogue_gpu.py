@@ -1,7 +1,8 @@
 """bg_conv2d_dgrad / bg_conv2d_fwd through the C ABI at shapes whose tiles exercise every epilogue path of the tcgen05 forward-type
 kernel (csrc/conv_tc.cu): fold mode (reflect-padded dgrad, ops.py:65-84) with tiles made of interior pixels only (bulk tensor
 stores), mixed tiles (direct stores + pad ring), fused gradient accumulation and the ReLU mask of the conv's input, all residual /
-mask vectors of a half-tile requested up front (BN <= 96) or in rolling groups (BN > 96), the mask on an unpadded 1x1 dgrad.
+mask vectors of a half-tile requested up front (BN <= 96) or in rolling groups (BN > 96), the mask on an unpadded 1x1 dgrad, and the
+per-tap folded dy path of the small maps (H <= 4).
 Checker: torch float32 autograd of the same convolution on the same bf16-rounded operands (test infrastructure only)."""
 import numpy as np
 import pytest
@@ -36,6 +37,10 @@ DGRAD_CASES = [
     (32, 8, 192, 192, 3, 1, True),      # BN = 192: rolling residual groups, mask inline
     (4, 64, 96, 32, 1, 1, False),       # unpadded 1x1: mask in the plain epilogue (tap-stacked RGB output conv)
     (3, 33, 48, 80, 3, 1, True),        # ragged: odd size, BN = 48
+    (64, 4, 256, 256, 3, 1, True),      # 4x4 map: dy folded per tap (reflect_dyfold_kernel), 9-tap GEMM on the unpadded domain
+    (24, 4, 512, 768, 3, 1, True),      # ... three n-tiles of 256, batch not a multiple of the 8-image box
+    (7, 3, 64, 96, 3, 1, True),         # 3x3 map: pixel 1 is the mirror image of both pad rows
+    (5, 2, 32, 64, 3, 1, True),         # 2x2 map
 ]
 
 

@@ -28,6 +28,7 @@ SHORT = [  # layers with a short main loop (epilogue / ingest bound)
 ]
 DEEP = [
     ("dgrad", 512, 4, 1536, 1536, 3, 1, 0, "reflect", 0, 1),
+    ("dgrad", 256, 4, 1536, 1536, 3, 1, 0, "reflect", 1, 1),
     ("dgrad", 512, 8, 768, 768, 3, 1, 0, "reflect", 0, 1),
     ("fwd", 256, 8, 1536, 1536, 3, 1, 1, "zero", 0, 0),
     ("fwd", 256, 16, 768, 384, 4, 2, 1, "zero", 0, 0),
