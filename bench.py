@@ -291,7 +291,7 @@ def main():
     peak = peaks["bf16_tflops_sustained"] if dtype == torch.bfloat16 else 75.0
     step_flops = {0: 0.87e9, 1: 212.7e9, 2: 212.7e9, 3: 714.0e9, 4: 603.6e9}[args.config] * B
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r3_conv_traffic.json")
     if os.path.exists(tp) and args.config == 1 and dtype == torch.bfloat16 and world == 1 and not args.batch:
         t = json.load(open(tp))      # dram__bytes_read.sum + dram__bytes_write.sum of the same kernels, per launch, one ncu capture
         traffic, traffic_src = t["dram_bytes_per_launch"], "%s (ncu, %d launches of one iteration)" % (t["source"], t["launches_per_step"])
