@@ -80,6 +80,37 @@ small_n_fwd_kernel(const __grid_constant__ BgGeom g, const T* __restrict__ in, c
   }
 }
 
+// ---- N <= 4 on a 1x1 map (fully_connected to <= 4 units: D_logit, BigGAN.py:687): one WARP per sample -------------------
+// The thread-per-pixel kernel above put a whole 1536-long dot product into one thread with 6 KB-strided loads: 2 CTAs, 150 us
+// for 3 MB (ncu launch list).  Here the lanes stride over K (coalesced), then a butterfly sum (fixed order: deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+small_n_fc_kernel(const __grid_constant__ BgGeom g, const T* __restrict__ in, const T* __restrict__ w, const float* __restrict__ bias,
+                  const T* residual, T* out, int act) {
+  const int row = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= g.B) return;                          // warp-uniform
+  const long w0 = (long)g.ph[0].taps[0].widx * g.wtap;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < g.Ci; k += 32) {
+    const float xv = bg_ld(in, (long)row * g.Ci + k);
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (n < g.Co) acc[n] = fmaf(xv, bg_ld(w, w0 + (long)k * g.wk + (long)n * g.wn), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+  if (lane == 0) {
+    const long obase = (long)row * g.Co;
+    for (int n = 0; n < g.Co; ++n) {
+      float v = acc[n];
+      if (bias) v += bias[n];
+      if (residual) v += bg_ld(residual, obase + n);
+      bg_st(out, obase + n, small_act(v, act));
+    }
+  }
+}
+
 // ---- K = g.Ci <= 4: one thread per (output pixel, 8 output channels) ------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -188,7 +219,12 @@ static int small_fwd_launch(const BgGeom& g, const T* in, const T* w, const floa
     maxtaps = max(maxtaps, g.ph[p].ntaps);
     maxM = max(maxM, (long)g.B * g.ph[p].Hp * g.ph[p].Wp);
   }
-  if (g.Co <= 4 && (long)maxtaps * g.Ci * 4 <= SMALL_MAX_W) {
+  if (g.Co <= 4 && g.nphase == 1 && g.Hi == 1 && g.Wi == 1 && g.Ho == 1 && g.Wo == 1 && g.ph[0].ntaps == 1 && g.ph[0].taps[0].dy == 0 &&
+      g.ph[0].taps[0].dx == 0 && g.Ci >= 64) {
+    small_n_fc_kernel<T><<<(int)bg_cdiv((long)g.B * 32, 256), 256, 0, st>>>(g, in, w, bias, residual, out, act);
+    BG_LAUNCH_CHECK();
+    *taken = 1;
+  } else if (g.Co <= 4 && (long)maxtaps * g.Ci * 4 <= SMALL_MAX_W) {
     const int tiles = (int)bg_cdiv(maxM, 256);
     small_n_fwd_kernel<T><<<tiles * g.nphase, 256, (size_t)maxtaps * g.Ci * 4 * sizeof(float), st>>>(g, in, w, bias, residual, out, act, tiles);
     BG_LAUNCH_CHECK();

@@ -220,7 +220,7 @@ def test_deconv(case, dtype):
 
 
 @pytest.mark.parametrize("sn", [True, False])
-@pytest.mark.parametrize("B,K,units", [(6, 52, 40), (6, 52, 200), (256, 148, 1536), (250, 300, 900), (3, 148, 96)])
+@pytest.mark.parametrize("B,K,units", [(6, 52, 40), (6, 52, 200), (256, 148, 1536), (250, 300, 900), (3, 148, 96), (37, 1536, 1), (5, 100, 3)])
 def test_fully_connected(B, K, units, sn):
     """ops.py:148-175 (SN path and tf.layers.dense path); the two large cases take the dedicated skinny-GEMM kernel
     (fc.cu): ragged row / column blocks, contraction longer than one shared-memory chunk."""
