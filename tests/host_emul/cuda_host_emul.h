@@ -207,6 +207,18 @@ inline float bg_block_sum(float v, float* sh) {
   __syncthreads();
   return sh[32];
 }
+// 4- / 8-wide vector access of bg_common.cuh (element loops here)
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  static void ld(const float* p, long i, float* v) { for (int e = 0; e < 4; ++e) v[e] = p[i + e]; }
+  static void st(float* p, long i, const float* v) { for (int e = 0; e < 4; ++e) p[i + e] = v[e]; }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  static void ld(const bf16* p, long i, float* v) { for (int e = 0; e < 8; ++e) v[e] = bg_emul_bf16_to_float(p[i + e]); }
+  static void st(bf16* p, long i, const float* v) { for (int e = 0; e < 8; ++e) p[i + e] = bg_emul_float_to_bf16(v[e]); }
+};
 #define BG_DISPATCH_DTYPE(dtype, T, ...)                                        \
   do {                                                                          \
     if ((dtype) == BG_F32) { typedef float T; __VA_ARGS__; }                    \
