@@ -103,7 +103,8 @@ int bg_conv2d_fwd(const bg_conv_desc* d, const void* x, const void* w, const voi
                   void* ws, size_t ws_bytes, int force_simt, void* stream);
 /* dx = conv_dgrad(dy) (+ residual).  For pad_mode REFLECT with padding the caller gets the gradient
  * w.r.t. the *unpadded* x (the reflect-pad adjoint is folded inside; ws holds the padded gradient).
- * relu_mask (may be NULL; reflect-padded convs only; same shape and dtype as dx): dx = residual + (relu_mask > 0 ?
+ * relu_mask (may be NULL; reflect-padded convs, or UNPADDED plain convs on the bf16 tensor-core path -- anything else returns
+ * BG_ERR_UNSUPPORTED; same shape and dtype as dx): dx = residual + (relu_mask > 0 ?
  * conv_dgrad(dy) : 0) -- the backward of a ReLU sitting on the conv's input (ops.py:297-301: act -> conv in the
  * residual blocks) is applied where the gradient is produced instead of in a pass of its own. */
 size_t bg_conv2d_dgrad_workspace_bytes(const bg_conv_desc* d, int dtype);
